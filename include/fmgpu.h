@@ -1,0 +1,131 @@
+/* fmgpu.h — C ABI of the B200-native batched query engine for index4j FM-indexes.
+ *
+ * The reference (dynatrace-oss/index4j) has no FFI seam: the drop-in boundary is the public method
+ * set of com.dynatrace.fm.FmIndex plus its serialized form.  Every entry point
+ * below names the reference method it replaces; paths are relative to
+ *   indices/src/main/java/com/dynatrace/   (FM = fm/FmIndex.java, SER = serialization/Serialization.java)
+ * A Java host binds these with Panama FFM (INTEGRATION.md shows the binding).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; caller owns every buffer it passes; the library owns device memory.
+ *   - return 0 = OK; < 0 = call-level failure (bad argument, malformed stream, CUDA error); the
+ *     message is in fmgpu_last_error() (thread-local).
+ *   - per-query Java exceptions are reported in status arrays with the FMGPU_ST_* codes, which map
+ *     1:1 onto the reference's exception messages so a Java shim can re-throw the identical exception.
+ *   - "chars" are UTF-16 code units exactly as in a Java char[]; pattern i is
+ *     chars[pat_off[i] .. pat_off[i+1]).
+ *   - *_device variants take DEVICE pointers and a cudaStream_t (as void*), enqueue asynchronously and
+ *     never synchronize; the host-pointer variants copy H2D, run, copy D2H and synchronize.
+ *   - there is no CPU fallback: without a CUDA device every call fails with FMGPU_ERR_CUDA.
+ */
+#ifndef FMGPU_H
+#define FMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FMGPU_OK 0
+#define FMGPU_ERR_ARG (-1)     /* null handle / bad argument */
+#define FMGPU_ERR_FORMAT (-2)  /* malformed stream, incl. "Incompatible serial versions! ..." (SER:46-56) */
+#define FMGPU_ERR_CUDA (-3)    /* CUDA runtime failure (no device, out of memory, launch error) */
+#define FMGPU_ERR_CAPACITY (-4) /* caller's output buffer too small (locate positions_cap) */
+#define FMGPU_ERR_UNSUPPORTED (-5)
+
+/* Per-query status = the Java exception the reference would have thrown. */
+#define FMGPU_ST_OK 0
+#define FMGPU_ST_NOT_ENABLED 1    /* RuntimeException("Text recovery not enabled at build time")   FM:566,611 */
+#define FMGPU_ST_POS_NEGATIVE 2   /* RuntimeException("Requested position less than 0")            FM:570,615 */
+#define FMGPU_ST_STOP_TOO_LONG 3  /* RuntimeException("Stop position longer than index string")    FM:574 */
+#define FMGPU_ST_POS_TOO_LONG 4   /* RuntimeException("Requested position longer than index string") FM:619 */
+#define FMGPU_ST_DST_TOO_SMALL 5  /* RuntimeException("Supplied destination is not large enough")  FM:591 */
+#define FMGPU_ST_DST_ZERO 6       /* IllegalArgumentException("Supplied destination for extraction has size zero") FM:623 */
+#define FMGPU_ST_NO_BOUNDARY 7    /* IllegalArgumentException("Boundary does not exist")           FM:659,792,849 */
+#define FMGPU_ST_DOES_NOT_FIT 8   /* RuntimeException("Extraction does not fit in the supplied destination. Currently extracted: N") FM:733,817,894; N in len_out */
+#define FMGPU_ST_INDEX_OOB 9      /* ArrayIndexOutOfBoundsException (empty pattern FM:456; rank(size,.) on a superblock boundary, wavelet/WaveletFixedBlockBoosting.java:1022-1026) */
+
+#define FMGPU_MODE_BOTH 0  /* FmIndex.extractUntilBoundary       FM:640 */
+#define FMGPU_MODE_LEFT 1  /* FmIndex.extractUntilBoundaryLeft   FM:772 */
+#define FMGPU_MODE_RIGHT 2 /* FmIndex.extractUntilBoundaryRight  FM:844 */
+
+typedef struct fmgpu_index fmgpu_index;
+
+typedef struct fmgpu_opts {
+    int32_t device;        /* CUDA device ordinal; -1 = current device */
+    int32_t host_threads;  /* threads used to re-lay the index out at load; 0 = all cores */
+    uint64_t reserved[3];
+} fmgpu_opts;
+
+const char* fmgpu_last_error(void);
+const char* fmgpu_version(void);
+
+/* Replaces Serialization.readFromByteArray(FmIndex::read, bytes) (SER:89-100, FM:983-1025).
+ * Accepts the ObjectOutputStream framing (AC ED 00 05 + block-data records) or the bare
+ * DataOutput primitives.  Parses the stream, re-lays the structures out into the device format
+ *  and uploads them once.  opts may be NULL. */
+int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out);
+void fmgpu_index_free(fmgpu_index* idx);
+
+int32_t fmgpu_input_length(const fmgpu_index* idx);     /* FmIndex.getInputLength()    FM:929 (= n+1) */
+int32_t fmgpu_alphabet_length(const fmgpu_index* idx);  /* FmIndex.getAlphabetLength() FM:939 */
+int32_t fmgpu_sample_rate(const fmgpu_index* idx);
+int32_t fmgpu_extract_enabled(const fmgpu_index* idx);
+int32_t fmgpu_device(const fmgpu_index* idx);
+uint64_t fmgpu_device_bytes(const fmgpu_index* idx);    /* bytes of HBM held by the index */
+/* component sizes (bytes): [0] cells [1] level sectors [2] node records [3] block descriptors
+ * [4] path overflow [5] sampled-row groups+offsets [6] SA samples [7] ISA samples */
+void fmgpu_layout_bytes(const fmgpu_index* idx, uint64_t out8[8]);
+
+/* FmIndex.count(char[] p, int off, int len)  FM:455-474 — one result per pattern.
+ * status_out may be NULL. */
+int fmgpu_count_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat,
+                      int32_t* counts_out, int32_t* status_out);
+int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars,
+                             uint32_t n_pat, int32_t* d_counts_out, int32_t* d_status_out, void* cuda_stream);
+
+/* FmIndex.locate(char[] p, int off, int len, int[] out, int max)  FM:504-552.
+ * max_hits <= 0 means unlimited (FM:544).  Hits of pattern i are written to
+ * positions_out[hit_off_out[i] .. hit_off_out[i+1]) in SA-row order (the order Java fills its
+ * array).  Two-phase sizing: with positions_out == NULL only n_hits_out / hit_off_out are produced.
+ * If positions_cap < total hits the call returns FMGPU_ERR_CAPACITY (hit_off_out is still valid). */
+int fmgpu_locate_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t max_hits,
+                       int32_t* n_hits_out, uint64_t* hit_off_out, int32_t* positions_out, uint64_t positions_cap,
+                       int32_t* status_out);
+/* Device form: d_positions_out has room for positions_cap entries; *total_hits_out (host) receives
+ * the number of hits (this call synchronizes the stream once to learn it). */
+int fmgpu_locate_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars,
+                              uint32_t n_pat, int32_t max_hits, int32_t* d_n_hits_out, uint64_t* d_hit_off_out,
+                              int32_t* d_positions_out, uint64_t positions_cap, int32_t* d_status_out,
+                              uint64_t* total_hits_out, void* cuda_stream);
+
+/* FmIndex.extract(int start, int stop, char[] dst, int off)  FM:564-608 with dst = the slot
+ * arena[arena_off[i] .. arena_off[i+1]) and off = 0.  len_out[i] = stop-start on success. */
+int fmgpu_extract_batch(fmgpu_index* idx, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena,
+                        const uint64_t* arena_off, int32_t* len_out, int32_t* status_out);
+int fmgpu_extract_batch_device(fmgpu_index* idx, const int32_t* d_start, const int32_t* d_stop, uint32_t n, uint16_t* d_arena,
+                               const uint64_t* d_arena_off, int32_t* d_len_out, int32_t* d_status_out, void* cuda_stream);
+
+/* FmIndex.extractUntilBoundary / ...Left / ...Right (FM:640-922) with dst = new char[dst_len],
+ * off = 0: slot i is arena[i*dst_len .. (i+1)*dst_len).  len_out[i] = returned length (or N of the
+ * "does not fit" message when status is FMGPU_ST_DOES_NOT_FIT).  Only arena[i*dst_len, +len) is
+ * defined, like the Java array beyond the returned length. */
+int fmgpu_extract_until_boundary_batch(fmgpu_index* idx, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len,
+                                       int32_t mode, uint16_t* arena, int32_t* len_out, int32_t* status_out);
+int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d_from, uint32_t n, uint16_t boundary,
+                                              int32_t dst_len, int32_t mode, uint16_t* d_arena, int32_t* d_len_out,
+                                              int32_t* d_status_out, void* cuda_stream);
+
+/* Work counters of the most recent batch call on this index (device-side counted, read back here):
+ * [0] rank queries that touched memory  [1] wavelet levels walked by rank queries
+ * [2] LF steps (inverseSelect walks)     [3] wavelet levels walked by LF steps
+ * [4] sampled-row bit tests              [5] kernels launched by the call
+ * Used by bench.py for the roofline's algorithmic-bytes figure. */
+int fmgpu_last_stats(fmgpu_index* idx, uint64_t out6[6]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FMGPU_H */

@@ -1,0 +1,591 @@
+// Host-side re-layout: parsed Java structures (jstream.hpp) -> the sector-record device format
+// (layout.h).  Runs once per fmgpu_index_load_serialized.  The information content is unchanged:
+// every record is a pre-evaluation of the position-independent part of what the reference's
+// WaveletFixedBlockBoosting.rank / inverseSelect and RrrVector.rankOnes / access compute per call
+// (wavelet/WaveletFixedBlockBoosting.java:1010-1537, bitsequence/RrrVector.java:314-396).
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "jstream.hpp"
+#include "layout.h"
+
+namespace fmgpu_host {
+
+using fmgpu::Rec32;
+
+// (class, offset) -> 15-bit block, generated from the ordering rule of the reference's literal
+// tables (RrrVector.java:8692-8698, :8705-16899): classes by popcount; inside a class by
+// descending value of the block read LSB-first.
+struct RrrTables {
+    uint16_t inverse[32768];
+    uint16_t class_base[16];
+    uint8_t bits_needed[16];  // RrrVector.java:111-129
+    RrrTables() {
+        int cnt[16] = {0};
+        for (int v = 0; v < 32768; ++v) cnt[__builtin_popcount(v)]++;
+        int acc = 0;
+        for (int k = 0; k < 16; ++k) {
+            class_base[k] = (uint16_t)acc;
+            int b = 0;
+            while ((1 << b) <= cnt[k]) ++b;
+            bits_needed[k] = (uint8_t)b;
+            acc += cnt[k];
+        }
+        int fill[16] = {0};
+        for (int r = 32767; r >= 0; --r) {
+            int v = 0;
+            for (int b = 0; b < 15; ++b)
+                if (r & (1 << b)) v |= 1 << (14 - b);
+            const int k = __builtin_popcount(v);
+            inverse[class_base[k] + fill[k]++] = (uint16_t)v;
+        }
+    }
+};
+inline const RrrTables& rrr_tables() {
+    static const RrrTables t;
+    return t;
+}
+
+// Whole RRR vector -> plain LSB-first bits (one slack word at the end).
+inline void rrr_decode_all(const RrrStream& r, std::vector<uint64_t>& bits) {
+    const RrrTables& T = rrr_tables();
+    const int64_t len = r.length;
+    const int64_t nblocks = (len + 14) / 15;
+    bits.assign((size_t)((len + 63) / 64) + 2, 0);
+    uint64_t bitpos = 0;
+    const uint64_t off_bits_avail = (uint64_t)(r.offsets.size() - 1) * 64;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        const int cls = (int)r.classes.get(b);
+        const int nb = T.bits_needed[cls];
+        if (bitpos + (uint64_t)nb > off_bits_avail) throw FormatError("RrrVector offset stream too short");
+        const size_t w = (size_t)(bitpos >> 6);
+        const int sh = (int)(bitpos & 63);
+        uint64_t off = r.offsets[w] >> sh;
+        if (sh + nb > 64) off |= r.offsets[w + 1] << (64 - sh);
+        off &= (1ULL << nb) - 1;
+        const uint32_t idx = (uint32_t)T.class_base[cls] + (uint32_t)off;
+        const uint64_t v = idx < 32768 ? T.inverse[idx] : 0;
+        const uint64_t p = (uint64_t)b * 15;
+        bits[p >> 6] |= v << (p & 63);
+        if ((p & 63) + 15 > 64) bits[(p >> 6) + 1] |= v >> (64 - (p & 63));
+        bitpos += (uint64_t)nb;
+    }
+}
+
+inline uint32_t bits_get(const std::vector<uint64_t>& bits, uint64_t pos, int n) {  // n <= 32
+    const size_t w = (size_t)(pos >> 6);
+    const int sh = (int)(pos & 63);
+    uint64_t v = bits[w] >> sh;
+    if (sh + n > 64) v |= bits[w + 1] << (64 - sh);
+    return (uint32_t)(n >= 32 ? (v & 0xffffffffULL) : (v & ((1ULL << n) - 1)));
+}
+
+struct FlatIndex {
+    fmgpu::DevIndex meta{};  // pointers unset
+    std::vector<uint32_t> C;
+    std::vector<uint16_t> char2code, code2char;
+    std::vector<fmgpu::SbDesc> sb;
+    std::vector<Rec32> cells, sectors, ovf, blocks, nodes, sgroups, sa, isa;
+    std::vector<uint32_t> soffsets;
+    int32_t alphabet_length = 0;
+};
+
+// Explicit shape of one block's Huffman-shaped wavelet tree, rebuilt from the variable-size
+// block header (layout written by encodeBlock, WaveletFixedBlockBoosting.java:742-809).
+struct BlockTree {
+    struct Node {
+        uint32_t start, size;  // bit range in the superblock's level bitvector
+        int32_t child[2];      // >= 0: internal node id; < 0: -(leaf local index + 1)
+        uint32_t sector;       // first sector (global index), set by the caller
+    };
+    std::vector<Node> nodes;  // BFS order, node 0 = root
+    struct Leaf {
+        int32_t parent;
+        uint8_t bit, len;
+        uint32_t code;
+    };
+    std::vector<Leaf> leaves;     // by block-local symbol index (canonical code order)
+    std::vector<uint16_t> sym;    // header symbol per leaf
+    std::vector<uint32_t> brank;  // rankAtBlockBoundary per leaf
+    int h = 0;
+    uint32_t n_sectors = 0, n_ovf_chunks = 0;
+};
+
+struct VarReader {
+    const std::vector<uint8_t>& v;
+    bool ok = true;
+    explicit VarReader(const std::vector<uint8_t>& v_) : v(v_) {}
+    uint32_t u16(int64_t p) {
+        if (p < 0 || (size_t)p + 2 > v.size()) {
+            ok = false;
+            return 0;
+        }
+        return (uint32_t)v[(size_t)p] | ((uint32_t)v[(size_t)p + 1] << 8);
+    }
+    uint32_t u24(int64_t p) {
+        if (p < 0 || (size_t)p + 3 > v.size()) {
+            ok = false;
+            return 0;
+        }
+        return (uint32_t)v[(size_t)p] | ((uint32_t)v[(size_t)p + 1] << 8) | ((uint32_t)v[(size_t)p + 2] << 16);
+    }
+};
+
+inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_block_size, BlockTree& T) {
+    const BlockHdr& H = S.blocks[b];
+    const int h = H.tree_height;
+    const int sig = (int)H.sigma_m1 + 1;
+    T.h = h;
+    T.nodes.clear();
+    T.leaves.clear();
+    T.sym.clear();
+    T.brank.clear();
+    T.n_sectors = 0;
+    T.n_ovf_chunks = 0;
+    if (sig < 1 || h < 0) throw FormatError("block header out of range");
+    VarReader R(S.var);
+    const int64_t var_off = H.var_off;
+    const int64_t ptr32 = var_off + (h > 0 ? (int64_t)(h - 1) * 4 : 0);
+    T.sym.resize((size_t)sig);
+    T.brank.resize((size_t)sig);
+    for (int i = 0; i < sig; ++i) {
+        T.sym[(size_t)i] = (uint16_t)R.u16(ptr32 + 5 * (int64_t)i);
+        T.brank[(size_t)i] = R.u24(ptr32 + 5 * (int64_t)i + 2);
+    }
+    if (!R.ok) throw FormatError("variable block header truncated");
+    if (h == 0) return;  // run block: no tree
+    if (sig < 2) throw FormatError("tree block with a single symbol");
+    T.leaves.resize((size_t)sig);
+    int64_t third = ptr32 + 5 * (int64_t)sig;
+    std::vector<uint32_t> level;  // node ids of the current depth, left to right
+    T.nodes.push_back({(uint32_t)H.bv_offset, cur_block_size, {0, 0}, 0});
+    level.push_back(0);
+    uint32_t level_start = (uint32_t)H.bv_offset;
+    int64_t leaves_before = 0;
+    std::vector<uint32_t> next;
+    for (int d = 0; d < h; ++d) {
+        const size_t n_int = level.size();
+        if (n_int == 0) throw FormatError("wavelet tree level without internal nodes");
+        uint32_t depth_total = 0;
+        for (uint32_t id : level) depth_total += T.nodes[id].size;
+        const uint32_t next_start = level_start + depth_total;
+        const int64_t nleaf_next = (d + 1 < h) ? (int64_t)R.u16(var_off + 4 * (int64_t)d) : (int64_t)(2 * n_int);
+        if (nleaf_next > (int64_t)(2 * n_int)) throw FormatError("wavelet tree leaf count exceeds level width");
+        next.clear();
+        uint32_t run = 0, prev_cum = 0;
+        for (size_t j = 0; j < n_int; ++j) {
+            const uint32_t id = level[j];
+            const uint32_t cum = R.u16(third + 2 * (int64_t)j);
+            const uint32_t ones = cum - prev_cum;
+            prev_cum = cum;
+            const uint32_t size = T.nodes[id].size;
+            if (ones > size) throw FormatError("wavelet node has more ones than bits");
+            for (int bit = 0; bit < 2; ++bit) {
+                const int64_t slot = 2 * (int64_t)j + bit;
+                const uint32_t csize = bit ? ones : size - ones;
+                if (slot < nleaf_next) {
+                    const int64_t li = leaves_before + slot;
+                    if (li >= sig) throw FormatError("wavelet tree has more leaves than symbols");
+                    T.nodes[id].child[bit] = (int32_t)(-(li + 1));
+                    T.leaves[(size_t)li].parent = (int32_t)id;
+                    T.leaves[(size_t)li].bit = (uint8_t)bit;
+                } else {
+                    const uint32_t nid = (uint32_t)T.nodes.size();
+                    T.nodes[id].child[bit] = (int32_t)nid;
+                    T.nodes.push_back({next_start + run, csize, {0, 0}, 0});
+                    run += csize;
+                    next.push_back(nid);
+                }
+            }
+        }
+        if (!R.ok) throw FormatError("variable block header truncated");
+        third += 2 * (int64_t)n_int;
+        leaves_before += nleaf_next;
+        level.swap(next);
+        level_start = next_start;
+    }
+    if (leaves_before != sig) throw FormatError("wavelet tree leaf count differs from block alphabet");
+    // parents of internal nodes, for path reconstruction
+    std::vector<int32_t> parent(T.nodes.size(), -1);
+    std::vector<uint8_t> pbit(T.nodes.size(), 0);
+    for (size_t id = 0; id < T.nodes.size(); ++id)
+        for (int bit = 0; bit < 2; ++bit)
+            if (T.nodes[id].child[bit] >= 0 && (size_t)T.nodes[id].child[bit] != 0) {
+                parent[(size_t)T.nodes[id].child[bit]] = (int32_t)id;
+                pbit[(size_t)T.nodes[id].child[bit]] = (uint8_t)bit;
+            }
+    for (int i = 0; i < sig; ++i) {
+        BlockTree::Leaf& L = T.leaves[(size_t)i];
+        uint32_t code = L.bit;
+        int len = 1;
+        int32_t id = L.parent;
+        while (parent[(size_t)id] >= 0) {
+            code |= (uint32_t)pbit[(size_t)id] << len;
+            ++len;
+            id = parent[(size_t)id];
+        }
+        if (len > 32) throw FormatError("Huffman code longer than 32 bits");
+        L.len = (uint8_t)len;
+        L.code = code;  // bit (len-1) = root decision
+        if (len > (int)fmgpu::CELL_INLINE_LEVELS) T.n_ovf_chunks += (uint32_t)((len - 4 + 7) / 8);
+    }
+    for (auto& n : T.nodes) T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
+}
+
+struct SbPlan {
+    uint32_t first_block = 0, rows = 0;
+    uint64_t sector_base = 0, node_base = 0, ovf_base = 0;
+    uint64_t n_sectors = 0, n_nodes = 0, n_ovf = 0;
+};
+
+inline uint32_t sb_block_size(const WfbbStream& W, size_t sb, size_t b) {
+    const int64_t bs = 1LL << W.sbs[sb].block_size_log;
+    const int64_t beg = ((int64_t)sb << 20) + (int64_t)b * bs;
+    return (uint32_t)std::min<int64_t>(bs, W.size - beg);
+}
+
+template <typename F>
+inline void parallel_sbs(size_t n, int threads, F&& f) {
+    std::atomic<size_t> next(0);
+    std::atomic<bool> failed(false);
+    std::string err;
+    auto worker = [&]() {
+        try {
+            for (;;) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n || failed.load()) break;
+                f(i);
+            }
+        } catch (const std::exception& e) {
+            if (!failed.exchange(true)) err = e.what();
+        }
+    };
+    if (threads < 1) threads = 1;
+    if ((size_t)threads > n) threads = (int)std::max<size_t>(1, n);
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& th : pool) th.join();
+    if (failed.load()) throw FormatError(err);
+}
+
+inline void put_cell(Rec32& c, uint32_t kind, uint32_t value) {
+    memset(&c, 0, sizeof c);
+    c.w[0] = value;
+    c.w[2] = kind << 8;
+}
+
+inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, FlatIndex& F) {
+    const SuperBlockHdr& S = W.sbs[sb];
+    const int32_t sigma = W.sigma;
+    const int bl = S.block_size_log;
+    const int blocks_log = 20 - bl;
+    const int64_t blocks_in_sb = 1LL << blocks_log;
+    const int64_t sb_sigma = (int64_t)S.sigma_m1 + 1;
+    const size_t nblk = S.blocks.size();
+
+    std::vector<uint64_t> bits;
+    rrr_decode_all(S.rank_support, bits);
+    const uint64_t nbits = (uint64_t)S.rank_support.length;
+
+    // --- per block: tree, sectors, node records, descriptors
+    std::vector<BlockTree> trees(nblk);
+    uint64_t sec = P.sector_base, node = P.node_base, ovf = P.ovf_base;
+    std::vector<uint64_t> block_node_base(nblk, 0), block_ovf_base(nblk, 0);
+    for (size_t b = 0; b < nblk; ++b) {
+        BlockTree& T = trees[b];
+        build_block_tree(S, b, sb_block_size(W, sb, b), T);
+        Rec32& D = F.blocks[(size_t)P.first_block + b];
+        memset(&D, 0, sizeof D);
+        if (T.h == 0) {
+            D.w[1] = 1u | (((uint32_t)T.sym[0] & 0xffu) << 8);  // inverseSelect keeps the low byte only (:1329-1332)
+            continue;
+        }
+        block_node_base[b] = node;
+        block_ovf_base[b] = ovf;
+        for (auto& n : T.nodes) {
+            n.sector = (uint32_t)sec;
+            const uint32_t nsec = n.size / fmgpu::SECTOR_BITS + 1;
+            if ((uint64_t)n.start + n.size > nbits) throw FormatError("wavelet node exceeds the level bitvector");
+            uint32_t ones = 0;
+            for (uint32_t s = 0; s < nsec; ++s) {
+                Rec32& X = F.sectors[(size_t)sec + s];
+                X.w[0] = ones;
+                const uint32_t lo = s * fmgpu::SECTOR_BITS;
+                for (int k = 0; k < 7; ++k) {
+                    const uint32_t p = lo + 32u * (uint32_t)k;
+                    uint32_t word = 0;
+                    if (p < n.size) {
+                        const int take = (int)std::min<uint32_t>(32, n.size - p);
+                        word = bits_get(bits, (uint64_t)n.start + p, take);
+                    }
+                    X.w[1 + k] = word;
+                    ones += (uint32_t)__builtin_popcount(word);
+                }
+            }
+            sec += nsec;
+        }
+        for (size_t id = 0; id < T.nodes.size(); ++id) {
+            uint32_t rec[4];
+            for (int bit = 0; bit < 2; ++bit) {
+                const int32_t c = T.nodes[id].child[bit];
+                if (c < 0) {
+                    const size_t li = (size_t)(-c - 1);
+                    const uint32_t s = T.sym[li];
+                    const uint64_t base = (uint64_t)W.hyper_rank[s < (uint32_t)sigma ? s : 0] +
+                                          (uint64_t)(s < (uint32_t)sigma ? W.sb_rank[sb * (size_t)sigma + s] : 0) + T.brank[li];
+                    rec[bit] = fmgpu::LEAF_FLAG | s;
+                    rec[2 + bit] = (uint32_t)base;
+                } else {
+                    rec[bit] = (uint32_t)(node + (uint64_t)c);
+                    rec[2 + bit] = T.nodes[(size_t)c].sector;
+                }
+            }
+            const uint64_t gi = node + id;
+            memcpy(&F.nodes[(size_t)(gi >> 1)].w[(gi & 1) * 4], rec, 16);
+            if (id == 0) {
+                D.w[0] = T.nodes[0].sector;
+                memcpy(&D.w[4], rec, 16);
+            }
+        }
+        node += T.nodes.size();
+        ovf += T.n_ovf_chunks;
+    }
+
+    // --- cells: rank(pos in block b, sym) with everything but the level walk pre-evaluated
+    const bool last_sb = (sb + 1 == W.sbs.size());
+    std::vector<uint32_t> ovf_next(nblk);
+    for (size_t b = 0; b < nblk; ++b) ovf_next[b] = (uint32_t)block_ovf_base[b];
+    VarReader R(S.var);
+    for (int32_t sym = 0; sym < sigma; ++sym) {
+        const int64_t sb_c = W.global_mapping[sb * (size_t)sigma + (size_t)sym];
+        const uint64_t rank_sb = (uint64_t)(int64_t)W.sb_rank[sb * (size_t)sigma + (size_t)sym];
+        const uint64_t rank_hb = (uint64_t)W.hyper_rank[(size_t)sym];
+        auto cell_at = [&](size_t row) -> Rec32& { return F.cells[((size_t)P.first_block + row) * (size_t)sigma + (size_t)sym]; };
+        if (sb_c >= sb_sigma) {  // :1040 symbol absent from the superblock
+            for (size_t row = 0; row < P.rows; ++row) put_cell(cell_at(row), fmgpu::CELL_CONST, (uint32_t)(rank_hb + rank_sb));
+            continue;
+        }
+        if (sb_c < 0) {
+            for (size_t row = 0; row < P.rows; ++row) put_cell(cell_at(row), fmgpu::CELL_THROW, 0);
+            continue;
+        }
+        // right-to-left sweep = the reference's "closest block to the right in which c occurs" scan (:1048-1069)
+        int64_t next_present = -1;
+        for (int64_t b = blocks_in_sb - 1; b >= 0; --b) {
+            const int64_t mi = (sb_c << blocks_log) + b;
+            const bool in_range = mi >= 0 && (size_t)mi < S.mapping.size();
+            const int32_t block_c = in_range ? (int32_t)S.mapping[(size_t)mi] : 0;
+            const bool absent = in_range && block_c == sigma - 1;
+            if ((size_t)b < P.rows) {
+                Rec32& cell = cell_at((size_t)b);
+                if (!in_range) {
+                    put_cell(cell, fmgpu::CELL_THROW, 0);
+                } else if (absent) {
+                    if (next_present < 0) {
+                        uint64_t v;
+                        if ((((int64_t)sb + 1) << 20) >= W.size) v = (uint64_t)W.count[(size_t)sym];
+                        else v = rank_hb + (uint64_t)(int64_t)W.sb_rank[(sb + 1) * (size_t)sigma + (size_t)sym];
+                        put_cell(cell, fmgpu::CELL_CONST, (uint32_t)v);
+                    } else if ((size_t)next_present >= nblk) {
+                        put_cell(cell, fmgpu::CELL_THROW, 0);
+                    } else {
+                        // :1071-1107 — rank taken from the later block's header with the CLAMPED code and without
+                        // the treeHeight>0 guard (quirks Q3 and the run-block variant): restated literally.
+                        const BlockHdr& H2 = S.blocks[(size_t)next_present];
+                        const int64_t bc2 = S.mapping[(size_t)((sb_c << blocks_log) + next_present)];
+                        const int64_t ptr = (int64_t)H2.var_off + ((int64_t)H2.tree_height - 1) * 4 + bc2 * 5 + 2;
+                        R.ok = true;
+                        const uint32_t r24 = R.u24(ptr);
+                        if (!R.ok) put_cell(cell, fmgpu::CELL_THROW, 0);
+                        else put_cell(cell, fmgpu::CELL_CONST, (uint32_t)(rank_hb + rank_sb + r24));
+                    }
+                } else if ((size_t)b >= nblk) {
+                    put_cell(cell, fmgpu::CELL_THROW, 0);
+                } else {
+                    // :1113-1138 present: clamp repair, boundary rank
+                    const BlockHdr& H = S.blocks[(size_t)b];
+                    const BlockTree& T = trees[(size_t)b];
+                    const int h = H.tree_height;
+                    const int64_t tmp = (int64_t)H.var_off + (h > 0 ? (int64_t)(h - 1) * 4 : 0);
+                    int64_t bc = block_c;
+                    R.ok = true;
+                    const uint32_t value = R.u16(tmp + 5 * bc);
+                    if (value != (uint32_t)sym) ++bc;
+                    const uint32_t rank_blk = R.u24(tmp + bc * 5 + 2);
+                    if (!R.ok) {
+                        put_cell(cell, fmgpu::CELL_THROW, 0);
+                    } else if (h == 0) {
+                        put_cell(cell, fmgpu::CELL_RUN, (uint32_t)(rank_hb + rank_sb + rank_blk));
+                    } else if (bc < 0 || (size_t)bc >= T.leaves.size()) {
+                        put_cell(cell, fmgpu::CELL_THROW, 0);
+                    } else {
+                        const BlockTree::Leaf& L = T.leaves[(size_t)bc];
+                        memset(&cell, 0, sizeof cell);
+                        cell.w[0] = (uint32_t)(rank_hb + rank_sb + rank_blk);
+                        cell.w[1] = L.code;
+                        cell.w[2] = (uint32_t)L.len | (fmgpu::CELL_NORMAL << 8);
+                        // node ids along the path, root first
+                        uint32_t path[32];
+                        {
+                            int32_t id = 0;
+                            for (int d = 0; d < L.len; ++d) {
+                                path[d] = T.nodes[(size_t)id].sector;
+                                if (d + 1 < L.len) id = T.nodes[(size_t)id].child[(L.code >> (L.len - 1 - d)) & 1];
+                            }
+                        }
+                        if (L.len <= (int)fmgpu::CELL_INLINE_LEVELS) {
+                            for (int d = 0; d < L.len; ++d) cell.w[3 + d] = path[d];
+                        } else {
+                            for (int d = 0; d < 4; ++d) cell.w[3 + d] = path[d];
+                            const uint32_t chunks = (uint32_t)((L.len - 4 + 7) / 8);
+                            const uint32_t at = ovf_next[(size_t)b];
+                            ovf_next[(size_t)b] += chunks;
+                            cell.w[7] = at;
+                            for (uint32_t k = 0; k < chunks * 8; ++k) {
+                                const int d = 4 + (int)k;
+                                F.ovf[(size_t)at + k / 8].w[k % 8] = d < L.len ? path[d] : 0xffffffffu;
+                            }
+                        }
+                    }
+                }
+            }
+            if (in_range && !absent) next_present = b;
+        }
+    }
+    (void)last_sb;
+}
+
+inline void flatten_sampled(const RrrStream& r, FlatIndex& F) {
+    const RrrTables& T = rrr_tables();
+    const int64_t nblocks = ((int64_t)r.length + 14) / 15;
+    const int64_t ngroups = (nblocks + fmgpu::SGROUP_BLOCKS - 1) / fmgpu::SGROUP_BLOCKS + 1;  // +1: rank at position == length
+    F.sgroups.assign((size_t)ngroups, Rec32{});
+    uint64_t bitpos = 0, ones = 0;
+    for (int64_t g = 0; g < ngroups; ++g) {
+        Rec32& G = F.sgroups[(size_t)g];
+        G.w[0] = (uint32_t)ones;
+        G.w[1] = (uint32_t)bitpos;
+        uint32_t sub_bits = 0, sub_ones = 0, gb = 0, go = 0;
+        for (uint32_t k = 0; k < fmgpu::SGROUP_BLOCKS; ++k) {
+            const int64_t b = g * (int64_t)fmgpu::SGROUP_BLOCKS + k;
+            if (k && (k % 8) == 0) {
+                sub_bits |= gb << (10 * (k / 8 - 1));
+                sub_ones |= go << (10 * (k / 8 - 1));
+            }
+            uint32_t cls = 0;
+            if (b < nblocks) {
+                cls = (uint32_t)r.classes.get(b);
+                gb += T.bits_needed[cls];
+                go += cls;
+            }
+            G.w[4 + k / 8] |= cls << (4 * (k % 8));
+        }
+        G.w[2] = sub_bits;
+        G.w[3] = sub_ones;
+        bitpos += gb;
+        ones += go;
+        if (bitpos > 0xffffffffULL) throw FormatError("sampled-row offset stream exceeds 2^32 bits");
+    }
+    // offset stream verbatim (LSB-first 64-bit words == little-endian 32-bit word pairs), padded
+    const size_t nw64 = r.offsets.size();
+    F.soffsets.assign(nw64 * 2 + 16, 0);
+    memcpy(F.soffsets.data(), r.offsets.data(), nw64 * 8);
+}
+
+inline void unpack_samples(const PackedInts& v, std::vector<Rec32>& out) {
+    const size_t n = (size_t)v.length;
+    out.assign(n / 8 + 1, Rec32{});
+    for (size_t i = 0; i < n; ++i) out[i / 8].w[i % 8] = (uint32_t)v.get((int64_t)i);
+}
+
+// budget for the dense (block x symbol) cell table; beyond it the index is rejected for now
+constexpr uint64_t MAX_CELL_BYTES = 48ULL << 30;
+
+inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
+    const WfbbStream& W = fm.wf;
+    fmgpu::DevIndex& M = F.meta;
+    M.length = (uint32_t)fm.length;
+    M.sample_rate = (uint32_t)fm.sample_rate;
+    M.n_c = (uint32_t)fm.C.size();
+    M.n_lookup = (uint32_t)fm.lookup.size();
+    M.sigma = (uint32_t)W.sigma;
+    M.n_sb = (uint32_t)W.sbs.size();
+    M.q4 = (W.size % (1LL << 20)) == 0 ? 1u : 0u;
+    M.extract_enabled = fm.enable_extract ? 1u : 0u;
+    M.n_isa = fm.enable_extract ? (uint32_t)fm.positions.length : 0u;
+    M.n_sa = (uint32_t)fm.suffixes.length;
+    M.s_total_ones = (uint32_t)fm.sampled.total_ones;
+    F.alphabet_length = (int32_t)fm.map.size();
+
+    F.C.assign(fm.C.begin(), fm.C.end());
+    F.char2code.assign(65536, 0);
+    for (const auto& kv : fm.map)
+        if (kv.first >= 0 && kv.first < 65536) F.char2code[(size_t)kv.first] = (uint16_t)kv.second;
+    F.code2char.resize(fm.lookup.size());
+    for (size_t i = 0; i < fm.lookup.size(); ++i) F.code2char[i] = (uint16_t)fm.lookup[i];
+    for (const auto& kv : fm.map)
+        if (kv.second < 0 || (size_t)kv.second + 1 >= fm.C.size()) throw FormatError("alphabet code outside cumulativeCounts");
+
+    // pass 1: sizes
+    const size_t nsb = W.sbs.size();
+    std::vector<SbPlan> plan(nsb);
+    parallel_sbs(nsb, threads, [&](size_t sb) {
+        const SuperBlockHdr& S = W.sbs[sb];
+        const int64_t bs = 1LL << S.block_size_log;
+        const int64_t sb_size = std::min<int64_t>(1LL << 20, W.size - ((int64_t)sb << 20));
+        const size_t expect = (size_t)((sb_size + bs - 1) / bs);
+        if (S.blocks.size() != expect) throw FormatError("block count does not match superblock size");
+        SbPlan& P = plan[sb];
+        P.rows = (uint32_t)expect;
+        if (sb + 1 == nsb && (sb_size % bs) == 0 && sb_size != (1LL << 20)) P.rows += 1;  // row for position == size
+        BlockTree T;
+        for (size_t b = 0; b < S.blocks.size(); ++b) {
+            build_block_tree(S, b, sb_block_size(W, sb, b), T);
+            P.n_sectors += T.n_sectors;
+            P.n_nodes += T.nodes.size();
+            P.n_ovf += T.n_ovf_chunks;
+        }
+    });
+    uint64_t blocks_total = 0, sectors_total = 0, nodes_total = 0, ovf_total = 0;
+    F.sb.resize(nsb);
+    for (size_t sb = 0; sb < nsb; ++sb) {
+        SbPlan& P = plan[sb];
+        P.first_block = (uint32_t)blocks_total;
+        P.sector_base = sectors_total;
+        P.node_base = nodes_total;
+        P.ovf_base = ovf_total;
+        blocks_total += P.rows;
+        sectors_total += P.n_sectors;
+        nodes_total += P.n_nodes;
+        ovf_total += P.n_ovf;
+        F.sb[sb].first_block = P.first_block;
+        F.sb[sb].block_log = (uint32_t)W.sbs[sb].block_size_log;
+    }
+    if (sectors_total >= 0xffffffffULL || nodes_total >= 0x7fffffffULL || ovf_total >= 0xffffffffULL || blocks_total >= 0xffffffffULL)
+        throw FormatError("index too large for 32-bit record indices");
+    const uint64_t cell_bytes = blocks_total * (uint64_t)W.sigma * 32;
+    if (cell_bytes > MAX_CELL_BYTES)
+        throw FormatError("alphabet x block count too large for the dense cell table (" + std::to_string(cell_bytes >> 20) + " MiB)");
+    F.cells.assign((size_t)(blocks_total * (uint64_t)W.sigma), Rec32{});
+    F.sectors.assign((size_t)sectors_total + 1, Rec32{});
+    F.nodes.assign((size_t)(nodes_total / 2 + 1), Rec32{});
+    F.ovf.assign((size_t)ovf_total + 1, Rec32{});
+    F.blocks.assign((size_t)blocks_total + 1, Rec32{});
+
+    // pass 2: fill
+    parallel_sbs(nsb, threads, [&](size_t sb) { flatten_superblock(W, sb, plan[sb], F); });
+
+    flatten_sampled(fm.sampled, F);
+    unpack_samples(fm.suffixes, F.sa);
+    if (fm.enable_extract) unpack_samples(fm.positions, F.isa);
+    else F.isa.assign(1, Rec32{});
+}
+
+}  // namespace fmgpu_host

@@ -1,0 +1,295 @@
+// libfmgpu — C ABI (include/fmgpu.h) over the sm_100a kernels.  No CPU fallback: every entry point
+// needs a CUDA device and fails with FMGPU_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fmgpu.h"
+#include "flatten.hpp"
+#include "jstream.hpp"
+#include "kernels.cuh"
+#include "kernels_lf.cuh"
+#include "layout.h"
+
+using namespace fmgpu;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(FMGPU_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = prev == dev || cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x 6 at word 2.. */, CTRL_WORDS = 32 };
+
+}  // namespace
+
+struct fmgpu_index {
+    int device = 0;
+    DevIndex dev{};
+    std::vector<void*> allocs;
+    uint64_t layout_bytes[8] = {0};
+    uint64_t total_bytes = 0;
+    int32_t alphabet_length = 0;
+    int sm_count = 0;
+    int count_ctas = 0, lf_ctas = 0;
+    size_t tables_smem = 0;
+    std::mutex mu;  // batch calls on one handle are serialised (v0)
+    cudaStream_t stream = nullptr;
+    Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b;
+    uint64_t last_launches = 0;
+    bool stats_valid = false;
+};
+
+namespace {
+
+template <typename T>
+int upload(fmgpu_index* ix, const std::vector<T>& v, const T** dptr, uint64_t* bytes_acc) {
+    void* p = nullptr;
+    const size_t n = v.size() * sizeof(T);
+    CU(cudaMalloc(&p, n ? n : 32));
+    ix->allocs.push_back(p);
+    if (n) CU(cudaMemcpy(p, v.data(), n, cudaMemcpyHostToDevice));
+    *dptr = reinterpret_cast<const T*>(p);
+    ix->total_bytes += n;
+    if (bytes_acc) *bytes_acc += n;
+    return 0;
+}
+
+int grid_for(const void* kernel, int sm_count, size_t smem, int* out) {
+    int per_sm = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, CTA_THREADS, smem));
+    if (per_sm < 1) return fail(FMGPU_ERR_CUDA, "kernel does not fit on an SM");
+    *out = per_sm * sm_count;
+    return 0;
+}
+
+int prepass_grid(uint64_t items, int sm_count) {
+    uint64_t g = (items + 255) / 256;
+    const uint64_t cap = (uint64_t)sm_count * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars, uint32_t n_pat,
+                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st) {
+    CU(ix->codes.reserve((size_t)total_chars * 2 + 64));
+    CU(ix->pats.reserve(((size_t)n_pat + 2) * sizeof(PatDesc)));
+    CU(ix->ctrl.reserve(CTRL_WORDS * 4));
+    CU(cudaMemsetAsync(ix->ctrl.p, 0, CTRL_WORDS * 4, st));
+    ix->last_launches = 0;
+    ix->stats_valid = true;
+    if (n_pat == 0) return 0;
+    unsigned int* ctrl = (unsigned int*)ix->ctrl.p;
+    k_prepass<<<prepass_grid(total_chars > n_pat ? total_chars : n_pat, ix->sm_count), 256, 0, st>>>(
+        d_chars, d_pat_off, n_pat, total_chars, ix->dev.char2code, (uint16_t*)ix->codes.p, (PatDesc*)ix->pats.p);
+    k_count<<<ix->count_ctas, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, (const uint16_t*)ix->codes.p, (const PatDesc*)ix->pats.p,
+                                                                  n_pat, d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
+                                                                  (unsigned long long*)(ctrl + CTRL_STATS));
+    ix->last_launches += 2;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace
+
+#include "api_lf.inc"
+
+extern "C" {
+
+const char* fmgpu_last_error(void) { return g_err.c_str(); }
+const char* fmgpu_version(void) { return "fmgpu 0.1 (sm_100a)"; }
+
+int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out) {
+    if (!buf || !out) return fail(FMGPU_ERR_ARG, "null argument");
+    *out = nullptr;
+    int dev = opts ? opts->device : -1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1)
+        return fail(FMGPU_ERR_CUDA, "no CUDA device available (libfmgpu has no CPU fallback)");
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(FMGPU_ERR_ARG, "device ordinal %d out of range", dev);
+    int threads = opts ? opts->host_threads : 0;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+
+    fmgpu_host::FlatIndex F;
+    try {
+        fmgpu_host::JavaIn in(buf, len);
+        fmgpu_host::FmStream fm;
+        fm.read(in);
+        fmgpu_host::flatten(fm, threads, F);
+    } catch (const fmgpu_host::FormatError& e) {
+        return fail(FMGPU_ERR_FORMAT, "%s", e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(FMGPU_ERR_FORMAT, "out of host memory while re-laying out the index");
+    } catch (const std::exception& e) {
+        return fail(FMGPU_ERR_FORMAT, "%s", e.what());
+    }
+
+    DeviceGuard g(dev);
+    if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", dev);
+    fmgpu_index* ix = new fmgpu_index();
+    ix->device = dev;
+    ix->dev = F.meta;
+    ix->alphabet_length = F.alphabet_length;
+    int rc = 0;
+    auto up = [&](int r) {
+        if (!rc) rc = r;
+    };
+    up(upload(ix, F.C, &ix->dev.C, nullptr));
+    up(upload(ix, F.char2code, &ix->dev.char2code, nullptr));
+    up(upload(ix, F.code2char, &ix->dev.code2char, nullptr));
+    up(upload(ix, F.sb, &ix->dev.sb, nullptr));
+    up(upload(ix, F.cells, &ix->dev.cells, &ix->layout_bytes[0]));
+    up(upload(ix, F.sectors, &ix->dev.sectors, &ix->layout_bytes[1]));
+    up(upload(ix, F.nodes, &ix->dev.nodes, &ix->layout_bytes[2]));
+    up(upload(ix, F.blocks, &ix->dev.blocks, &ix->layout_bytes[3]));
+    up(upload(ix, F.ovf, &ix->dev.ovf, &ix->layout_bytes[4]));
+    up(upload(ix, F.sgroups, &ix->dev.sgroups, &ix->layout_bytes[5]));
+    up(upload(ix, F.soffsets, &ix->dev.soffsets, &ix->layout_bytes[5]));
+    up(upload(ix, F.sa, &ix->dev.sa, &ix->layout_bytes[6]));
+    up(upload(ix, F.isa, &ix->dev.isa, &ix->layout_bytes[7]));
+    if (!rc) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) rc = fail(FMGPU_ERR_CUDA, "cudaGetDeviceProperties failed");
+        else ix->sm_count = prop.multiProcessorCount;
+    }
+    if (!rc) {
+        ix->tables_smem = tables_smem_bytes(ix->dev);
+        rc = grid_for((const void*)k_count, ix->sm_count, ix->tables_smem, &ix->count_ctas);
+    }
+    if (!rc) rc = lf_setup(ix);
+    if (!rc && cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
+        rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreate failed");
+    if (rc) {
+        fmgpu_index_free(ix);
+        return rc;
+    }
+    *out = ix;
+    return 0;
+}
+
+void fmgpu_index_free(fmgpu_index* ix) {
+    if (!ix) return;
+    DeviceGuard g(ix->device);
+    for (void* p : ix->allocs) cudaFree(p);
+    for (Scratch* s : {&ix->codes, &ix->pats, &ix->ctrl, &ix->ranges, &ix->in_a, &ix->in_b, &ix->out_a, &ix->out_b, &ix->out_c,
+                       &ix->tmp_a, &ix->tmp_b})
+        s->release();
+    if (ix->stream) cudaStreamDestroy(ix->stream);
+    delete ix;
+}
+
+int32_t fmgpu_input_length(const fmgpu_index* ix) { return ix ? (int32_t)ix->dev.length : -1; }
+int32_t fmgpu_alphabet_length(const fmgpu_index* ix) { return ix ? ix->alphabet_length : -1; }
+int32_t fmgpu_sample_rate(const fmgpu_index* ix) { return ix ? (int32_t)ix->dev.sample_rate : -1; }
+int32_t fmgpu_extract_enabled(const fmgpu_index* ix) { return ix ? (int32_t)ix->dev.extract_enabled : -1; }
+int32_t fmgpu_device(const fmgpu_index* ix) { return ix ? ix->device : -1; }
+uint64_t fmgpu_device_bytes(const fmgpu_index* ix) { return ix ? ix->total_bytes : 0; }
+void fmgpu_layout_bytes(const fmgpu_index* ix, uint64_t out8[8]) {
+    for (int i = 0; i < 8; ++i) out8[i] = ix ? ix->layout_bytes[i] : 0;
+}
+
+int fmgpu_count_batch_device(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars, uint32_t n_pat,
+                             int32_t* d_counts_out, int32_t* d_status_out, void* cuda_stream) {
+    if (!ix || !d_pat_off || !d_counts_out || (!d_chars && total_chars)) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", ix->device);
+    return count_on_stream(ix, d_chars, d_pat_off, total_chars, n_pat, d_counts_out, d_status_out, nullptr, (cudaStream_t)cuda_stream);
+}
+
+int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts_out,
+                      int32_t* status_out) {
+    if (!ix || !pat_off || !counts_out) return fail(FMGPU_ERR_ARG, "null argument");
+    const uint64_t total = pat_off[n_pat];
+    if (total && !chars) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", ix->device);
+    cudaStream_t st = ix->stream;
+    CU(ix->in_a.reserve((size_t)total * 2 + 64));
+    CU(ix->in_b.reserve(((size_t)n_pat + 1) * 8));
+    CU(ix->out_a.reserve((size_t)n_pat * 4 + 64));
+    CU(ix->out_b.reserve((size_t)n_pat * 4 + 64));
+    if (total) CU(cudaMemcpyAsync(ix->in_a.p, chars, (size_t)total * 2, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ix->in_b.p, pat_off, ((size_t)n_pat + 1) * 8, cudaMemcpyHostToDevice, st));
+    int rc = count_on_stream(ix, (const uint16_t*)ix->in_a.p, (const uint64_t*)ix->in_b.p, total, n_pat, (int32_t*)ix->out_a.p,
+                             (int32_t*)ix->out_b.p, nullptr, st);
+    if (rc) return rc;
+    if (n_pat) {
+        CU(cudaMemcpyAsync(counts_out, ix->out_a.p, (size_t)n_pat * 4, cudaMemcpyDeviceToHost, st));
+        if (status_out) CU(cudaMemcpyAsync(status_out, ix->out_b.p, (size_t)n_pat * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fmgpu_last_stats(fmgpu_index* ix, uint64_t out6[6]) {
+    if (!ix || !out6) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    memset(out6, 0, 6 * sizeof(uint64_t));
+    if (!ix->stats_valid || !ix->ctrl.p) return 0;
+    CU(cudaDeviceSynchronize());
+    uint32_t words[CTRL_WORDS];
+    CU(cudaMemcpy(words, ix->ctrl.p, sizeof words, cudaMemcpyDeviceToHost));
+    memcpy(out6, words + CTRL_STATS, 5 * sizeof(uint64_t));
+    out6[5] = ix->last_launches;
+    return 0;
+}
+
+}  // extern "C"

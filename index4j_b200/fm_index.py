@@ -1,6 +1,342 @@
+"""Host-side mirror of ``com.dynatrace.fm.FmIndex`` over the C ABI of ``libfmgpu.so``.
+
+The reference class (indices/src/main/java/com/dynatrace/fm/FmIndex.java) exposes
+``count`` :443/:455, ``locate`` :487/:504, ``extract`` :564, ``extractUntilBoundary`` :640,
+``extractUntilBoundaryLeft`` :772, ``extractUntilBoundaryRight`` :844, ``getInputLength`` :929,
+``getAlphabetLength`` :939 and ``read`` :983.  This module keeps those names, argument meanings
+and error behaviour (Java exceptions become :class:`FmIndexError` subclasses carrying the same
+message) and adds the batched forms the GPU engine is built for.  Everything goes through the
+``extern "C"`` functions of ``include/fmgpu.h`` with plain pointers — exactly what a Java host binds
+through Panama FFM.  There is no CPU path: if the CUDA library or a GPU is missing
+the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+
+MODE_BOTH, MODE_LEFT, MODE_RIGHT = 0, 1, 2
+
+_MESSAGES = {
+    1: "Text recovery not enabled at build time",
+    2: "Requested position less than 0",
+    3: "Stop position longer than index string",
+    4: "Requested position longer than index string",
+    5: "Supplied destination is not large enough",
+    6: "Supplied destination for extraction has size zero",
+    7: "Boundary does not exist",
+    8: "Extraction does not fit in the supplied destination. Currently extracted: {n}",
+    9: "ArrayIndexOutOfBoundsException",
+}
+
+
 class FmIndexError(RuntimeError):
-    pass
+    """A Java RuntimeException of the reference, or a call-level failure of the native library."""
+
+    def __init__(self, message: str, status: int = 0, n: int = 0):
+        super().__init__(message)
+        self.status = status
+        self.n = n
 
 
-class FmIndex:  # placeholder, replaced below
-    pass
+class FmIndexIllegalArgument(FmIndexError, ValueError):
+    """IllegalArgumentException of the reference (status 6 and 7)."""
+
+
+class FmIndexOutOfBounds(FmIndexError, IndexError):
+    """ArrayIndexOutOfBoundsException of the reference (status 9)."""
+
+
+def raise_status(status: int, n: int = 0):
+    msg = _MESSAGES.get(int(status), "status %d" % status).format(n=int(n))
+    if status in (6, 7):
+        raise FmIndexIllegalArgument(msg, int(status), int(n))
+    if status == 9:
+        raise FmIndexOutOfBounds(msg, int(status), int(n))
+    raise FmIndexError(msg, int(status), int(n))
+
+
+_lib = None
+
+
+def native():
+    """The loaded ``libfmgpu.so`` (raises if it has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_build.GPU_LIB):
+            raise FmIndexError("libfmgpu.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(_build.GPU_LIB)
+        vp, i32, u32, u64, u16 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64, C.c_uint16
+        L.fmgpu_last_error.restype = C.c_char_p
+        L.fmgpu_version.restype = C.c_char_p
+        L.fmgpu_index_load_serialized.argtypes = [vp, C.c_size_t, vp, C.POINTER(vp)]
+        L.fmgpu_index_free.argtypes = [vp]
+        for f in ("fmgpu_input_length", "fmgpu_alphabet_length", "fmgpu_sample_rate", "fmgpu_extract_enabled", "fmgpu_device"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = i32
+        L.fmgpu_device_bytes.argtypes = [vp]
+        L.fmgpu_device_bytes.restype = u64
+        L.fmgpu_layout_bytes.argtypes = [vp, vp]
+        L.fmgpu_count_batch.argtypes = [vp, vp, vp, u32, vp, vp]
+        L.fmgpu_count_batch_device.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp]
+        L.fmgpu_locate_batch.argtypes = [vp, vp, vp, u32, i32, vp, vp, vp, u64, vp]
+        L.fmgpu_locate_batch_device.argtypes = [vp, vp, vp, u64, u32, i32, vp, vp, vp, u64, vp, C.POINTER(u64), vp]
+        L.fmgpu_extract_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
+        L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
+        L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp]
+        L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp, vp]
+        L.fmgpu_last_stats.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+class _Opts(C.Structure):
+    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("reserved", C.c_uint64 * 3)]
+
+
+def _u16(a) -> np.ndarray:
+    if isinstance(a, str):
+        return np.frombuffer(a.encode("utf-16-le", "surrogatepass"), dtype=np.uint16).copy()
+    return np.ascontiguousarray(a, dtype=np.uint16)
+
+
+def concat_patterns(patterns):
+    """list of str / uint16 arrays -> (chars uint16[total], pat_off uint64[n+1])"""
+    arrs = [_u16(p) for p in patterns]
+    off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+    if arrs:
+        off[1:] = np.cumsum([a.size for a in arrs])
+    chars = np.concatenate(arrs) if arrs else np.zeros(0, dtype=np.uint16)
+    return np.ascontiguousarray(chars, dtype=np.uint16), off
+
+
+class FmIndex:
+    """GPU-resident FM-index with the reference's query API."""
+
+    def __init__(self, handle, lib):
+        self._h = handle
+        self._lib = lib
+
+    # --- construction --------------------------------------------------------------------
+    @classmethod
+    def read(cls, serialized, device: int | None = None, host_threads: int = 0) -> "FmIndex":
+        """``Serialization.readFromByteArray(FmIndex::read, bytes)`` (Serialization.java:89, FmIndex.java:983)."""
+        lib = native()
+        buf = np.frombuffer(serialized, dtype=np.uint8)
+        opts = _Opts(-1 if device is None else int(device), int(host_threads))
+        h = C.c_void_p()
+        rc = lib.fmgpu_index_load_serialized(buf.ctypes.data, buf.size, C.byref(opts), C.byref(h))
+        if rc != 0:
+            msg = lib.fmgpu_last_error().decode()
+            if rc == -2:
+                raise IOError(msg)  # IOException of the reference (incompatible serial version, truncated stream)
+            raise FmIndexError(msg)
+        return cls(h, lib)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.fmgpu_index_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise FmIndexError(self._lib.fmgpu_last_error().decode(), status=rc)
+
+    # --- metadata --------------------------------------------------------------------------
+    def getInputLength(self) -> int:
+        return self._lib.fmgpu_input_length(self._h)
+
+    def getAlphabetLength(self) -> int:
+        return self._lib.fmgpu_alphabet_length(self._h)
+
+    @property
+    def sample_rate(self) -> int:
+        return self._lib.fmgpu_sample_rate(self._h)
+
+    @property
+    def device(self) -> int:
+        return self._lib.fmgpu_device(self._h)
+
+    def device_bytes(self) -> int:
+        return int(self._lib.fmgpu_device_bytes(self._h))
+
+    def layout_bytes(self) -> dict:
+        out = np.zeros(8, dtype=np.uint64)
+        self._lib.fmgpu_layout_bytes(self._h, out.ctypes.data)
+        names = ["cells", "level_sectors", "node_records", "block_descriptors", "path_overflow", "sampled_rows", "sa_samples", "isa_samples"]
+        return {k: int(v) for k, v in zip(names, out)}
+
+    def last_stats(self) -> dict:
+        out = np.zeros(6, dtype=np.uint64)
+        self._check(self._lib.fmgpu_last_stats(self._h, out.ctypes.data))
+        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches"]
+        return {k: int(v) for k, v in zip(names, out)}
+
+    # --- batched API (host buffers) ----------------------------------------------------------
+    def count_batch(self, chars, pat_off, return_status: bool = False):
+        chars = _u16(chars)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.fmgpu_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data))
+        return (counts, status) if return_status else counts
+
+    def locate_batch(self, chars, pat_off, max_hits: int = -1):
+        """-> (n_hits int32[n], hit_off uint64[n+1], positions int32[total], status int32[n])"""
+        chars = _u16(chars)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        n_hits = np.zeros(n, dtype=np.int32)
+        hit_off = np.zeros(n + 1, dtype=np.uint64)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.fmgpu_locate_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data,
+                                                 hit_off.ctypes.data, None, 0, status.ctypes.data))
+        total = int(hit_off[-1])
+        positions = np.zeros(max(total, 1), dtype=np.int32)
+        if total:
+            self._check(self._lib.fmgpu_locate_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data,
+                                                     hit_off.ctypes.data, positions.ctypes.data, total, status.ctypes.data))
+        return n_hits, hit_off, positions[:total], status
+
+    def extract_batch(self, start, stop, arena_off=None):
+        """-> (arena uint16[..], arena_off, len int32[n], status int32[n]); slot i = arena[arena_off[i]:arena_off[i+1]]"""
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        stop = np.ascontiguousarray(stop, dtype=np.int32)
+        n = start.size
+        if arena_off is None:
+            arena_off = np.zeros(n + 1, dtype=np.uint64)
+            arena_off[1:] = np.cumsum(np.maximum(stop.astype(np.int64) - start.astype(np.int64), 0))
+        arena_off = np.ascontiguousarray(arena_off, dtype=np.uint64)
+        arena = np.zeros(max(int(arena_off[-1]), 1), dtype=np.uint16)
+        ln = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.fmgpu_extract_batch(self._h, start.ctypes.data, stop.ctypes.data, n, arena.ctypes.data, arena_off.ctypes.data,
+                                                  ln.ctypes.data, st.ctypes.data))
+        return arena, arena_off, ln, st
+
+    def extract_until_boundary_batch(self, frm, boundary, dst_len: int, mode: int = MODE_BOTH):
+        """-> (arena uint16[n, dst_len], len int32[n], status int32[n])"""
+        frm = np.ascontiguousarray(frm, dtype=np.int32)
+        n = frm.size
+        b = ord(boundary) if isinstance(boundary, str) else int(boundary)
+        arena = np.zeros((n, max(dst_len, 1)), dtype=np.uint16)
+        ln = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.fmgpu_extract_until_boundary_batch(self._h, frm.ctypes.data, n, b, dst_len, mode,
+                                                                 arena.ctypes.data if dst_len > 0 else None, ln.ctypes.data, st.ctypes.data))
+        return arena, ln, st
+
+    # --- the reference's single-query methods -----------------------------------------------------
+    def count(self, pattern, offset: int = 0, length: int | None = None) -> int:
+        """``FmIndex.count(char[] pattern, int offset, int length)`` (FmIndex.java:443,455)."""
+        p = _u16(pattern)
+        if length is None:
+            length = p.size - offset
+        counts, status = self.count_batch(p[offset: offset + length], np.array([0, max(length, 0)], dtype=np.uint64), True)
+        if status[0]:
+            raise_status(status[0])
+        return int(counts[0])
+
+    def locate(self, pattern, offset: int = 0, length: int | None = None, locations=None, max_matches: int = -1):
+        """``FmIndex.locate(char[] pattern, int offset, int length, int[] locations, int maxMatches)`` (:487,:504).
+
+        With ``locations`` (an int32 array) the hits are written into it and their number is returned,
+        like Java; without it the located positions are returned as an array.
+        """
+        p = _u16(pattern)
+        if length is None:
+            length = p.size - offset
+        n_hits, _, pos, status = self.locate_batch(p[offset: offset + length], np.array([0, max(length, 0)], dtype=np.uint64), max_matches)
+        if status[0]:
+            raise_status(status[0])
+        if locations is None:
+            return pos
+        if pos.size > len(locations):
+            raise FmIndexOutOfBounds(_MESSAGES[9], 9)
+        locations[: pos.size] = pos
+        return int(n_hits[0])
+
+    def extract(self, start: int, stop: int, destination=None, offset: int = 0):
+        """``FmIndex.extract(int start, int stop, char[] destination, int offset)`` (:564)."""
+        room = (len(destination) - offset) if destination is not None else max(stop - start, 0)
+        arena, _, ln, st = self.extract_batch([start], [stop], np.array([0, max(room, 0)], dtype=np.uint64))
+        if st[0]:
+            raise_status(st[0])
+        if destination is None:
+            return arena[: max(int(ln[0]), 0)].copy()
+        k = max(int(ln[0]), 0)
+        destination[offset: offset + k] = arena[:k]
+        return int(ln[0])
+
+    def _eub(self, frm, destination, offset, boundary, mode):
+        if isinstance(destination, int):
+            dst_len, dest = destination, None
+        else:
+            dst_len, dest = len(destination) - offset, destination
+        arena, ln, st = self.extract_until_boundary_batch([frm], boundary, max(dst_len, 0), mode)
+        if st[0]:
+            raise_status(st[0], ln[0])
+        k = int(ln[0])
+        if dest is None:
+            return arena[0, : max(k, 0)].copy()
+        dest[offset: offset + max(k, 0)] = arena[0, : max(k, 0)]
+        return k
+
+    def extractUntilBoundary(self, frm: int, destination, offset: int = 0, boundary="\n"):
+        """``FmIndex.extractUntilBoundary(int from, char[] destination, int offset, char boundary)`` (:640)."""
+        return self._eub(frm, destination, offset, boundary, MODE_BOTH)
+
+    def extractUntilBoundaryLeft(self, frm: int, destination, offset: int = 0, boundary="\n"):
+        return self._eub(frm, destination, offset, boundary, MODE_LEFT)
+
+    def extractUntilBoundaryRight(self, frm: int, destination, offset: int = 0, boundary="\n"):
+        return self._eub(frm, destination, offset, boundary, MODE_RIGHT)
+
+    # --- device-resident forms (torch tensors on this index's GPU; asynchronous on the current stream) ----
+    def count_batch_device(self, d_chars, d_pat_off, d_counts, d_status=None, stream: int | None = None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_chars.device).cuda_stream
+        n = d_pat_off.numel() - 1
+        self._check(self._lib.fmgpu_count_batch_device(self._h, d_chars.data_ptr(), d_pat_off.data_ptr(), d_chars.numel(), n,
+                                                       d_counts.data_ptr(), d_status.data_ptr() if d_status is not None else None, stream))
+
+    def locate_batch_device(self, d_chars, d_pat_off, max_hits, d_n_hits, d_hit_off, d_positions, d_status=None, stream: int | None = None) -> int:
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_chars.device).cuda_stream
+        n = d_pat_off.numel() - 1
+        total = C.c_uint64()
+        self._check(self._lib.fmgpu_locate_batch_device(self._h, d_chars.data_ptr(), d_pat_off.data_ptr(), d_chars.numel(), n, max_hits,
+                                                        d_n_hits.data_ptr(), d_hit_off.data_ptr(),
+                                                        d_positions.data_ptr() if d_positions is not None else None,
+                                                        d_positions.numel() if d_positions is not None else 0,
+                                                        d_status.data_ptr() if d_status is not None else None, C.byref(total), stream))
+        return int(total.value)
+
+    def extract_until_boundary_batch_device(self, d_from, boundary, dst_len, mode, d_arena, d_len, d_status, stream: int | None = None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_from.device).cuda_stream
+        b = ord(boundary) if isinstance(boundary, str) else int(boundary)
+        self._check(self._lib.fmgpu_extract_until_boundary_batch_device(self._h, d_from.data_ptr(), d_from.numel(), b, dst_len, mode,
+                                                                        d_arena.data_ptr(), d_len.data_ptr(), d_status.data_ptr(), stream))
+
+    def extract_batch_device(self, d_start, d_stop, d_arena, d_arena_off, d_len, d_status, stream: int | None = None):
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_start.device).cuda_stream
+        self._check(self._lib.fmgpu_extract_batch_device(self._h, d_start.data_ptr(), d_stop.data_ptr(), d_start.numel(), d_arena.data_ptr(),
+                                                         d_arena_off.data_ptr(), d_len.data_ptr(), d_status.data_ptr(), stream))

@@ -1,0 +1,258 @@
+// TEST SUPPORT (not product code): replays the product's host re-layout (flatten.hpp) and the
+// per-lane logic of the kernels (lane_logic.h, walk_lane.h) on the CPU, one lane at a time, so that
+// tests can compare the device data layout and lane state machines with the oracle without a GPU.
+// The kernels run exactly these functions per lane; only the warp-level scheduling differs.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../index4j_b200/csrc/flatten.hpp"
+#include "../../index4j_b200/csrc/jstream.hpp"
+#include "../../index4j_b200/csrc/walk_lane.h"
+
+using namespace fmgpu;
+
+namespace {
+thread_local std::string g_err;
+struct FC {
+    fmgpu_host::FlatIndex F;
+    DevIndex ix;
+    SmemTables T;
+    uint16_t binom[15 * 16];
+};
+const Rec32 ZERO{};
+
+// rank(pos, sym) through the cell / level / overflow records; returns status (0 or 9)
+int host_rank(const FC& h, uint32_t pos, uint32_t sym, uint32_t* out, uint64_t* n_rank, uint64_t* n_level) {
+    RankSt s;
+    s.p5 = s.p6 = s.p7 = 0;
+    const Rec32* addr = nullptr;
+    uint32_t val = 0;
+    uint32_t o = rank_begin(h.ix, h.T, pos, sym, s, &addr, &val);
+    if (o == RK_THROW) return 9;
+    if (o == RK_DONE) {
+        *out = val;
+        return 0;
+    }
+    if (n_rank) ++*n_rank;
+    o = rank_on_cell(h.ix, *addr, s, &addr, &val);
+    if (o == RK_THROW) return 9;
+    while (o == RK_MORE) {
+        bool want = false;
+        if (n_level) ++*n_level;
+        o = rank_on_level(h.ix, *addr, s, &addr, &val, &want);
+        if (o == RK_MORE && want) rank_on_ovf(h.ix, *addr, s, &addr);
+    }
+    *out = val;
+    return 0;
+}
+
+template <int MODE>
+void run_walk(const FC& h, const WalkParams& P, uint64_t* counters) {
+    WalkCounters cnt{};
+    for (uint32_t w = 0; w < P.n_items; ++w) {
+        WalkLane<MODE> lane;
+        lane.init();
+        lane.w = w;
+        lane.phase = W_ITEM;
+        while (lane.phase != W_IDLE) {
+            ItemRaw raw{};
+            if (lane.phase == W_ITEM) raw = walk_load_item<MODE>(P, w);
+            const Rec32 A = lane.needs_a() ? *lane.addr_a : ZERO;
+            const Rec32 B = (lane.needs_a() && lane.need_b) ? *lane.addr_b : ZERO;
+            lane.step(h.ix, h.T, P, raw, A, B, cnt);
+        }
+    }
+    if (counters) {
+        counters[0] += cnt.ranks;
+        counters[1] += cnt.rank_levels;
+        counters[2] += cnt.lf_steps;
+        counters[3] += cnt.lf_levels;
+        counters[4] += cnt.sbits;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+const char* fc_last_error(void) { return g_err.c_str(); }
+
+int fc_load(const uint8_t* buf, uint64_t len, int threads, void** out) {
+    try {
+        FC* h = new FC();
+        fmgpu_host::JavaIn in(buf, (size_t)len);
+        fmgpu_host::FmStream fm;
+        fm.read(in);
+        fmgpu_host::flatten(fm, threads, h->F);
+        h->ix = h->F.meta;
+        h->ix.C = h->F.C.data();
+        h->ix.char2code = h->F.char2code.data();
+        h->ix.code2char = h->F.code2char.data();
+        h->ix.sb = h->F.sb.data();
+        h->ix.cells = h->F.cells.data();
+        h->ix.sectors = h->F.sectors.data();
+        h->ix.ovf = h->F.ovf.data();
+        h->ix.blocks = h->F.blocks.data();
+        h->ix.nodes = h->F.nodes.data();
+        h->ix.sgroups = h->F.sgroups.data();
+        h->ix.soffsets = h->F.soffsets.data();
+        h->ix.sa = h->F.sa.data();
+        h->ix.isa = h->F.isa.data();
+        h->T.C = h->ix.C;
+        h->T.sb = h->ix.sb;
+        fill_binom(h->binom);
+        *out = h;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -2;
+    }
+}
+void fc_free(void* h) { delete (FC*)h; }
+int32_t fc_alphabet_length(void* h) { return ((FC*)h)->F.alphabet_length; }
+void fc_sizes(void* hv, uint64_t* out8) {
+    FC* h = (FC*)hv;
+    out8[0] = h->F.cells.size() * 32;
+    out8[1] = h->F.sectors.size() * 32;
+    out8[2] = h->F.nodes.size() * 32;
+    out8[3] = h->F.blocks.size() * 32;
+    out8[4] = h->F.ovf.size() * 32;
+    out8[5] = h->F.sgroups.size() * 32 + h->F.soffsets.size() * 4;
+    out8[6] = h->F.sa.size() * 32;
+    out8[7] = h->F.isa.size() * 32;
+}
+
+int fc_rank(void* h, uint32_t pos, uint32_t sym, int64_t* out) {
+    uint32_t v = 0;
+    const int st = host_rank(*(FC*)h, pos, sym, &v, nullptr, nullptr);
+    *out = v;
+    return st;
+}
+
+// FmIndex.count over the flat layout (sequential restatement of what a lane pair does)
+void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
+                    uint32_t* ranges, uint64_t* counters) {
+    FC& h = *(FC*)hv;
+    uint64_t n_rank = 0, n_level = 0;
+    for (uint32_t p = 0; p < n_pat; ++p) {
+        const uint16_t* pat = chars + pat_off[p];
+        const int64_t len = (int64_t)(pat_off[p + 1] - pat_off[p]);
+        int32_t result = 0, st = 0;
+        uint32_t sp = 0, ep = 0;
+        if (len == 0) {
+            st = 9;
+        } else {
+            int64_t i = len - 1;
+            uint32_t c = h.ix.char2code[pat[i]];
+            if (c != 0) {
+                sp = h.ix.C[c];
+                ep = h.ix.C[c + 1];
+                bool zero = false;
+                while (sp < ep && i >= 1) {
+                    c = h.ix.char2code[pat[--i]];
+                    if (c == 0) {
+                        zero = true;
+                        break;
+                    }
+                    uint32_t a = 0, b = 0;
+                    const int s1 = host_rank(h, sp, c, &a, &n_rank, &n_level);
+                    const int s2 = host_rank(h, ep, c, &b, &n_rank, &n_level);
+                    if (s1 || s2) {
+                        st = 9;
+                        break;
+                    }
+                    sp = h.ix.C[c] + a;
+                    ep = h.ix.C[c] + b;
+                }
+                if (!zero && !st) result = ep > sp ? (int32_t)(ep - sp) : 0;
+            }
+        }
+        counts[p] = st ? 0 : result;
+        if (status) status[p] = st;
+        if (ranges) {
+            ranges[2 * p] = sp;
+            ranges[2 * p + 1] = (!st && result > 0) ? ep : sp;
+        }
+    }
+    if (counters) {
+        counters[0] += n_rank;
+        counters[1] += n_level;
+    }
+}
+
+void fc_locate_rows(void* hv, uint32_t* rows_pos, uint32_t n, int32_t* status, uint64_t* counters) {
+    FC& h = *(FC*)hv;
+    WalkParams P{};
+    P.n_items = n;
+    P.rows_pos = rows_pos;
+    P.status_out = status;
+    P.binom = h.binom;
+    run_walk<WM_LOCATE>(h, P, counters);
+}
+
+void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena, const uint64_t* arena_off,
+                int32_t* len_out, int32_t* status, uint64_t* counters) {
+    FC& h = *(FC*)hv;
+    WalkParams P{};
+    P.n_items = n;
+    P.start = start;
+    P.stop = stop;
+    P.arena_off = arena_off;
+    P.arena = arena;
+    P.len_out = len_out;
+    P.status_out = status;
+    P.binom = h.binom;
+    run_walk<WM_EXTRACT>(h, P, counters);
+}
+
+void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len, int32_t mode, uint16_t* arena,
+            int32_t* len_out, int32_t* status, uint64_t* counters) {
+    FC& h = *(FC*)hv;
+    std::vector<uint16_t> left((size_t)n * (size_t)(dst_len > 0 ? dst_len : 1), 0);
+    std::vector<int32_t> down(n, 0);
+    WalkParams P{};
+    P.n_items = n;
+    P.from = from;
+    P.mb = h.ix.char2code[boundary];
+    P.dst_len = dst_len;
+    P.eub_mode = mode;
+    P.left = left.data();
+    P.down_len = down.data();
+    P.arena = arena;
+    P.len_out = len_out;
+    P.status_out = status;
+    P.binom = h.binom;
+    run_walk<WM_EUB>(h, P, counters);
+    if (mode != 2)
+        for (uint32_t w = 0; w < n; ++w)  // what k_eub_assemble does
+            for (int32_t q = 0; q < down[w] && q < dst_len; ++q)
+                arena[(size_t)w * dst_len + q] = left[(size_t)w * dst_len + (down[w] - 1 - q)];
+}
+
+// sampled-row access/rank through the group records
+void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
+    FC& h = *(FC*)hv;
+    SgSt s;
+    uint32_t b = 0, r = 0;
+    const Rec32* oa = nullptr;
+    const Rec32* ob = nullptr;
+    bool st = false;
+    const uint32_t o = sg_on_group(h.ix, *sg_addr(h.ix, pos), pos, s, &b, &r, &oa, &ob, &st);
+    if (o == SG_OFFSET) sg_on_offset(*oa, st ? *ob : ZERO, st, h.binom, s, &b, &r);
+    *bit = (int32_t)b;
+    *rank = (int32_t)r;
+}
+
+// all 32768 (class, offset) pairs through the device unranking, in table order
+void fc_unrank_table(uint16_t* out32768) {
+    uint16_t binom[15 * 16];
+    fill_binom(binom);
+    int cnt[16] = {0};
+    for (int v = 0; v < 32768; ++v) cnt[__builtin_popcount(v)]++;
+    size_t at = 0;
+    for (uint32_t cls = 0; cls < 16; ++cls)
+        for (int off = 0; off < cnt[cls]; ++off) out32768[at++] = (uint16_t)rrr_unrank(binom, cls, (uint32_t)off, 15);
+}
+
+}  // extern "C"

@@ -1,0 +1,119 @@
+"""ctypes binding of tests/support/libflatcheck.so (host replay of the device layout + lane logic)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libflatcheck.so")
+ROOT = os.path.dirname(os.path.dirname(HERE))
+_lib = None
+
+
+def build(force=False):
+    srcs = [os.path.join(HERE, "flatcheck.cpp")] + [
+        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "layout.h")
+    ]
+    if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
+                               "-o", LIB, srcs[0]])
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, i32, u32, u64 = C.c_void_p, C.c_int32, C.c_uint32, C.c_uint64
+        L.fc_last_error.restype = C.c_char_p
+        L.fc_load.argtypes = [vp, u64, i32, C.POINTER(vp)]
+        L.fc_free.argtypes = [vp]
+        L.fc_alphabet_length.argtypes = [vp]
+        L.fc_sizes.argtypes = [vp, vp]
+        L.fc_rank.argtypes = [vp, u32, u32, C.POINTER(C.c_int64)]
+        L.fc_count_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
+        L.fc_locate_rows.argtypes = [vp, vp, u32, vp, vp]
+        L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
+        L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp]
+        L.fc_sampled.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
+        L.fc_unrank_table.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+class FlatIndexHost:
+    def __init__(self, serialized: bytes, threads: int = 4):
+        self._h = C.c_void_p()
+        buf = np.frombuffer(serialized, dtype=np.uint8)
+        rc = lib().fc_load(buf.ctypes.data, buf.size, threads, C.byref(self._h))
+        if rc:
+            raise IOError(lib().fc_last_error().decode())
+        self.counters = np.zeros(8, dtype=np.uint64)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().fc_free(self._h)
+            self._h = None
+
+    def sizes(self):
+        out = np.zeros(8, dtype=np.uint64)
+        lib().fc_sizes(self._h, out.ctypes.data)
+        return out
+
+    def rank(self, pos, sym):
+        out = C.c_int64()
+        st = lib().fc_rank(self._h, pos, sym, C.byref(out))
+        return st, out.value
+
+    def count_batch(self, chars, pat_off):
+        chars = np.ascontiguousarray(chars, dtype=np.uint16)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        ranges = np.zeros(2 * n, dtype=np.uint32)
+        lib().fc_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data,
+                             ranges.ctypes.data, self.counters.ctypes.data)
+        return counts, status, ranges.reshape(n, 2)
+
+    def locate_rows(self, rows):
+        rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()
+        st = np.zeros(rp.size, dtype=np.int32)
+        lib().fc_locate_rows(self._h, rp.ctypes.data, rp.size, st.ctypes.data, self.counters.ctypes.data)
+        return rp.astype(np.int64), st
+
+    def extract(self, start, stop, arena_off):
+        start = np.ascontiguousarray(start, dtype=np.int32)
+        stop = np.ascontiguousarray(stop, dtype=np.int32)
+        arena_off = np.ascontiguousarray(arena_off, dtype=np.uint64)
+        n = start.size
+        arena = np.zeros(int(arena_off[-1]) + 1, dtype=np.uint16)
+        ln = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        lib().fc_extract(self._h, start.ctypes.data, stop.ctypes.data, n, arena.ctypes.data, arena_off.ctypes.data, ln.ctypes.data,
+                         st.ctypes.data, self.counters.ctypes.data)
+        return arena, ln, st
+
+    def eub(self, frm, boundary, dst_len, mode):
+        frm = np.ascontiguousarray(frm, dtype=np.int32)
+        n = frm.size
+        arena = np.zeros((n, max(dst_len, 1)), dtype=np.uint16)
+        ln = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        lib().fc_eub(self._h, frm.ctypes.data, n, boundary, dst_len, mode, arena.ctypes.data, ln.ctypes.data, st.ctypes.data,
+                     self.counters.ctypes.data)
+        return arena, ln, st
+
+    def sampled(self, pos):
+        b, r = C.c_int32(), C.c_int32()
+        lib().fc_sampled(self._h, pos, C.byref(b), C.byref(r))
+        return b.value, r.value
+
+
+def unrank_table():
+    t = np.zeros(32768, dtype=np.uint16)
+    lib().fc_unrank_table(t.ctypes.data)
+    return t

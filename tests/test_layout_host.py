@@ -1,0 +1,111 @@
+"""CPU tests of the product's host re-layout (flatten.hpp) and per-lane logic (lane_logic.h,
+walk_lane.h): tests/support/libflatcheck.so replays exactly the functions every GPU lane runs, one
+lane at a time with plain memory reads, and the results must be bit-exact with the oracle.
+"""
+import numpy as np
+import pytest
+
+from conftest import CASE_NAMES, get_case, make_patterns
+
+import flatcheck
+import pyoracle
+
+
+@pytest.fixture(scope="module")
+def flats():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = flatcheck.FlatIndexHost(get_case(name).blob)
+        return cache[name]
+
+    return get
+
+
+def test_unranking_reproduces_reference_table():
+    assert np.array_equal(flatcheck.unrank_table(), pyoracle.rrr_inverse_table())
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_rank_cells_match_oracle(flats, name):
+    case, f = get_case(name), flats(name)
+    rng = np.random.default_rng(1)
+    L = case.oracle.getInputLength()
+    sigma = case.oracle.getAlphabetLength() + 2
+    pos = np.concatenate([rng.integers(0, L + 1, 30000), [0, 1, L - 1, L, L + 5]])
+    # positions around block boundaries, where the absent-from-block fallbacks live
+    pos = np.concatenate([pos, (rng.integers(1, max(2, L >> 9), 4000) << 9) + rng.integers(-1, 2, 4000)])
+    pos = np.clip(pos, 0, L + 5)
+    for p in pos:
+        s = int(rng.integers(0, sigma))
+        try:
+            want, st = case.oracle.wfbb_rank(int(p), s), 0
+        except pyoracle.JavaException as e:
+            want, st = None, e.status
+        got_st, got = f.rank(int(p), s)
+        assert got_st == st and (st or got == want), (int(p), s, want, got, st, got_st)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_sampled_rows_match_oracle(flats, name):
+    case, f = get_case(name), flats(name)
+    rng = np.random.default_rng(2)
+    L = case.oracle.getInputLength()
+    for p in np.concatenate([rng.integers(0, L, 20000), [0, L - 1]]):
+        b, r = f.sampled(int(p))
+        assert b == case.oracle.sampled_access(int(p)) and r == case.oracle.sampled_rank(int(p)), int(p)
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_count_and_locate_lanes(flats, name):
+    case, f = get_case(name), flats(name)
+    chars, off = make_patterns(case.text, 2500, 1, 40, seed=3)
+    want, want_st = case.oracle.count_batch(chars, off, threads=4)
+    got, got_st, ranges = f.count_batch(chars, off)
+    assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
+    n_hits, pos, st = case.oracle.locate_batch(chars, off, 50, 50, threads=4)
+    rows, exp = [], []
+    for i in range(n_hits.size):
+        rows += list(range(int(ranges[i, 0]), int(ranges[i, 0]) + int(n_hits[i])))
+        exp += list(pos[i, : n_hits[i]])
+    got_pos, _ = f.locate_rows(np.array(rows, dtype=np.uint32))
+    assert np.array_equal(got_pos, np.array(exp, dtype=np.int64))
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_extract_lanes(flats, name):
+    case, f = get_case(name), flats(name)
+    rng = np.random.default_rng(4)
+    n = case.text.size
+    m = 1500
+    start = rng.integers(0, n - 200, m).astype(np.int32)
+    ln = rng.integers(0, 150, m).astype(np.int32)
+    stop = start + ln
+    start[:3] = [0, n - 40, n - 1]
+    stop[:3] = [70, n, n]
+    aoff = np.zeros(m + 1, dtype=np.uint64)
+    aoff[1:] = np.cumsum(stop - start)
+    arena, got_len, st = f.extract(start, stop, aoff)
+    assert not st.any() and np.array_equal(got_len, stop - start)
+    for i in range(m):
+        assert np.array_equal(arena[int(aoff[i]): int(aoff[i + 1])], case.text[start[i]: stop[i]]), i
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_extract_until_boundary_lanes(flats, name, mode):
+    case, f = get_case(name), flats(name)
+    n = case.text.size
+    rng = np.random.default_rng(5 + mode)
+    for dst_len in (512, 40, 10, 3, 1):
+        frm = np.concatenate([rng.integers(0, n, 700), np.arange(n - 12, n + 2), np.arange(-1, 5)]).astype(np.int32)
+        a1, l1, s1 = case.oracle.extract_until_boundary_batch(frm, 10, dst_len, mode, threads=4)
+        a2, l2, s2 = f.eub(frm, 10, dst_len, mode)
+        assert np.array_equal(s1, s2), (dst_len, np.flatnonzero(s1 != s2)[:5])
+        ok = (s1 == 0) | (s1 == 8)
+        assert np.array_equal(l1[ok], l2[ok]), dst_len
+        for i in np.flatnonzero(s1 == 0):
+            if frm[i] >= n:
+                continue
+            assert np.array_equal(a1[i, : l1[i]], a2[i, : l1[i]]), (dst_len, i, int(frm[i]))
