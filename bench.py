@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py — backward-search (count) throughput of the FM-index query engine.
+
+Workload (BASELINE.json configs[1]): FmIndex sampleRate=32 over 1 GiB (2^30 chars) of synthetic
+log-like text; 1,000,000 count queries, substrings of the text of length 4-64 (the reference's JMH
+workload shape, indices/src/jmh/java/com/dynatrace/fm/FmIndexThroughputState.java:76-83).
+A step = one pass of FmIndex.count over the whole 1 M-pattern batch.  With N GPUs the index is
+replicated and every rank runs its own 1 M-pattern batch (weak scaling, no data-path collective).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA engine
+  python bench.py --impl reference [--steps K] [--warmup W]      # the reference's CPU path (C++ oracle port,
+                                                                 # all host threads; no JVM exists in this image)
+One JSON line on stdout (rank 0).  See DESIGN.md §5 for how every field is measured.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CACHE = os.path.join(ROOT, ".index_cache")
+ALT_CACHE = "/tmp/index_cache"  # where indexes built in the development container are kept (outside the repo snapshot)
+
+METRIC = "backward-search patterns/sec (count)"
+UNIT = "patterns/s"
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def cache_path(name: str) -> str:
+    for d in (CACHE, ALT_CACHE):
+        p = os.path.join(d, name)
+        if os.path.exists(p):
+            return p
+    os.makedirs(CACHE, exist_ok=True)
+    return os.path.join(CACHE, name)
+
+
+def get_text(n: int) -> np.ndarray:
+    from index4j_b200.builder import gen_log_text
+    return gen_log_text(n)
+
+
+def get_index_blob(n: int, sr: int, text_holder: dict, use_gpu_sa: bool = True) -> bytes:
+    """Serialized FmIndex (reference layout) of the synthetic text; built once per box and cached."""
+    p = cache_path("log_n%d_sr%d.fmi" % (n, sr))
+    if os.path.exists(p):
+        with open(p, "rb") as fh:
+            return fh.read()
+    from index4j_b200.builder import build_index, map_text
+    t0 = time.time()
+    text = text_holder.get("text")
+    if text is None:
+        text = text_holder["text"] = get_text(n)
+    sa = None
+    if use_gpu_sa:
+        import torch
+        if torch.cuda.is_available():
+            from index4j_b200.gpu_sa import suffix_array
+            codes, sigma = map_text(text)
+            sa = suffix_array(codes, sigma, device="cuda", verbose=True)
+            del codes
+            torch.cuda.empty_cache()
+    log("suffix array ready after %.1fs" % (time.time() - t0))
+    blob = build_index(text, sr, True, framed=False, verbose=True, suffix_array=sa)
+    del sa
+    tmp = p + ".tmp%d" % os.getpid()
+    with open(tmp, "wb") as fh:
+        fh.write(blob)
+    os.replace(tmp, p)
+    log("index built in %.1fs (%d bytes) -> %s" % (time.time() - t0, len(blob), p))
+    return blob
+
+
+def get_patterns(n: int, n_pat: int, lo: int, hi: int, seed: int, text_holder: dict):
+    p = cache_path("pat_n%d_%d_%d_%d_s%d.npz" % (n, n_pat, lo, hi, seed))
+    if os.path.exists(p):
+        z = np.load(p)
+        return z["chars"], z["off"]
+    from index4j_b200.builder import gen_patterns
+    text = text_holder.get("text")
+    if text is None:
+        text = text_holder["text"] = get_text(n)
+    chars, off = gen_patterns(text, n_pat, lo, hi, seed)
+    tmp = p + ".tmp%d.npz" % os.getpid()
+    np.savez(tmp, chars=chars, off=off)
+    os.replace(tmp, p)
+    return chars, off
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ["clocks.sm", "clocks.max.sm", "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
+              "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + ",".join(self.FIELDS),
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as fh:
+                d = json.load(fh)
+            v = d.get("hbm_gbs")
+            if v:
+                return float(v), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_count_throughput(blob: bytes, chars, off, n_sample: int, threads: int, repeats: int = 1):
+    """The reference's CPU path (C++ restatement of the Java loops = oracle port) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    o = pyoracle.OracleFmIndex(blob)
+    n_sample = min(n_sample, off.size - 1)
+    sub_off = off[: n_sample + 1]
+    sub_chars = chars[: int(sub_off[-1])]
+    best = None
+    counts = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        counts, _ = o.count_batch(sub_chars, sub_off, threads=threads)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_sample / best, best, counts, o
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    holder = {}
+    blob = get_index_blob(args.n_text, args.sample_rate, holder, use_gpu_sa=True)
+    chars, off = get_patterns(args.n_text, args.n_pat, args.min_len, args.max_len, 42, holder)
+    holder.clear()
+    threads = os.cpu_count() or 1
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    o = pyoracle.OracleFmIndex(blob)
+    n_sample = min(args.ref_sample, off.size - 1)
+    sub_off = off[: n_sample + 1]
+    sub_chars = chars[: int(sub_off[-1])]
+    for _ in range(args.warmup):
+        o.count_batch(sub_chars, sub_off, threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        o.count_batch(sub_chars, sub_off, threads=threads)
+    dt = time.perf_counter() - t0
+    value = n_sample * args.steps / dt
+    sample = "first %d of the %d patterns per step (C++ restatement of the Java loops; no JVM in this image)" % (n_sample, args.n_pat)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "count: %d patterns len %d-%d (substrings of the text) per GPU per step over FmIndex(sampleRate=%d) of %d chars of synthetic log text"
+                        % (args.n_pat, args.min_len, args.max_len, args.sample_rate, args.n_text),
+            "index": "replicated per GPU", "batch_per_gpu": args.n_pat,
+            "l2": "index (>0.7 GB) + inputs larger than the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-text", type=int, default=1 << 30)
+    ap.add_argument("--n-pat", type=int, default=1_000_000)
+    ap.add_argument("--min-len", type=int, default=4)
+    ap.add_argument("--max-len", type=int, default=64)
+    ap.add_argument("--sample-rate", type=int, default=32)
+    ap.add_argument("--ref-sample", type=int, default=200_000, help="patterns per step of the CPU reference arm")
+    ap.add_argument("--cpu-sample", type=int, default=200_000, help="patterns of the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from index4j_b200 import FmIndex
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    holder = {}
+    if rank == 0:
+        get_index_blob(args.n_text, args.sample_rate, holder)  # build + cache once per box
+        for r in range(world):
+            get_patterns(args.n_text, args.n_pat, args.min_len, args.max_len, 42 + r, holder)
+    barrier()
+    blob = get_index_blob(args.n_text, args.sample_rate, holder)
+    chars, off = get_patterns(args.n_text, args.n_pat, args.min_len, args.max_len, 42 + rank, holder)
+    holder.clear()
+    t0 = time.time()
+    ix = FmIndex.read(blob, device=local)
+    log("rank %d: index on device in %.1fs, %.1f MB HBM, layout %s" % (rank, time.time() - t0, ix.device_bytes() / 1e6, ix.layout_bytes()))
+    n_pat = off.size - 1
+
+    # resident inputs / outputs for the kernel-level number
+    d_chars = torch.from_numpy(chars.view(np.int16)).to(dev)
+    d_off = torch.from_numpy(off.view(np.int64)).to(dev)
+    d_counts = torch.empty(n_pat, dtype=torch.int32, device=dev)
+    d_status = torch.empty(n_pat, dtype=torch.int32, device=dev)
+    ix.set_timing(True)
+
+    def step():
+        ix.count_batch_device(d_chars, d_off, d_counts, d_status)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    kernel_ms = [ix.search_kernel_ms(i) for i in range(min(args.steps, 64))]
+    stats = ix.last_stats()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
+    p_chars = torch.from_numpy(chars.view(np.int16)).pin_memory()
+    p_off = torch.from_numpy(off.view(np.int64)).pin_memory()
+    p_counts = torch.empty(n_pat, dtype=torch.int32).pin_memory()
+    p_status = torch.empty(n_pat, dtype=torch.int32).pin_memory()
+    h_chars, h_off = p_chars.numpy().view(np.uint16), p_off.numpy().view(np.uint64)
+    h_counts, h_status = p_counts.numpy(), p_status.numpy()
+    for _ in range(2):
+        ix.count_batch_into(h_chars, h_off, h_counts, h_status)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ix.count_batch_into(h_chars, h_off, h_counts, h_status)
+    e2e_s = time.perf_counter() - t0
+    assert np.array_equal(h_counts, d_counts.cpu().numpy())
+
+    times = torch.tensor([ms_total, e2e_s * 1e3, statistics.mean(kernel_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms, kern_ms = [float(x) for x in times.cpu()]
+
+    if rank == 0:
+        value = world * n_pat * args.steps / (ms_total / 1e3)
+        e2e_value = world * n_pat * args.steps / (e2e_ms / 1e3)
+        peak, peak_src = hbm_peak()
+        # algorithmic bytes of one k_count launch: every rank query reads one 32-byte cell and one 32-byte level
+        # sector per wavelet level; plus the pattern codes and descriptors it streams.
+        alg_bytes = 32.0 * (stats["ranks"] + stats["rank_levels"]) + 2.0 * chars.size + 16.0 * n_pat + 8.0 * n_pat
+        achieved = alg_bytes / (kern_ms / 1e3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic", "config": workload_config(args), "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(chars.nbytes + off.nbytes),
+                    "d2h_bytes_per_step": int(h_counts.nbytes + h_status.nbytes)},
+            "gpu_launches": int(stats["launches"]) * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
+                         "sectors_per_rank": (stats["ranks"] + stats["rank_levels"]) / max(1, stats["ranks"]),
+                         "ranks_per_s": stats["ranks"] / (kern_ms / 1e3)},
+            "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob)},
+        }
+        traffic_file = os.path.join(ROOT, "profiles", "k_count_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as fh:
+                    out["roofline"]["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+            except Exception:
+                pass
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, dt, cpu_counts, _ = cpu_count_throughput(blob, chars, off, args.cpu_sample, threads)
+            assert np.array_equal(cpu_counts, h_counts[: cpu_counts.size]), "GPU counts differ from the CPU oracle"
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "first %d of the %d patterns, one pass, %.1fs (C++ restatement of the reference's Java loops; no JVM in this image)"
+                                             % (cpu_counts.size, n_pat, dt)}
+        print(json.dumps(out), flush=True)
+    ix.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -125,6 +125,12 @@ int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d
  * Used by bench.py for the roofline's algorithmic-bytes figure. */
 int fmgpu_last_stats(fmgpu_index* idx, uint64_t out6[6]);
 
+/* Measurement hooks (bench.py): with timing enabled every count/locate call brackets its backward-search
+ * kernel with CUDA events on the stream it is launched on; fmgpu_search_kernel_ms returns the device
+ * time of the kernel launched `calls_back` calls ago (0 = the most recent; up to 64 are kept). */
+int fmgpu_set_timing(fmgpu_index* idx, int enable);
+int fmgpu_search_kernel_ms(fmgpu_index* idx, uint32_t calls_back, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

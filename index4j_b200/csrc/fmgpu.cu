@@ -90,6 +90,11 @@ struct fmgpu_index {
     Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b;
     uint64_t last_launches = 0;
     bool stats_valid = false;
+    // optional per-call timing of the dominant kernel (bench.py's roofline): ring of event pairs
+    static constexpr int TIMING_SLOTS = 64;
+    bool timing = false;
+    cudaEvent_t ev0[TIMING_SLOTS] = {nullptr}, ev1[TIMING_SLOTS] = {nullptr};
+    uint64_t timed_calls = 0;
 };
 
 namespace {
@@ -135,9 +140,15 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
     unsigned int* ctrl = (unsigned int*)ix->ctrl.p;
     k_prepass<<<prepass_grid(total_chars > n_pat ? total_chars : n_pat, ix->sm_count), 256, 0, st>>>(
         d_chars, d_pat_off, n_pat, total_chars, ix->dev.char2code, (uint16_t*)ix->codes.p, (PatDesc*)ix->pats.p);
+    const int slot = (int)(ix->timed_calls % fmgpu_index::TIMING_SLOTS);
+    if (ix->timing) CU(cudaEventRecord(ix->ev0[slot], st));
     k_count<<<ix->count_ctas, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, (const uint16_t*)ix->codes.p, (const PatDesc*)ix->pats.p,
                                                                   n_pat, d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
                                                                   (unsigned long long*)(ctrl + CTRL_STATS));
+    if (ix->timing) {
+        CU(cudaEventRecord(ix->ev1[slot], st));
+        ix->timed_calls++;
+    }
     ix->last_launches += 2;
     CU(cudaGetLastError());
     return 0;
@@ -230,6 +241,10 @@ void fmgpu_index_free(fmgpu_index* ix) {
                        &ix->tmp_a, &ix->tmp_b})
         s->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
+    for (int i = 0; i < fmgpu_index::TIMING_SLOTS; ++i) {
+        if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
+        if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
+    }
     delete ix;
 }
 
@@ -275,6 +290,33 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
         if (status_out) CU(cudaMemcpyAsync(status_out, ix->out_b.p, (size_t)n_pat * 4, cudaMemcpyDeviceToHost, st));
     }
     CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int fmgpu_set_timing(fmgpu_index* ix, int enable) {
+    if (!ix) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (enable && !ix->ev0[0]) {
+        for (int i = 0; i < fmgpu_index::TIMING_SLOTS; ++i) {
+            CU(cudaEventCreate(&ix->ev0[i]));
+            CU(cudaEventCreate(&ix->ev1[i]));
+        }
+    }
+    ix->timing = enable != 0;
+    ix->timed_calls = 0;
+    return 0;
+}
+
+int fmgpu_search_kernel_ms(fmgpu_index* ix, uint32_t calls_back, float* ms_out) {
+    if (!ix || !ms_out) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!ix->ev0[0] || calls_back >= ix->timed_calls || calls_back >= (uint32_t)fmgpu_index::TIMING_SLOTS)
+        return fail(FMGPU_ERR_ARG, "no timing recorded for that call");
+    const int slot = (int)((ix->timed_calls - 1 - calls_back) % fmgpu_index::TIMING_SLOTS);
+    CU(cudaEventSynchronize(ix->ev1[slot]));
+    CU(cudaEventElapsedTime(ms_out, ix->ev0[slot], ix->ev1[slot]));
     return 0;
 }
 

@@ -91,6 +91,8 @@ def native():
         L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp, vp]
         L.fmgpu_last_stats.argtypes = [vp, vp]
+        L.fmgpu_set_timing.argtypes = [vp, i32]
+        L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
@@ -182,6 +184,19 @@ class FmIndex:
         self._check(self._lib.fmgpu_last_stats(self._h, out.ctypes.data))
         names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches"]
         return {k: int(v) for k, v in zip(names, out)}
+
+    def set_timing(self, enable: bool = True):
+        self._check(self._lib.fmgpu_set_timing(self._h, int(enable)))
+
+    def search_kernel_ms(self, calls_back: int = 0) -> float:
+        ms = C.c_float()
+        self._check(self._lib.fmgpu_search_kernel_ms(self._h, calls_back, C.byref(ms)))
+        return float(ms.value)
+
+    def count_batch_into(self, chars: np.ndarray, pat_off: np.ndarray, counts: np.ndarray, status: np.ndarray | None = None):
+        """``count_batch`` writing into caller-owned (e.g. pinned) buffers — the raw C-ABI call."""
+        self._check(self._lib.fmgpu_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, pat_off.size - 1, counts.ctypes.data,
+                                                status.ctypes.data if status is not None else None))
 
     # --- batched API (host buffers) ----------------------------------------------------------
     def count_batch(self, chars, pat_off, return_status: bool = False):
