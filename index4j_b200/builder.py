@@ -36,8 +36,40 @@ def _host():
         lib.fmhost_gen_log_text.argtypes = [C.c_void_p, C.c_int64, C.c_uint64]
         lib.fmhost_gen_patterns.argtypes = [C.c_void_p, C.c_int64, C.c_uint32, C.c_int32, C.c_int32, C.c_uint64,
                                             C.c_void_p, C.c_void_p]
+        lib.fmhost_build_wfbb.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        lib.fmhost_build_rrr.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         _lib = lib
     return _lib
+
+
+def _take(lib, rc, out, n) -> bytes:
+    if rc != 0:
+        raise ValueError(lib.fmhost_last_error().decode())
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib.fmhost_free(out)
+
+
+def build_wfbb(symbols, sampling_rate: int = 64, framed: bool = False) -> bytes:
+    """Serialized stand-alone ``WaveletFixedBlockBoosting`` (``new WaveletFixedBlockBoosting(short[]/char[] text, samplingRate)``)."""
+    lib = _host()
+    s = as_chars(symbols)
+    out, n = C.c_void_p(), C.c_uint64()
+    rc = lib.fmhost_build_wfbb(s.ctypes.data, s.size, sampling_rate, int(framed), 2, C.byref(out), C.byref(n))
+    return _take(lib, rc, out, n)
+
+
+def build_rrr(bits, sample_size: int = 32, framed: bool = False) -> bytes:
+    """Serialized stand-alone ``RrrVector`` over a 0/1 array (``new RrrVector(BitVector, sampleSize)``)."""
+    lib = _host()
+    b = np.ascontiguousarray(bits, dtype=np.uint8)
+    words = np.zeros((b.size + 63) // 64 + 1, dtype=np.uint64)
+    packed = np.packbits(b, bitorder="little")
+    words.view(np.uint8)[: packed.size] = packed
+    out, n = C.c_void_p(), C.c_uint64()
+    rc = lib.fmhost_build_rrr(words.ctypes.data, b.size, sample_size, int(framed), C.byref(out), C.byref(n))
+    return _take(lib, rc, out, n)
 
 
 def as_chars(text) -> np.ndarray:

@@ -374,6 +374,49 @@ int fmhost_build_with_sa(const uint16_t* text, int64_t n, const int32_t* sa, int
 
 void fmhost_free(void* p) { free(p); }
 
+static int emit(std::vector<uint8_t>& bytes, uint8_t** out, uint64_t* out_len) {
+    *out = (uint8_t*)malloc(bytes.size() ? bytes.size() : 1);
+    if (!*out) {
+        g_err = "out of memory";
+        return -2;
+    }
+    memcpy(*out, bytes.data(), bytes.size());
+    *out_len = bytes.size();
+    return 0;
+}
+
+// Stand-alone serialized WaveletFixedBlockBoosting over `syms` (values used as symbols directly, like
+// new WaveletFixedBlockBoosting(short[] text, int samplingRate), WaveletFixedBlockBoosting.java:130-154).
+int fmhost_build_wfbb(const uint16_t* syms, int64_t n, int32_t rrr_rate, int32_t framed, int32_t threads, uint8_t** out,
+                      uint64_t* out_len) {
+    if (n < 1) {
+        g_err = "Input length must be > 0";
+        return -1;
+    }
+    int32_t sigma = 0;
+    for (int64_t i = 0; i < n; ++i) sigma = std::max<int32_t>(sigma, syms[i]);
+    sigma += 1;
+    WfbbEnc w;
+    wfbb_encode(syms, n, sigma, rrr_rate, threads > 0 ? threads : 1, w);
+    JavaSink s(framed != 0);
+    write_wfbb(s, w);
+    s.finish();
+    return emit(s.out, out, out_len);
+}
+
+// Stand-alone serialized RrrVector over `nbits` LSB-first bits (new RrrVector(BitVector, sampleSize), RrrVector.java:225-286).
+int fmhost_build_rrr(const uint64_t* words, int64_t nbits, int32_t sample_size, int32_t framed, uint8_t** out, uint64_t* out_len) {
+    BitString bv;
+    bv.resize((uint64_t)nbits);
+    for (int64_t i = 0; i < (nbits + 63) / 64; ++i) bv.w[(size_t)i] = words[i];
+    RrrEnc r;
+    r.encode(bv, sample_size);
+    JavaSink s(framed != 0);
+    write_rrr(s, r);
+    s.finish();
+    return emit(s.out, out, out_len);
+}
+
 // First-appearance code mapping of a text (sentinel appended): what the suffix sorter must sort.
 // codes_out has n+1 entries.  Returns the number of codes (alphabet incl. sentinel).
 int32_t fmhost_map_text(const uint16_t* text, int64_t n, uint16_t* codes_out) {
