@@ -554,7 +554,7 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
         }
     });
     uint64_t blocks_total = 0, sectors_total = 0, nodes_total = 0, ovf_total = 0;
-    F.sb.resize(nsb);
+    F.sb.assign(nsb + 1, fmgpu::SbDesc{0, 16});  // +1: a lane may form the (unused) descriptor address of position == length
     for (size_t sb = 0; sb < nsb; ++sb) {
         SbPlan& P = plan[sb];
         P.first_block = (uint32_t)blocks_total;

@@ -83,147 +83,229 @@ __global__ void k_prepass(const uint16_t* __restrict__ chars, const uint64_t* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// Backward search.
+// Length bucketing: a warp runs 32 patterns of (nearly) equal length in lockstep, so the batch is
+// first ordered by pattern length with a counting sort (lengths >= LEN_BINS-1 share the last bin).
 // ---------------------------------------------------------------------------------------------
-enum CountPhase : uint32_t { CP_IDLE = 0, CP_FETCH, CP_CELL, CP_LEVEL, CP_OVF, CP_WAIT, CP_EXIT };
+constexpr uint32_t LEN_BINS = 1024;
+
+__global__ void __launch_bounds__(256) k_len_hist(const PatDesc* __restrict__ pats, uint32_t n_pat, uint32_t* __restrict__ bins) {
+    __shared__ uint32_t h[LEN_BINS];
+    for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pat; i += gridDim.x * blockDim.x) {
+        const uint32_t len = pats[i].len;
+        atomicAdd(&h[len < LEN_BINS - 1 ? len : LEN_BINS - 1], 1u);
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&bins[i], h[i]);
+}
+// exclusive scan of the bins, longest patterns first (they are the long poles of the launch)
+__global__ void __launch_bounds__(LEN_BINS) k_len_scan(uint32_t* __restrict__ bins) {
+    __shared__ uint32_t s[LEN_BINS];
+    const uint32_t t = threadIdx.x;
+    s[t] = bins[LEN_BINS - 1 - t];
+    __syncthreads();
+    for (uint32_t o = 1; o < LEN_BINS; o <<= 1) {
+        const uint32_t v = t >= o ? s[t - o] : 0u;
+        __syncthreads();
+        s[t] += v;
+        __syncthreads();
+    }
+    bins[LEN_BINS - 1 - t] = t ? s[t - 1] : 0u;
+}
+__global__ void __launch_bounds__(256) k_len_scatter(const PatDesc* __restrict__ pats, uint32_t n_pat, uint32_t* __restrict__ bins,
+                                                     uint32_t* __restrict__ order) {
+    // warp-aggregated cursor bump per distinct length inside the warp
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n_pat; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + lane;
+        const bool ok = i < n_pat;
+        uint32_t bin = LEN_BINS;
+        if (ok) {
+            const uint32_t len = pats[i].len;
+            bin = len < LEN_BINS - 1 ? len : LEN_BINS - 1;
+        }
+        const unsigned peers = __match_any_sync(FULL, bin);
+        const int leader = __ffs(peers) - 1;
+        uint32_t at = 0;
+        if ((int)lane == leader && ok) at = atomicAdd(&bins[bin], (uint32_t)__popc(peers));
+        at = __shfl_sync(FULL, at, leader);
+        if (ok) order[at + __popc(peers & ((1u << lane) - 1u))] = i;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward search (FmIndex.count, fm/FmIndex.java:455-474) — warp-lockstep.
+//
+// A warp takes 32 patterns of equal length from the length-ordered batch; lane = pattern.  All
+// lanes perform step k of their pattern together: one (block, symbol) cell fetch, then the level
+// loop.  The two rank queries of a step, rank(start, c) and rank(end, c), walk the SAME tree path
+// when start and end lie in the same block, so a lane carries both positions down one walk (one
+// sector fetch per level when they share a 224-bit sector, two otherwise); when the blocks differ
+// the lane runs a second walk.  The code is plain SIMT loops — the hardware reconverges the warp
+// after each level loop — which costs ~5x fewer issued instructions per rank than the lane state
+// machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...: issue-bound at 43-47 %
+// lane utilisation); the price is that a step lasts as long as its deepest walk.
+// ---------------------------------------------------------------------------------------------
+struct WalkOut {
+    uint32_t a, b, err;
+};
+
+// one wavelet level for two positions of the same node (WaveletFixedBlockBoosting.java:1185-1279)
+__device__ __forceinline__ void level_pair(const DevIndex& ix, uint32_t node, uint32_t bit, uint32_t& ra, uint32_t& rb, uint32_t& n_load) {
+    const uint32_t qa = ra / SECTOR_BITS, qb = rb / SECTOR_BITS;
+    const Rec32 A = ld256(ix.sectors + (node + qa));
+    Rec32 B = A;
+    if (qb != qa) B = ld256(ix.sectors + (node + qb));
+    n_load += qb != qa ? 2u : 1u;
+    const uint32_t ones_a = sector_rank(A, ra - qa * SECTOR_BITS);
+    const uint32_t ones_b = sector_rank(B, rb - qb * SECTOR_BITS);
+    ra = bit ? ones_a : ra - ones_a;
+    rb = bit ? ones_b : rb - ones_b;
+}
+
+// rank(., c) of two positions of ONE block: ra/rb are block-relative positions (rb == ra for a single query)
+__device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, uint32_t c, uint32_t ra, uint32_t rb, bool on,
+                                             uint32_t queries, uint32_t& n_level, uint32_t& n_load) {
+    WalkOut o;
+    o.a = o.b = o.err = 0;
+    if (!on) return o;
+    const Rec32 cell = ld256(ix.cells + ((uint64_t)blk * ix.sigma + c));
+    ++n_load;
+    const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
+    const uint32_t base = cell.w[0];
+    if (kind != CELL_NORMAL) {
+        const uint32_t run = kind == CELL_RUN ? 0xffffffffu : 0u;  // :1141-1146
+        o.a = base + (ra & run);
+        o.b = base + (rb & run);
+        o.err = kind == CELL_THROW;
+        return o;
+    }
+    const uint32_t code = cell.w[1];
+    const uint32_t L = cell.w[2] & 0xffu;
+    const uint32_t inl = L > CELL_INLINE_LEVELS ? 4u : L;
+#pragma unroll
+    for (uint32_t d = 0; d < CELL_INLINE_LEVELS; ++d)
+        if (d < inl) level_pair(ix, cell.w[3 + d], (code >> (L - 1u - d)) & 1u, ra, rb, n_load);
+    if (L > CELL_INLINE_LEVELS) {  // deep codes (rare symbols): the rest of the path is in the overflow array
+        const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);
+        for (uint32_t d = 4; d < L; ++d) level_pair(ix, __ldg(more + (d - 4u)), (code >> (L - 1u - d)) & 1u, ra, rb, n_load);
+    }
+    n_level += L * queries;
+    o.a = base + ra;
+    o.b = base + rb;
+    return o;
+}
 
 __global__ void __launch_bounds__(CTA_THREADS)
-k_count(const DevIndex ix, const uint16_t* __restrict__ codes, const PatDesc* __restrict__ pats, uint32_t n_pat,
-        int32_t* __restrict__ counts, int32_t* __restrict__ status, uint32_t* __restrict__ ranges, unsigned int* queue,
+k_count(const DevIndex ix, const uint16_t* __restrict__ codes, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,
+        uint32_t n_pat, int32_t* __restrict__ counts, int32_t* __restrict__ status, uint32_t* __restrict__ ranges, unsigned int* queue,
         unsigned long long* stats) {
     extern __shared__ uint32_t smem[];
     const SmemTables T = stage_tables(ix, smem);
     const unsigned lane = threadIdx.x & 31u;
-    const bool odd = lane & 1u;
-    const unsigned pair_shift = lane & ~1u;
-
-    uint32_t phase = CP_IDLE;
-    uint32_t pat = 0, sp = 0, ep = 0, c = 0, cnext = 0, val = 0, err = 0;
-    int32_t i = 0;
-    uint64_t off = 0;
-    const Rec32* addr = nullptr;
-    RankSt rs;
-    rs.p5 = rs.p6 = rs.p7 = 0;
-    uint32_t n_rank = 0, n_level = 0;
+    uint32_t n_rank = 0, n_level = 0, n_load = 0;
 
     for (;;) {
-        // refill idle pairs from the global queue (one atomic per warp)
-        const unsigned idle = __ballot_sync(FULL, phase == CP_IDLE && !odd);
-        if (idle) {
-            const int leader = __ffs(idle) - 1;
-            unsigned base = 0;
-            if ((int)lane == leader) base = atomicAdd(queue, (unsigned)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            const unsigned mine = base + __popc(idle & ((1u << lane) - 1u));
-            const unsigned got = __shfl_sync(FULL, mine, pair_shift);
-            if (phase == CP_IDLE) {
-                pat = got;
-                if (pat < n_pat) {
-                    phase = CP_FETCH;
-                    addr = reinterpret_cast<const Rec32*>(pats) + (pat >> 1);
-                } else {
-                    phase = CP_EXIT;
-                }
-            }
+        unsigned batch = 0;
+        if (lane == 0) batch = atomicAdd(queue, 1u);
+        batch = __shfl_sync(FULL, batch, 0);
+        if ((uint64_t)batch * 32u >= n_pat) break;
+        const uint32_t slot = batch * 32u + lane;
+        const bool have = slot < n_pat;
+        const uint32_t pat = have ? order[slot] : 0u;
+        PatDesc pd;
+        pd.off = 0;
+        pd.len = 0;
+        pd.last = 0;
+        if (have) pd = pats[pat];
+
+        uint32_t c = pd.last, sp = 0, ep = 0, err = 0;
+        int32_t i = (int32_t)pd.len - 1;
+        bool alive = have;
+        if (have && pd.len == 0) {  // pattern[-1]: ArrayIndexOutOfBounds (FmIndex.java:456-457)
+            err = 1;
+            alive = false;
+        } else if (have && c == 0) {  // :458
+            alive = false;
+        } else if (have) {
+            sp = T.C[c];
+            ep = T.C[c + 1];
         }
-        if (!__any_sync(FULL, phase != CP_EXIT)) break;
+        uint32_t cnext = (alive && i >= 1) ? (uint32_t)__ldg(codes + pd.off + (uint64_t)(i - 1)) : 0u;
 
-        Rec32 A;
-        if (phase >= CP_FETCH && phase <= CP_OVF) A = ld256(addr);
-
-        bool step = false;  // (sp, ep, i) hold a fresh range: decide how the pattern goes on
-        if (phase == CP_FETCH) {
-            const bool hi = pat & 1u;
-            off = (uint64_t)(hi ? A.w[4] : A.w[0]) | ((uint64_t)(hi ? A.w[5] : A.w[1]) << 32);
-            const uint32_t len = hi ? A.w[6] : A.w[2];
-            c = hi ? A.w[7] : A.w[3];
-            i = (int32_t)len - 1;
-            err = 0;
-            if (len == 0) {  // pattern[-1]: ArrayIndexOutOfBounds (FmIndex.java:456-457)
-                err = 1;
-                sp = ep = 0;
-            } else if (c == 0) {  // :458
-                sp = ep = 0;
-                i = 0;
+        for (;;) {
+            // :464  while (start < end && i >= offset + 1)
+            bool go = alive && sp < ep && i >= 1;
+            if (go) {
+                --i;
+                c = cnext;
+                if (c == 0 || c >= ix.sigma) {  // :466-468 unknown symbol => 0 ; rank of a symbol >= sigma is 0 => empty range
+                    sp = ep = 0;
+                    alive = false;
+                    go = false;
+                } else if (ix.q4 && ep >= ix.length) {  // rank(size, .) on a superblock boundary throws (:1022-1026)
+                    err = 1;
+                    alive = false;
+                    go = false;
+                }
             } else {
-                sp = T.C[c];
-                ep = T.C[c + 1];
-                cnext = i >= 1 ? (uint32_t)__ldg(codes + off + (uint64_t)(i - 1)) : 0u;
+                alive = false;
             }
-            step = true;
-        } else if (phase == CP_CELL) {
-            ++n_rank;
-            const uint32_t o = rank_on_cell(ix, A, rs, &addr, &val);
-            if (o == RK_MORE) phase = CP_LEVEL;
-            else {
-                phase = CP_WAIT;
-                err |= (o == RK_THROW);
-            }
-        } else if (phase == CP_LEVEL) {
-            ++n_level;
-            bool want_ovf = false;
-            const uint32_t o = rank_on_level(ix, A, rs, &addr, &val, &want_ovf);
-            if (o == RK_DONE) phase = CP_WAIT;
-            else if (want_ovf) phase = CP_OVF;
-        } else if (phase == CP_OVF) {
-            rank_on_ovf(ix, A, rs, &addr);
-            phase = CP_LEVEL;
-        }
+            if (!__any_sync(FULL, go)) break;
+            if (go && i >= 1) cnext = (uint32_t)__ldg(codes + pd.off + (uint64_t)(i - 1));
 
-        // the two ranks of a step meet here
-        const unsigned waitm = __ballot_sync(FULL, phase == CP_WAIT);
-        const unsigned errm = __ballot_sync(FULL, err != 0);
-        const uint32_t mine = T.C[c] + val;  // :469-470
-        const uint32_t theirs = __shfl_xor_sync(FULL, mine, 1);
-        if (((waitm >> pair_shift) & 3u) == 3u) {
-            sp = odd ? theirs : mine;
-            ep = odd ? mine : theirs;
-            err = (errm >> pair_shift) & 3u;
-            step = true;
-        }
-        if (step) {
-            bool finished = true;
-            int32_t result = 0;
-            if (!err) {
-                if (sp < ep && i >= 1) {  // :464
-                    --i;
-                    c = cnext;
-                    if (c != 0) {  // :466-468: unknown symbol => 0
-                        finished = false;
-                        cnext = i >= 1 ? (uint32_t)__ldg(codes + off + (uint64_t)(i - 1)) : 0u;
-                        const uint32_t o = rank_begin(ix, T, odd ? ep : sp, c, rs, &addr, &val);
-                        if (o == RK_MORE) phase = CP_CELL;
-                        else {
-                            phase = CP_WAIT;
-                            err = (o == RK_THROW);
-                        }
-                    }
+            // block of each position; start == 0 needs no query (rank(0, c) == 0, :1012)
+            const SbDesc se = T.sb[ep >> SB_LOG];
+            const uint32_t blk_e = se.first_block + ((ep & SB_MASK) >> se.block_log);
+            const uint32_t re = ep & ((1u << se.block_log) - 1u);
+            const SbDesc ss = T.sb[sp >> SB_LOG];
+            const uint32_t blk_s = ss.first_block + ((sp & SB_MASK) >> ss.block_log);
+            const uint32_t rs = sp & ((1u << ss.block_log) - 1u);
+            const bool with_s = sp != 0u && blk_s == blk_e;
+            const bool second = go && sp != 0u && blk_s != blk_e;
+            n_rank += go ? (sp != 0u ? 2u : 1u) : 0u;
+
+            const WalkOut w1 = walk_pair(ix, blk_e, c, with_s ? rs : re, re, go, with_s ? 2u : 1u, n_level, n_load);
+            uint32_t val_s = with_s ? w1.a : 0u;
+            const uint32_t val_e = w1.b;
+            uint32_t e2 = 0;
+            if (__any_sync(FULL, second)) {
+                const WalkOut w2 = walk_pair(ix, blk_s, c, rs, rs, second, 1u, n_level, n_load);
+                if (second) val_s = w2.a;
+                e2 = w2.err;
+            }
+            if (go) {
+                if (w1.err | e2) {
+                    err = 1;
+                    alive = false;
                 } else {
-                    result = ep > sp ? (int32_t)(ep - sp) : 0;  // :473
+                    sp = T.C[c] + val_s;  // :469-470
+                    ep = T.C[c] + val_e;
                 }
             }
-            if (finished) {
-                if (!odd) {
-                    counts[pat] = err ? 0 : result;
-                    if (status) status[pat] = err ? 9 : 0;
-                    if (ranges) {
-                        ranges[2 * (uint64_t)pat] = sp;
-                        ranges[2 * (uint64_t)pat + 1] = (!err && result > 0) ? ep : sp;
-                    }
-                }
-                phase = CP_IDLE;
+        }
+        if (have) {
+            const int32_t result = (!err && ep > sp) ? (int32_t)(ep - sp) : 0;  // :473
+            counts[pat] = result;
+            if (status) status[pat] = err ? 9 : 0;
+            if (ranges) {
+                ranges[2 * (uint64_t)pat] = sp;
+                ranges[2 * (uint64_t)pat + 1] = result > 0 ? ep : sp;
             }
         }
     }
 
-    // work counters (roofline accounting): warp-reduce, one atomic pair per warp
     for (int o = 16; o; o >>= 1) {
         n_rank += __shfl_xor_sync(FULL, n_rank, o);
         n_level += __shfl_xor_sync(FULL, n_level, o);
+        n_load += __shfl_xor_sync(FULL, n_load, o);
     }
     if (lane == 0 && stats) {
         atomicAdd(stats + 0, (unsigned long long)n_rank);
         atomicAdd(stats + 1, (unsigned long long)n_level);
+        atomicAdd(stats + 6, (unsigned long long)n_load);
     }
 }
 

@@ -38,15 +38,23 @@ FMGPU_HD uint32_t rec_word(const Rec32& s, uint32_t k) {
     return v;
 }
 
+// mask of the low min(max(width, 0), 32) bits
+FMGPU_HD uint32_t low_mask_clamped(int width) {
+#if defined(__CUDA_ARCH__)
+    uint32_t m;
+    const uint32_t w = (uint32_t)(width > 0 ? width : 0);
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(m) : "r"(0u), "r"(w));
+    return m;
+#else
+    return width >= 32 ? 0xffffffffu : (width <= 0 ? 0u : ((1u << width) - 1u));
+#endif
+}
+
 // ones among the first `nbits` (< 224) payload bits of a level sector, plus its running count
 FMGPU_HD uint32_t sector_rank(const Rec32& s, uint32_t nbits) {
     uint32_t ones = s.w[0];
 #pragma unroll
-    for (int k = 0; k < 7; ++k) {
-        const int rem = (int)nbits - 32 * k;
-        const uint32_t m = rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
-        ones += popc32(s.w[1 + k] & m);
-    }
+    for (int k = 0; k < 7; ++k) ones += popc32(s.w[1 + k] & low_mask_clamped((int)nbits - 32 * k));
     return ones;
 }
 FMGPU_HD uint32_t sector_bit(const Rec32& s, uint32_t b) { return (rec_word(s, 1u + (b >> 5)) >> (b & 31u)) & 1u; }

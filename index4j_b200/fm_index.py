@@ -180,9 +180,9 @@ class FmIndex:
         return {k: int(v) for k, v in zip(names, out)}
 
     def last_stats(self) -> dict:
-        out = np.zeros(6, dtype=np.uint64)
+        out = np.zeros(8, dtype=np.uint64)
         self._check(self._lib.fmgpu_last_stats(self._h, out.ctypes.data))
-        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches"]
+        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "reserved"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def set_timing(self, enable: bool = True):

@@ -256,3 +256,74 @@ void fc_unrank_table(uint16_t* out32768) {
 }
 
 }  // extern "C"
+
+// ---- design aid (not a test): cost model of a warp-lockstep backward search.  Patterns are taken in groups
+// of 32 in the given order; per step the warp needs 1 cell trip + max over its lanes of the level count.
+extern "C" void fc_lockstep_sim(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, uint64_t* out8) {
+    FC& h = *(FC*)hv;
+    uint64_t warp_steps = 0, sum_max = 0, lane_steps = 0, sum_levels = 0, diff_steps = 0, hist[16] = {0};
+    for (uint32_t g = 0; g < n_pat; g += 32) {
+        const uint32_t m = std::min<uint32_t>(32, n_pat - g);
+        uint32_t sp[32], ep[32];
+        int64_t i[32];
+        bool alive[32];
+        int64_t maxlen = 0;
+        for (uint32_t l = 0; l < m; ++l) {
+            const uint64_t a = pat_off[g + l], b = pat_off[g + l + 1];
+            i[l] = (int64_t)(b - a) - 1;
+            alive[l] = i[l] >= 0;
+            if (alive[l]) {
+                const uint32_t c = h.ix.char2code[chars[b - 1]];
+                if (!c) alive[l] = false;
+                else {
+                    sp[l] = h.ix.C[c];
+                    ep[l] = h.ix.C[c + 1];
+                }
+            }
+            maxlen = std::max<int64_t>(maxlen, i[l]);
+        }
+        for (int64_t s = 0; s < maxlen; ++s) {
+            uint32_t mx = 0;
+            bool any = false;
+            for (uint32_t l = 0; l < m; ++l) {
+                if (!alive[l]) continue;
+                if (!(sp[l] < ep[l] && i[l] >= 1)) {
+                    alive[l] = false;
+                    continue;
+                }
+                const uint32_t c = h.ix.char2code[chars[pat_off[g + l] + (uint64_t)(--i[l])]];
+                if (!c) {
+                    alive[l] = false;
+                    continue;
+                }
+                any = true;
+                uint64_t r1 = 0, l1 = 0, r2 = 0, l2 = 0;
+                uint32_t a = 0, b = 0;
+                host_rank(h, sp[l], c, &a, &r1, &l1);
+                host_rank(h, ep[l], c, &b, &r2, &l2);
+                const bool diff = (sp[l] >> 9) != (ep[l] >> 9) && sp[l] != 0 &&
+                                  ((sp[l] >> 16) != (ep[l] >> 16));  // rough: different 64K block
+                uint32_t lv = (uint32_t)std::max(l1, l2);
+                if (diff) {
+                    lv = (uint32_t)(l1 + l2) + 1;  // two sequential walks
+                    ++diff_steps;
+                }
+                mx = std::max(mx, lv);
+                sum_levels += l1 + l2;
+                hist[std::min<uint64_t>(15, l2)]++;
+                ++lane_steps;
+                sp[l] = h.ix.C[c] + a;
+                ep[l] = h.ix.C[c] + b;
+            }
+            if (!any) break;
+            ++warp_steps;
+            sum_max += mx;
+        }
+    }
+    out8[0] = warp_steps;
+    out8[1] = sum_max;
+    out8[2] = lane_steps;
+    out8[3] = sum_levels;
+    out8[4] = diff_steps;
+    for (int k = 0; k < 16; ++k) out8[8 + k] = hist[k];
+}
