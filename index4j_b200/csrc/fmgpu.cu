@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -86,7 +87,9 @@ struct fmgpu_index {
     int count_ctas = 0, lf_ctas = 0;
     size_t tables_smem = 0;
     std::mutex mu;  // batch calls on one handle are serialised (v0)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, down_stream = nullptr;
+    static constexpr int PIPE_SLOTS = 8;
+    cudaEvent_t pipe_in[PIPE_SLOTS] = {nullptr}, pipe_out[PIPE_SLOTS] = {nullptr};
     Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b, order, bins;
     uint64_t last_launches = 0;
     bool stats_valid = false;
@@ -128,37 +131,41 @@ int prepass_grid(uint64_t items, int sm_count) {
     return (int)g;
 }
 
+// Backward search over n_pat patterns on stream `st`.  `first_of_call` resets the work counters; later
+// chunks of the same call only re-arm the work queue.
 int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars, uint32_t n_pat,
-                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st) {
-    CU(ix->codes.reserve((size_t)total_chars * 2 + 64));
+                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st, bool first_of_call = true) {
+    (void)total_chars;
     CU(ix->pats.reserve(((size_t)n_pat + 2) * sizeof(PatDesc)));
     CU(ix->ctrl.reserve(CTRL_WORDS * 4));
     CU(ix->order.reserve((size_t)n_pat * 4 + 64));
     CU(ix->bins.reserve(LEN_BINS * 4));
-    CU(cudaMemsetAsync(ix->ctrl.p, 0, CTRL_WORDS * 4, st));
-    CU(cudaMemsetAsync(ix->bins.p, 0, LEN_BINS * 4, st));
-    ix->last_launches = 0;
-    ix->stats_valid = true;
+    if (first_of_call) {
+        CU(cudaMemsetAsync(ix->ctrl.p, 0, CTRL_WORDS * 4, st));
+        ix->last_launches = 0;
+        ix->stats_valid = true;
+    } else {
+        CU(cudaMemsetAsync(ix->ctrl.p, 0, 8, st));  // the two queue heads
+    }
     if (n_pat == 0) return 0;
+    CU(cudaMemsetAsync(ix->bins.p, 0, LEN_BINS * 4, st));
     unsigned int* ctrl = (unsigned int*)ix->ctrl.p;
-    k_prepass<<<prepass_grid(total_chars > n_pat ? total_chars : n_pat, ix->sm_count), 256, 0, st>>>(
-        d_chars, d_pat_off, n_pat, total_chars, ix->dev.char2code, (uint16_t*)ix->codes.p, (PatDesc*)ix->pats.p);
-    // order the batch by pattern length (counting sort) so that a warp's 32 patterns run in lockstep
-    const int sort_grid = prepass_grid(n_pat, ix->sm_count);
-    k_len_hist<<<sort_grid, 256, 0, st>>>((const PatDesc*)ix->pats.p, n_pat, (uint32_t*)ix->bins.p);
+    // descriptors + length histogram, then a counting sort by length so that a warp's 32 patterns run in lockstep
+    const int pre_grid = prepass_grid(n_pat, ix->sm_count);
+    k_prepass<<<pre_grid, 256, 0, st>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)ix->pats.p, (uint32_t*)ix->bins.p);
     k_len_scan<<<1, LEN_BINS, 0, st>>>((uint32_t*)ix->bins.p);
-    k_len_scatter<<<sort_grid, 256, 0, st>>>((const PatDesc*)ix->pats.p, n_pat, (uint32_t*)ix->bins.p, (uint32_t*)ix->order.p);
-    ix->last_launches += 3;
+    const int sc_grid = prepass_grid(((uint64_t)n_pat + SCATTER_PER_THREAD - 1) / SCATTER_PER_THREAD, ix->sm_count);
+    k_len_scatter<<<sc_grid, 256, 0, st>>>((const PatDesc*)ix->pats.p, n_pat, (uint32_t*)ix->bins.p, (uint32_t*)ix->order.p);
     const int slot = (int)(ix->timed_calls % fmgpu_index::TIMING_SLOTS);
     if (ix->timing) CU(cudaEventRecord(ix->ev0[slot], st));
-    k_count<<<ix->count_ctas, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, (const uint16_t*)ix->codes.p, (const PatDesc*)ix->pats.p,
+    k_count<<<ix->count_ctas, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)ix->pats.p,
                                                                   (const uint32_t*)ix->order.p, n_pat, d_counts, d_status, d_ranges,
                                                                   ctrl + CTRL_QUEUE, (unsigned long long*)(ctrl + CTRL_STATS));
     if (ix->timing) {
         CU(cudaEventRecord(ix->ev1[slot], st));
         ix->timed_calls++;
     }
-    ix->last_launches += 2;
+    ix->last_launches += 4;
     CU(cudaGetLastError());
     return 0;
 }
@@ -232,8 +239,19 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
         rc = grid_for((const void*)k_count, ix->sm_count, ix->tables_smem, &ix->count_ctas);
     }
     if (!rc) rc = lf_setup(ix);
-    if (!rc && cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess)
+    if (!rc && (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+                cudaStreamCreateWithFlags(&ix->down_stream, cudaStreamNonBlocking) != cudaSuccess))
         rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreate failed");
+    for (int i = 0; !rc && i < fmgpu_index::PIPE_SLOTS; ++i)
+        if (cudaEventCreateWithFlags(&ix->pipe_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ix->pipe_out[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(FMGPU_ERR_CUDA, "cudaEventCreate failed");
+    if (!rc) {
+        // optional experiment knob: L2 fetch granularity for the random 32-byte record gathers
+        const char* g = getenv("FMGPU_L2_FETCH");
+        if (g && atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    }
     if (rc) {
         fmgpu_index_free(ix);
         return rc;
@@ -250,6 +268,12 @@ void fmgpu_index_free(fmgpu_index* ix) {
                        &ix->tmp_a, &ix->tmp_b, &ix->order, &ix->bins})
         s->release();
     if (ix->stream) cudaStreamDestroy(ix->stream);
+    if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
+    if (ix->down_stream) cudaStreamDestroy(ix->down_stream);
+    for (int i = 0; i < fmgpu_index::PIPE_SLOTS; ++i) {
+        if (ix->pipe_in[i]) cudaEventDestroy(ix->pipe_in[i]);
+        if (ix->pipe_out[i]) cudaEventDestroy(ix->pipe_out[i]);
+    }
     for (int i = 0; i < fmgpu_index::TIMING_SLOTS; ++i) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
         if (ix->ev1[i]) cudaEventDestroy(ix->ev1[i]);
@@ -284,20 +308,45 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", ix->device);
-    cudaStream_t st = ix->stream;
+    cudaStream_t st = ix->stream, cp = ix->copy_stream;
     CU(ix->in_a.reserve((size_t)total * 2 + 64));
     CU(ix->in_b.reserve(((size_t)n_pat + 1) * 8));
     CU(ix->out_a.reserve((size_t)n_pat * 4 + 64));
     CU(ix->out_b.reserve((size_t)n_pat * 4 + 64));
-    if (total) CU(cudaMemcpyAsync(ix->in_a.p, chars, (size_t)total * 2, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(ix->in_b.p, pat_off, ((size_t)n_pat + 1) * 8, cudaMemcpyHostToDevice, st));
-    int rc = count_on_stream(ix, (const uint16_t*)ix->in_a.p, (const uint64_t*)ix->in_b.p, total, n_pat, (int32_t*)ix->out_a.p,
-                             (int32_t*)ix->out_b.p, nullptr, st);
-    if (rc) return rc;
-    if (n_pat) {
-        CU(cudaMemcpyAsync(counts_out, ix->out_a.p, (size_t)n_pat * 4, cudaMemcpyDeviceToHost, st));
-        if (status_out) CU(cudaMemcpyAsync(status_out, ix->out_b.p, (size_t)n_pat * 4, cudaMemcpyDeviceToHost, st));
+    // The batch is cut into chunks so that the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels
+    // of chunk k (copy stream + compute stream, events in between).  Chunk chars land at their absolute offsets in the
+    // device buffer, so pattern offsets need no rebasing.
+    uint32_t min_chunk = 350000;
+    if (const char* e = getenv("FMGPU_PIPE_CHUNK")) min_chunk = (uint32_t)atoi(e) > 0 ? (uint32_t)atoi(e) : min_chunk;
+    uint32_t n_chunks = n_pat / min_chunk;
+    if (n_chunks > (uint32_t)fmgpu_index::PIPE_SLOTS) n_chunks = fmgpu_index::PIPE_SLOTS;
+    if (n_chunks < 1) n_chunks = 1;
+    uint16_t* d_chars = (uint16_t*)ix->in_a.p;
+    uint64_t* d_off = (uint64_t*)ix->in_b.p;
+    int32_t* d_counts = (int32_t*)ix->out_a.p;
+    int32_t* d_status = (int32_t*)ix->out_b.p;
+    for (uint32_t k = 0; k < n_chunks; ++k) {  // all uploads are queued first: they only depend on the host buffers
+        const uint32_t lo = (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
+        const uint64_t c0 = pat_off[lo], c1 = pat_off[hi];
+        if (c1 > c0) CU(cudaMemcpyAsync(d_chars + c0, chars + c0, (size_t)(c1 - c0) * 2, cudaMemcpyHostToDevice, cp));
+        CU(cudaMemcpyAsync(d_off + lo, pat_off + lo, ((size_t)(hi - lo) + 1) * 8, cudaMemcpyHostToDevice, cp));
+        CU(cudaEventRecord(ix->pipe_in[k], cp));
     }
+    for (uint32_t k = 0; k < n_chunks; ++k) {
+        const uint32_t lo = (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
+        CU(cudaStreamWaitEvent(st, ix->pipe_in[k], 0));
+        int rc = count_on_stream(ix, d_chars, d_off + lo, total, hi - lo, d_counts + lo, d_status + lo, nullptr, st, k == 0);
+        if (rc) return rc;
+        CU(cudaEventRecord(ix->pipe_out[k], st));
+        CU(cudaStreamWaitEvent(ix->down_stream, ix->pipe_out[k], 0));
+        if (hi > lo) {
+            CU(cudaMemcpyAsync(counts_out + lo, d_counts + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ix->down_stream));
+            if (status_out)
+                CU(cudaMemcpyAsync(status_out + lo, d_status + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ix->down_stream));
+        }
+    }
+    CU(cudaStreamSynchronize(ix->down_stream));
+    CU(cudaStreamSynchronize(cp));
     CU(cudaStreamSynchronize(st));
     return 0;
 }

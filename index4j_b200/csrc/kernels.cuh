@@ -64,37 +64,27 @@ inline size_t tables_smem_bytes(const DevIndex& ix) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Pre-pass: UTF-16 units -> alphabet codes (monotonicMap.getOrDefault(ch, 0), FmIndex.java:457,465)
-// and one descriptor per pattern.  Fully coalesced; negligible next to the search.
+// Pre-pass: one descriptor per pattern (offset, length, alphabet code of the last char =
+// monotonicMap.getOrDefault(ch, 0), FmIndex.java:457) and the histogram of pattern lengths.
+// A warp runs 32 patterns of (nearly) equal length in lockstep, so the batch is ordered by length
+// with a counting sort (lengths >= LEN_BINS-1 share the last bin).
 // ---------------------------------------------------------------------------------------------
-__global__ void k_prepass(const uint16_t* __restrict__ chars, const uint64_t* __restrict__ pat_off, uint32_t n_pat, uint64_t total_chars,
-                          const uint16_t* __restrict__ char2code, uint16_t* __restrict__ codes, PatDesc* __restrict__ pats) {
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t t0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t i = t0; i < total_chars; i += stride) codes[i] = __ldg(char2code + chars[i]);
-    for (uint64_t i = t0; i < n_pat; i += stride) {
+constexpr uint32_t LEN_BINS = 1024;
+
+__global__ void __launch_bounds__(256) k_prepass(const uint16_t* __restrict__ chars, const uint64_t* __restrict__ pat_off, uint32_t n_pat,
+                                                 const uint16_t* __restrict__ char2code, PatDesc* __restrict__ pats,
+                                                 uint32_t* __restrict__ bins) {
+    __shared__ uint32_t h[LEN_BINS];
+    for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pat; i += gridDim.x * blockDim.x) {
         const uint64_t a = pat_off[i], b = pat_off[i + 1];
         PatDesc d;
         d.off = a;
         d.len = b > a ? (uint32_t)(b - a) : 0u;
         d.last = d.len ? (uint32_t)__ldg(char2code + chars[b - 1]) : 0u;
         pats[i] = d;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Length bucketing: a warp runs 32 patterns of (nearly) equal length in lockstep, so the batch is
-// first ordered by pattern length with a counting sort (lengths >= LEN_BINS-1 share the last bin).
-// ---------------------------------------------------------------------------------------------
-constexpr uint32_t LEN_BINS = 1024;
-
-__global__ void __launch_bounds__(256) k_len_hist(const PatDesc* __restrict__ pats, uint32_t n_pat, uint32_t* __restrict__ bins) {
-    __shared__ uint32_t h[LEN_BINS];
-    for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x) h[i] = 0;
-    __syncthreads();
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pat; i += gridDim.x * blockDim.x) {
-        const uint32_t len = pats[i].len;
-        atomicAdd(&h[len < LEN_BINS - 1 ? len : LEN_BINS - 1], 1u);
+        atomicAdd(&h[d.len < LEN_BINS - 1 ? d.len : LEN_BINS - 1], 1u);
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x)
@@ -114,24 +104,38 @@ __global__ void __launch_bounds__(LEN_BINS) k_len_scan(uint32_t* __restrict__ bi
     }
     bins[LEN_BINS - 1 - t] = t ? s[t - 1] : 0u;
 }
+// Scatter pattern ids into length order.  A block ranks its tile inside shared memory (the value returned by the
+// shared-memory atomic is the pattern's rank among the block's patterns of that length) and takes ONE global
+// atomic per (block, length) for the base, instead of one per pattern on ~60 hot addresses.
+constexpr uint32_t SCATTER_PER_THREAD = 8;
 __global__ void __launch_bounds__(256) k_len_scatter(const PatDesc* __restrict__ pats, uint32_t n_pat, uint32_t* __restrict__ bins,
                                                      uint32_t* __restrict__ order) {
-    // warp-aggregated cursor bump per distinct length inside the warp
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; base < n_pat; base += gridDim.x * blockDim.x) {
-        const uint32_t i = base + lane;
-        const bool ok = i < n_pat;
-        uint32_t bin = LEN_BINS;
-        if (ok) {
-            const uint32_t len = pats[i].len;
-            bin = len < LEN_BINS - 1 ? len : LEN_BINS - 1;
+    __shared__ uint32_t h[LEN_BINS];
+    const uint32_t tile = 256u * SCATTER_PER_THREAD;
+    for (uint32_t base = blockIdx.x * tile; base < n_pat; base += gridDim.x * tile) {
+        for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x) h[i] = 0;
+        __syncthreads();
+        uint32_t bin[SCATTER_PER_THREAD], rk[SCATTER_PER_THREAD];
+#pragma unroll
+        for (uint32_t k = 0; k < SCATTER_PER_THREAD; ++k) {
+            const uint32_t i = base + k * 256u + threadIdx.x;
+            bin[k] = LEN_BINS;
+            if (i < n_pat) {
+                const uint32_t len = pats[i].len;
+                bin[k] = len < LEN_BINS - 1 ? len : LEN_BINS - 1;
+                rk[k] = atomicAdd(&h[bin[k]], 1u);
+            }
         }
-        const unsigned peers = __match_any_sync(FULL, bin);
-        const int leader = __ffs(peers) - 1;
-        uint32_t at = 0;
-        if ((int)lane == leader && ok) at = atomicAdd(&bins[bin], (uint32_t)__popc(peers));
-        at = __shfl_sync(FULL, at, leader);
-        if (ok) order[at + __popc(peers & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x)
+            if (h[i]) h[i] = atomicAdd(&bins[i], h[i]);
+        __syncthreads();
+#pragma unroll
+        for (uint32_t k = 0; k < SCATTER_PER_THREAD; ++k) {
+            const uint32_t i = base + k * 256u + threadIdx.x;
+            if (bin[k] < LEN_BINS) order[h[bin[k]] + rk[k]] = i;
+        }
+        __syncthreads();
     }
 }
 
@@ -198,8 +202,11 @@ __device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, u
     return o;
 }
 
-__global__ void __launch_bounds__(CTA_THREADS)
-k_count(const DevIndex ix, const uint16_t* __restrict__ codes, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,
+#ifndef COUNT_MIN_CTAS
+#define COUNT_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, COUNT_MIN_CTAS)
+k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,
         uint32_t n_pat, int32_t* __restrict__ counts, int32_t* __restrict__ status, uint32_t* __restrict__ ranges, unsigned int* queue,
         unsigned long long* stats) {
     extern __shared__ uint32_t smem[];
@@ -233,7 +240,11 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ codes, const PatDesc* __
             sp = T.C[c];
             ep = T.C[c + 1];
         }
-        uint32_t cnext = (alive && i >= 1) ? (uint32_t)__ldg(codes + pd.off + (uint64_t)(i - 1)) : 0u;
+        // the pattern's chars are mapped to alphabet codes on the fly, fetched two steps ahead (raw char) and one
+        // step ahead (its code) so that neither load is on the step's critical path
+        const uint16_t* pch = chars + pd.off;
+        uint32_t cnext = (alive && i >= 1) ? (uint32_t)__ldg(ix.char2code + __ldg(pch + (i - 1))) : 0u;
+        uint32_t raw2 = (alive && i >= 2) ? (uint32_t)__ldg(pch + (i - 2)) : 0u;
 
         for (;;) {
             // :464  while (start < end && i >= offset + 1)
@@ -254,7 +265,8 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ codes, const PatDesc* __
                 alive = false;
             }
             if (!__any_sync(FULL, go)) break;
-            if (go && i >= 1) cnext = (uint32_t)__ldg(codes + pd.off + (uint64_t)(i - 1));
+            if (go && i >= 1) cnext = (uint32_t)__ldg(ix.char2code + raw2);
+            if (go && i >= 2) raw2 = (uint32_t)__ldg(pch + (i - 2));
 
             // block of each position; start == 0 needs no query (rank(0, c) == 0, :1012)
             const SbDesc se = T.sb[ep >> SB_LOG];

@@ -1,0 +1,19 @@
+#!/bin/bash
+# usage: bash tools/variants2.sh "<ENV=..;nvcc flags>" ...   each arg: "ENVASSIGN|nvccflags"
+cd /root/repo
+mkdir -p gpurun_out
+python bench.py --build-only 2> gpurun_out/variants_build.log
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "count" 2>&1 | tail -2
+i=0
+for spec in "$@"; do
+  i=$((i+1))
+  envs="${spec%%|*}"; flags="${spec#*|}"
+  nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math -Xcompiler -fPIC,-O3,-pthread -shared -Xptxas -v \
+       -I include $flags -o index4j_b200/libfmgpu.so index4j_b200/csrc/fmgpu.cu -lcudart 2> gpurun_out/variant_$i.nvcc.log
+  grep -A2 "k_count" gpurun_out/variant_$i.nvcc.log | grep -E "Used|spill" | tr '\n' ' '
+  echo "== variant $i: $spec"
+  env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/variant_$i.log | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); r=d['roofline']
+print('   value %.1f M/s  step %.3f ms  kernel %.3f ms  frac %.3f  e2e %.1f M/s' % (d['value']/1e6, d['ms_per_step'], r['kernel_ms'], r['frac'], d['e2e']['value']/1e6))"
+done
