@@ -460,6 +460,24 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         }
     }
     (void)last_sb;
+
+    // single-symbol blocks: the LF step needs rank(j, c') for the symbol c' inverseSelect decodes (low byte only) and
+    // j inside the same block; that is the (block, c') cell, which never has a level walk here — copy it into the descriptor
+    for (size_t b = 0; b < nblk; ++b) {
+        if (trees[b].h != 0) continue;
+        Rec32& D = F.blocks[(size_t)P.first_block + b];
+        const uint32_t c = (D.w[1] >> 8) & 0xffffu;
+        if (c >= (uint32_t)sigma) {  // rank of a symbol outside the alphabet is 0 (:1018-1020)
+            D.w[2] = 0;
+            D.w[3] = fmgpu::CELL_CONST;
+            continue;
+        }
+        const Rec32& cell = F.cells[((size_t)P.first_block + b) * (size_t)sigma + c];
+        const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
+        if (kind == fmgpu::CELL_NORMAL) throw FormatError("single-symbol block with a level walk");
+        D.w[2] = cell.w[0];
+        D.w[3] = kind;
+    }
 }
 
 inline void flatten_sampled(const RrrStream& r, FlatIndex& F) {

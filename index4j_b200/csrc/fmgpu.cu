@@ -16,6 +16,7 @@
 #include "jstream.hpp"
 #include "kernels.cuh"
 #include "kernels_lf.cuh"
+#include "kernels_locate.cuh"
 #include "layout.h"
 
 using namespace fmgpu;
@@ -84,7 +85,8 @@ struct fmgpu_index {
     uint64_t total_bytes = 0;
     int32_t alphabet_length = 0;
     int sm_count = 0;
-    int count_ctas = 0, lf_ctas = 0;
+    int count_ctas = 0, lf_ctas = 0, locate_ctas = 0, extract_ctas = 0, eub_ctas = 0;
+    bool locate_v1 = false;
     size_t tables_smem = 0;
     std::mutex mu;  // batch calls on one handle are serialised (v0)
     cudaStream_t stream = nullptr, copy_stream = nullptr, down_stream = nullptr;
@@ -227,6 +229,12 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
     up(upload(ix, F.ovf, &ix->dev.ovf, &ix->layout_bytes[4]));
     up(upload(ix, F.sgroups, &ix->dev.sgroups, &ix->layout_bytes[5]));
     up(upload(ix, F.soffsets, &ix->dev.soffsets, &ix->layout_bytes[5]));
+    {
+        const fmgpu_host::RrrTables& RT = fmgpu_host::rrr_tables();
+        std::vector<uint16_t> inv(RT.inverse, RT.inverse + 32768), cb(RT.class_base, RT.class_base + 16);
+        up(upload(ix, inv, &ix->dev.rrr_inv, nullptr));
+        up(upload(ix, cb, &ix->dev.rrr_cbase, nullptr));
+    }
     up(upload(ix, F.sa, &ix->dev.sa, &ix->layout_bytes[6]));
     up(upload(ix, F.isa, &ix->dev.isa, &ix->layout_bytes[7]));
     if (!rc) {

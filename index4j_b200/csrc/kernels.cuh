@@ -18,6 +18,7 @@
 
 #include "lane_logic.h"
 #include "layout.h"
+#include "ldrec.h"
 
 namespace fmgpu {
 
@@ -25,14 +26,6 @@ constexpr unsigned FULL = 0xffffffffu;
 constexpr int CTA_THREADS = 256;
 constexpr uint32_t SMEM_C_MAX = 4096;   // entries of C kept in shared memory
 constexpr uint32_t SMEM_SB_MAX = 2048;  // superblock descriptors kept in shared memory
-
-__device__ __forceinline__ Rec32 ld256(const Rec32* p) {
-    Rec32 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7])
-                 : "l"(p));
-    return r;
-}
 
 // Index tables small enough for shared memory (C array, superblock descriptors).
 __device__ __forceinline__ SmemTables stage_tables(const DevIndex& ix, uint32_t* smem) {

@@ -31,7 +31,8 @@ constexpr uint32_t CELL_INLINE_LEVELS = 5;
 // node touches exactly one sector.
 
 // --- block descriptor (LF / inverseSelect entry, :1305-1537):
-//   w0 root sector, w1 info (bit0 = run block, bits 8-23 = run symbol as inverseSelect decodes it),
+//   w0 root sector, w1 info (bit0 = run block, bits 8-23 = run symbol c' as inverseSelect decodes it),
+//   run blocks: w2 / w3 = value / kind of the (block, c') cell, i.e. rank(j, c') for j inside the block;
 //   w4..w7 = node record of the root.
 // --- node record (16 B, two per sector): c0, c1, a0, a1.  Child b: c_b bit31 set => leaf, low 16
 // bits = symbol, a_b = boundary rank of that symbol; else c_b = record index of the child node
@@ -79,6 +80,8 @@ struct DevIndex {
     const Rec32* nodes;    // node records, two per Rec32
     const Rec32* sgroups;
     const uint32_t* soffsets;
+    const uint16_t* rrr_inv;    // [32768] (class, offset) -> 15-bit block, RrrVector.java:8705-16899 regenerated
+    const uint16_t* rrr_cbase;  // [16]    RrrVector.java:8692-8698
     const Rec32* sa;       // SA samples, 8 per Rec32
     const Rec32* isa;      // ISA samples, 8 per Rec32
 };

@@ -1,0 +1,356 @@
+// Straight-line per-lane code of one LF step and of the sampled-row test (locate v2, lockstep kernels).
+//
+// Unlike the lane state machine of walk_lane.h (one record per trip, every phase's code executed every
+// trip), these are plain sequential functions: a warp runs them for its 32 work items together and the
+// hardware reconverges the lanes after each data-dependent loop.  Host/device code: the kernels fetch
+// records with 256-bit loads, the host layout test (tests/support/flatcheck.cpp) with plain reads.
+//
+// Reference semantics (paths under indices/src/main/java/com/dynatrace/):
+//   sampled_access_rank  bitsequence/RrrVector.java:314-349 (access) and :358-396 (rankOnes)
+//   rank_generic         wavelet/WaveletFixedBlockBoosting.java:1010-1285 (rank)
+//   lf_step              fm/FmIndex.java:532-535 / :597-599  c = (short) inverseSelect(j-1); j = C[c] + rank(j, c)
+//                        with inverseSelect = wavelet/WaveletFixedBlockBoosting.java:1305-1537
+#pragma once
+#include <cstdint>
+
+#include "lane_logic.h"
+#include "ldrec.h"
+#include "walk_lane.h"  // WalkParams, ItemRaw, walk_load_item, WalkMode
+
+namespace fmgpu {
+
+// (class, offset) -> 15-bit block: inv[cbase[cls] + off] — the reference's INVERSE_VALUES / CARDINALITY_OFFSETS
+// tables (RrrVector.java:8692-16899), regenerated from their ordering rule; shared memory on the device.
+struct RrrTab {
+    const uint16_t* inv;    // [32768]
+    const uint16_t* cbase;  // [16]
+};
+
+struct LfCounters {
+    uint32_t lf_steps, lf_levels, ranks, rank_levels, sbits;
+};
+
+// access(pos) and rankOnes(pos) of the sampled-row vector from its group record G (already fetched)
+FMGPU_HD void sampled_access_rank(const DevIndex& ix, const RrrTab& R, const Rec32& G, uint32_t pos, uint32_t* bit, uint32_t* rank) {
+    const uint32_t blk = pos / RRR_BLOCK;
+    const uint32_t k = blk & 31u, sub = k >> 3, kk = k & 7u;
+    const uint32_t use = pos - blk * RRR_BLOCK;
+    uint32_t offb = G.w[1], ones = G.w[0];
+    if (sub) {
+        offb += (G.w[2] >> (10u * (sub - 1u))) & 1023u;
+        ones += (G.w[3] >> (10u * (sub - 1u))) & 1023u;
+    }
+    const uint32_t word = rec_word(G, 4u + sub);
+    // classes of the blocks before this one inside its 8-block word: sum of nibbles / of their offset widths
+    const uint32_t before = word & low_mask_clamped((int)(4u * kk));
+#pragma unroll
+    for (uint32_t i = 0; i < 7; ++i) {
+        const uint32_t c = (before >> (4u * i)) & 15u;
+        ones += c;
+        offb += i < kk ? rrr_bits(c) : 0u;
+    }
+    const uint32_t cls = (word >> (4u * kk)) & 15u;
+    if (cls == 0u) {
+        *bit = 0;
+        *rank = ones;
+        return;
+    }
+    if (cls == 15u) {
+        *bit = 1;
+        *rank = ones + use;
+        return;
+    }
+    const uint32_t nb = rrr_bits(cls);
+    const uint32_t wi = offb >> 5, sh = offb & 31u;
+    const uint32_t lo = FMGPU_LDG32(ix.soffsets + wi);
+    const uint32_t hi = FMGPU_LDG32(ix.soffsets + wi + 1u);  // the stream is padded
+    const unsigned long long both = ((unsigned long long)hi << 32) | lo;
+    const uint32_t off = (uint32_t)(both >> sh) & ((1u << nb) - 1u);
+    const uint32_t block = R.inv[(uint32_t)R.cbase[cls] + off];
+    *bit = (block >> use) & 1u;
+    *rank = ones + popc32(block & ((1u << use) - 1u));
+}
+
+// rank(pos, sym) through the cell / level / overflow records.  Returns 0, or 9 where the reference throws.
+FMGPU_HD uint32_t rank_generic(const DevIndex& ix, const SmemTables& T, uint32_t pos, uint32_t sym, uint32_t* out, LfCounters& cnt) {
+    RankSt s;
+    s.p5 = s.p6 = s.p7 = 0;
+    const Rec32* addr = nullptr;
+    uint32_t val = 0;
+    uint32_t o = rank_begin(ix, T, pos, sym, s, &addr, &val);
+    if (o == RK_THROW) return 9u;
+    if (o == RK_DONE) {
+        *out = val;
+        return 0u;
+    }
+    ++cnt.ranks;
+    {
+        const Rec32 cell = FMGPU_LD256(addr);
+        o = rank_on_cell(ix, cell, s, &addr, &val);
+    }
+    if (o == RK_THROW) return 9u;
+    while (o == RK_MORE) {
+        bool want = false;
+        ++cnt.rank_levels;
+        const Rec32 A = FMGPU_LD256(addr);
+        o = rank_on_level(ix, A, s, &addr, &val, &want);
+        if (o == RK_MORE && want) {
+            const Rec32 V = FMGPU_LD256(addr);
+            rank_on_ovf(ix, V, s, &addr);
+        }
+    }
+    *out = val;
+    return 0u;
+}
+
+// One LF step from row j (Java's 1-based j): returns the new j.  D is the block descriptor of position j-1
+// (already fetched), bmask the block-size mask of that position's superblock.
+//   * tree block: inverseSelect walks DOWN the block's tree — per level one level sector and the node record of
+//     the child — and its leaf gives the symbol AND rank(j-1, c); bwt[j-1] == c, so rank(j, c) = rank(j-1, c) + 1
+//     whenever j lies in the same block;
+//   * single-symbol block: the descriptor carries the symbol as inverseSelect decodes it (low byte only,
+//     :1329-1332) and the pre-evaluated (block, symbol) cell, so rank(j, c) = value [+ (j mod block)] needs no
+//     further record when j lies in the same block;
+//   * otherwise (j starts a new block) the generic rank(j, c) is evaluated exactly as the reference would.
+FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& D, uint32_t j, uint32_t bmask, uint32_t* sym_out,
+                          uint32_t* err, LfCounters& cnt) {
+    const uint32_t pos = j - 1u;
+    const uint32_t jrel = j & bmask;
+    uint32_t sym, rank_j = 0;
+    bool have = false;
+    ++cnt.lf_steps;
+    if (D.w[1] & 1u) {
+        sym = (D.w[1] >> 8) & 0xffffu;
+        if (jrel != 0u) {
+            const uint32_t kind = D.w[3];
+            if (kind == CELL_THROW) {
+                *err = 1;
+                *sym_out = sym;
+                return j;
+            }
+            rank_j = D.w[2] + (kind == CELL_RUN ? jrel : 0u);
+            have = true;
+        }
+    } else {
+        uint32_t r = pos & bmask;
+        uint32_t c0 = D.w[4], c1 = D.w[5], a0 = D.w[6], a1 = D.w[7];
+        uint32_t sec = D.w[0];
+        for (;;) {
+            const Rec32 S = FMGPU_LD256(ix.sectors + (sec + r / SECTOR_BITS));
+            ++cnt.lf_levels;
+            const uint32_t b = r % SECTOR_BITS;
+            const uint32_t ones = sector_rank(S, b);
+            const uint32_t bit = sector_bit(S, b);
+            const uint32_t cb = bit ? c1 : c0;
+            const uint32_t ab = bit ? a1 : a0;
+            r = bit ? ones : r - ones;
+            if (cb & LEAF_FLAG) {
+                sym = cb & 0xffffu;
+                rank_j = ab + r + 1u;
+                break;
+            }
+            sec = ab;
+            const Rec32 N = FMGPU_LD256(ix.nodes + (cb >> 1));
+            const bool hi = (cb & 1u) != 0u;
+            c0 = hi ? N.w[4] : N.w[0];
+            c1 = hi ? N.w[5] : N.w[1];
+            a0 = hi ? N.w[6] : N.w[2];
+            a1 = hi ? N.w[7] : N.w[3];
+        }
+        have = jrel != 0u;
+    }
+    *sym_out = sym;
+    if (!have) {
+        const uint32_t st = rank_generic(ix, T, j, sym, &rank_j, cnt);
+        if (st) {
+            *err = 1;
+            return j;
+        }
+    }
+    return T.C[sym] + rank_j;
+}
+
+// ------------------------------------------------------------------------------------------------
+// extract / extractUntilBoundary* work item of the lockstep kernel k_extract: the control flow around the LF
+// steps (fm/FmIndex.java:564-608, :640-759, :772-831, :844-922).  Same arithmetic as the phase machine of
+// walk_lane.h, expressed as "what happens after an LF step produced a char" so that every trip of the warp
+// loop is: [ISA sample if a walk starts] -> one LF step -> on_char().
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+struct ExLane {
+    uint32_t w, j, dist, isa_idx;
+    bool active, need_isa;
+    int32_t from, skip, remaining, k, down, cur, end, pb, rel, stage;
+    uint64_t out0;
+
+    FMGPU_HD void init() {
+        active = false;
+        need_isa = false;
+        w = j = dist = isa_idx = 0;
+        from = skip = remaining = k = down = cur = end = pb = rel = stage = 0;
+        out0 = 0;
+    }
+    FMGPU_HD void finish(const WalkParams& P, int32_t status, int32_t value) {
+        P.len_out[w] = value;
+        P.status_out[w] = status;
+        if (MODE == WM_EUB) P.down_len[w] = (status == 0 || status == 8) ? down : 0;
+        active = false;
+    }
+    FMGPU_HD void start_isa(uint32_t idx) {
+        isa_idx = idx;
+        need_isa = true;
+    }
+    FMGPU_HD void begin_right(const DevIndex& ix) {  // interval [cur, end): walk from the ISA sample at `end`
+        const uint32_t sr = ix.sample_rate;
+        const uint32_t s = (uint32_t)cur / sr;
+        const uint64_t e = ((uint64_t)s + 1u) * sr;
+        end = e < (uint64_t)ix.length ? (int32_t)e : (int32_t)ix.length;
+        dist = 0;
+        pb = -1;
+        start_isa(s + 1u);
+    }
+    // checks of extract (:566-593) / checkBoundsForExtraction (:610-626) and the first ISA sample
+    FMGPU_HD void begin(const DevIndex& ix, const WalkParams& P, uint32_t item, const ItemRaw& raw) {
+        w = item;
+        active = true;
+        need_isa = false;
+        dist = 0;
+        k = 0;
+        down = 0;
+        stage = 0;
+        rel = -1;
+        if (MODE == WM_EXTRACT) {
+            const int32_t st = raw.a, sp = raw.b;
+            out0 = raw.o0;
+            if (!ix.extract_enabled) return finish(P, 1, 0);
+            if (st < 0) return finish(P, 2, 0);
+            if (sp >= (int32_t)ix.length) return finish(P, 3, 0);
+            const int32_t sr = (int32_t)ix.sample_rate;
+            const int32_t idx = sp / sr + 1;
+            if (idx < 0 || idx >= (int32_t)ix.n_isa) return finish(P, 9, 0);
+            skip = sr - sp % sr;
+            if (sp / sr == (int32_t)ix.n_isa - 2) skip = (int32_t)ix.length - sp;
+            const int32_t range = sp - st;
+            const int64_t room = (int64_t)(raw.o1 - raw.o0);
+            if (room < (int64_t)range) return finish(P, 5, 0);
+            remaining = range;
+            k = range;
+            if (range <= 0) return finish(P, 0, range);
+            start_isa((uint32_t)idx);
+        } else {
+            from = raw.a;
+            if (P.eub_mode == 1) ++from;  // :774
+            if (!ix.extract_enabled) return finish(P, 1, 0);
+            if (from < 0) return finish(P, 2, 0);
+            if (from >= (int32_t)ix.length) return finish(P, 4, 0);
+            if (P.dst_len == 0) return finish(P, 6, 0);
+            if (P.mb == 0u) return finish(P, 7, 0);
+            remaining = P.dst_len;
+            if (P.eub_mode == 2) {
+                stage = 1;
+                cur = from;
+                begin_right(ix);
+            } else {
+                const int32_t sr = (int32_t)ix.sample_rate;
+                skip = sr - from % sr;
+                if (from / sr == (int32_t)ix.n_isa - 2) skip = (int32_t)ix.length - from;
+                start_isa((uint32_t)(from / sr + 1));
+            }
+        }
+    }
+    // an LF step produced `sym` (the char left of the previous one)
+    FMGPU_HD void on_char(const DevIndex& ix, const WalkParams& P, uint32_t sym) {
+        if (MODE == WM_EXTRACT) {
+            if ((int32_t)dist >= skip) {  // :601-604
+                P.arena[out0 + (uint64_t)(remaining - 1)] = ix.code2char[sym];
+                --remaining;
+            }
+            ++dist;
+            if (remaining <= 0) finish(P, 0, k);
+            return;
+        }
+        const uint64_t slot = (uint64_t)w * (uint64_t)P.dst_len;
+        if (stage == 0) {  // left walk (:664-686, :797-826)
+            bool stop_left = false;
+            if ((int32_t)dist >= skip) {
+                if (sym == P.mb || sym == 0u) {
+                    stop_left = true;
+                } else if (P.eub_mode == 1) {
+                    const int32_t idx = P.dst_len - 1 - k;  // downStreamPos
+                    if (idx < 0) return finish(P, 9, 0);
+                    P.left[slot + (uint64_t)k] = ix.code2char[sym];
+                    ++k;
+                    down = k;
+                    if (idx - 1 == 0) return finish(P, 8, P.dst_len);  // :817-821
+                } else {
+                    P.left[slot + (uint64_t)k] = ix.code2char[sym];
+                    ++k;
+                    --remaining;
+                    if (remaining == 0) stop_left = true;
+                }
+            }
+            ++dist;
+            if (!stop_left) return;
+            down = k;
+            if (P.eub_mode == 1) return finish(P, 0, k);
+            stage = 1;
+            cur = from;
+            begin_right(ix);
+            return;
+        }
+        // right walk over one sample interval: step `dist` produced text[end-1-dist]
+        const int32_t p = end - 1 - (int32_t)dist;
+        if (p >= from && p < (int32_t)ix.length - 1) {
+            if (sym == P.mb) pb = p;
+            if (P.eub_mode == 2) {
+                const int32_t idx = p - from - 1;
+                if (idx >= 0 && idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
+            } else {
+                const int64_t idx = (int64_t)down + (p - from);
+                if (idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
+            }
+        }
+        ++dist;
+        if (p > cur) return;
+        if (rel < 0 && pb >= 0) rel = pb - from;  // intervals go left to right: the first boundary seen is the nearest
+        bool more = true;
+        if (rel >= 0) {
+            // The reference reads whole 4-char chunks; when the boundary's chunk is also the one that reaches the end of
+            // the text, its end-of-text rule (quirk Q5) returns chars beyond the boundary: fetch them too.
+            const int64_t chunk_end = (int64_t)from + 4 * ((int64_t)rel / 4 + 1);
+            more = chunk_end >= (int64_t)ix.length - 1 && end < (int32_t)ix.length;
+        } else if (end >= (int32_t)ix.length) {
+            more = false;
+        } else if ((int64_t)end - from > (int64_t)P.dst_len + 8) {
+            rel = 0x3fffffff;  // the destination overflows before any boundary
+            more = false;
+        }
+        if (more) {
+            cur = end;
+            begin_right(ix);
+        } else {
+            const EubOut o = eub_right_chunks(from, down, rel, (int32_t)ix.length, P.dst_len, P.eub_mode == 2);
+            finish(P, o.status, o.value);
+        }
+    }
+    // one trip: [ISA sample] -> LF step -> on_char
+    FMGPU_HD void trip(const DevIndex& ix, const SmemTables& T, const WalkParams& P, LfCounters& cnt) {
+        if (need_isa) {
+            const Rec32 I = FMGPU_LD256(ix.isa + (isa_idx >> 3));
+            j = rec_word(I, isa_idx & 7u) + 1u;  // :579 / :645
+            need_isa = false;
+        }
+        const uint32_t pos = j - 1u;
+        const SbDesc sd = T.sb[pos >> SB_LOG];
+        const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
+        const uint32_t bmask = (1u << sd.block_log) - 1u;
+        const Rec32 D = FMGPU_LD256(ix.blocks + blk);
+        uint32_t sym = 0, err = 0;
+        const uint32_t jn = lf_step(ix, T, D, j, bmask, &sym, &err, cnt);
+        if (err) return finish(P, 9, 0);
+        j = jn;
+        on_char(ix, P, sym);
+    }
+};
+
+}  // namespace fmgpu

@@ -9,6 +9,7 @@
 
 #include "../../index4j_b200/csrc/flatten.hpp"
 #include "../../index4j_b200/csrc/jstream.hpp"
+#include "../../index4j_b200/csrc/lf_lane.h"
 #include "../../index4j_b200/csrc/walk_lane.h"
 
 using namespace fmgpu;
@@ -48,8 +49,28 @@ int host_rank(const FC& h, uint32_t pos, uint32_t sym, uint32_t* out, uint64_t* 
     return 0;
 }
 
+bool g_v2 = false;  // replay the lockstep lanes of lf_lane.h (k_extract) instead of the phase machine of walk_lane.h (k_walk)
+
+template <int MODE>
+void run_walk_v2(const FC& h, const WalkParams& P, uint64_t* counters) {
+    LfCounters cnt{};
+    for (uint32_t w = 0; w < P.n_items; ++w) {
+        ExLane<MODE> lane;
+        lane.init();
+        lane.begin(h.ix, P, w, walk_load_item<MODE>(P, w));
+        while (lane.active) lane.trip(h.ix, h.T, P, cnt);
+    }
+    if (counters) {
+        counters[0] += cnt.ranks;
+        counters[1] += cnt.rank_levels;
+        counters[2] += cnt.lf_steps;
+        counters[3] += cnt.lf_levels;
+    }
+}
+
 template <int MODE>
 void run_walk(const FC& h, const WalkParams& P, uint64_t* counters) {
+    if (g_v2 && MODE != WM_LOCATE) return run_walk_v2<MODE == WM_LOCATE ? WM_EXTRACT : MODE>(h, P, counters);
     WalkCounters cnt{};
     for (uint32_t w = 0; w < P.n_items; ++w) {
         WalkLane<MODE> lane;
@@ -110,6 +131,7 @@ int fc_load(const uint8_t* buf, uint64_t len, int threads, void** out) {
     }
 }
 void fc_free(void* h) { delete (FC*)h; }
+void fc_set_v2(int on) { g_v2 = on != 0; }
 int32_t fc_alphabet_length(void* h) { return ((FC*)h)->F.alphabet_length; }
 void fc_sizes(void* hv, uint64_t* out8) {
     FC* h = (FC*)hv;
@@ -240,6 +262,58 @@ void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
     bool st = false;
     const uint32_t o = sg_on_group(h.ix, *sg_addr(h.ix, pos), pos, s, &b, &r, &oa, &ob, &st);
     if (o == SG_OFFSET) sg_on_offset(*oa, st ? *ob : ZERO, st, h.binom, s, &b, &r);
+    *bit = (int32_t)b;
+    *rank = (int32_t)r;
+}
+
+// locate v2 (k_locate): the straight-line lane code of lf_lane.h, one hit at a time
+void fc_locate_rows_v2(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* counters) {
+    FC& h = *(FC*)hv;
+    const fmgpu_host::RrrTables& RT = fmgpu_host::rrr_tables();
+    RrrTab R;
+    R.inv = RT.inverse;
+    R.cbase = RT.class_base;
+    LfCounters cnt{};
+    for (uint32_t w = 0; w < n; ++w) {
+        uint32_t j = rows_pos[w] + 1u, dist = 0;
+        for (;;) {
+            const uint32_t pos = j - 1u;
+            const SbDesc sd = h.T.sb[pos >> SB_LOG];
+            const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
+            const uint32_t bmask = (1u << sd.block_log) - 1u;
+            uint32_t bit = 0, rank = 0;
+            ++cnt.sbits;
+            sampled_access_rank(h.ix, R, *sg_addr(h.ix, pos), pos, &bit, &rank);
+            if (bit) {
+                rows_pos[w] = rec_word(h.ix.sa[rank >> 3], rank & 7u) + dist;
+                break;
+            }
+            uint32_t sym = 0, err = 0;
+            const uint32_t jn = lf_step(h.ix, h.T, h.ix.blocks[blk], j, bmask, &sym, &err, cnt);
+            if (err) {
+                rows_pos[w] = 0xffffffffu;
+                break;
+            }
+            j = jn;
+            ++dist;
+        }
+    }
+    if (counters) {
+        counters[0] += cnt.ranks;
+        counters[1] += cnt.rank_levels;
+        counters[2] += cnt.lf_steps;
+        counters[3] += cnt.lf_levels;
+        counters[4] += cnt.sbits;
+    }
+}
+void fc_sampled_v2(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
+    FC& h = *(FC*)hv;
+    const fmgpu_host::RrrTables& RT = fmgpu_host::rrr_tables();
+    RrrTab R;
+    R.inv = RT.inverse;
+    R.cbase = RT.class_base;
+    uint32_t b = 0, r = 0;
+    sampled_access_rank(h.ix, R, *sg_addr(h.ix, pos), pos, &b, &r);
     *bit = (int32_t)b;
     *rank = (int32_t)r;
 }

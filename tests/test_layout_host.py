@@ -55,6 +55,7 @@ def test_sampled_rows_match_oracle(flats, name):
     for p in np.concatenate([rng.integers(0, L, 20000), [0, L - 1]]):
         b, r = f.sampled(int(p))
         assert b == case.oracle.sampled_access(int(p)) and r == case.oracle.sampled_rank(int(p)), int(p)
+        assert (b, r) == f.sampled_v2(int(p)), int(p)  # table decode of k_locate (lf_lane.h)
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
@@ -71,10 +72,19 @@ def test_count_and_locate_lanes(flats, name):
         exp += list(pos[i, : n_hits[i]])
     got_pos, _ = f.locate_rows(np.array(rows, dtype=np.uint32))
     assert np.array_equal(got_pos, np.array(exp, dtype=np.int64))
+    got_v2 = f.locate_rows_v2(np.array(rows, dtype=np.uint32))  # lane code of k_locate (lf_lane.h)
+    assert np.array_equal(got_v2, np.array(exp, dtype=np.int64))
+
+
+@pytest.fixture(params=["phase_machine", "lockstep"])
+def lane_impl(request):
+    flatcheck.FlatIndexHost.set_v2(request.param == "lockstep")
+    yield request.param
+    flatcheck.FlatIndexHost.set_v2(False)
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
-def test_extract_lanes(flats, name):
+def test_extract_lanes(flats, name, lane_impl):
     case, f = get_case(name), flats(name)
     rng = np.random.default_rng(4)
     n = case.text.size
@@ -94,7 +104,7 @@ def test_extract_lanes(flats, name):
 
 @pytest.mark.parametrize("name", CASE_NAMES)
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_extract_until_boundary_lanes(flats, name, mode):
+def test_extract_until_boundary_lanes(flats, name, mode, lane_impl):
     case, f = get_case(name), flats(name)
     n = case.text.size
     rng = np.random.default_rng(5 + mode)

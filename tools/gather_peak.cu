@@ -19,7 +19,7 @@ __global__ void k_gather(const Rec32* buf, uint64_t n_rec, int iters, uint32_t* 
     uint32_t acc = 0;
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
-    for (int k = 0; k < ILP; ++k) idx[k] = (tid * 0x9E3779B97F4A7C15ULL + k * 0xBF58476D1CE4E5B9ULL) % n_rec;
+    for (int k = 0; k < ILP; ++k) idx[k] = __umul64hi((tid + 1) * 0x9E3779B97F4A7C15ULL + k * 0xBF58476D1CE4E5B9ULL, n_rec);
     for (int it = 0; it < iters; ++it) {
         Rec32 r[ILP];
 #pragma unroll
@@ -27,7 +27,8 @@ __global__ void k_gather(const Rec32* buf, uint64_t n_rec, int iters, uint32_t* 
 #pragma unroll
         for (int k = 0; k < ILP; ++k) {
             acc += r[k].w[1];
-            idx[k] = (idx[k] * 6364136223846793005ULL + 1442695040888963407ULL + r[k].w[0]) % n_rec;
+            // range reduction by multiply-high (a 64-bit '%' costs ~100 instructions and made v1 of this tool ALU-bound)
+            idx[k] = __umul64hi((idx[k] + r[k].w[0] + it) * 6364136223846793005ULL + 1442695040888963407ULL, n_rec);
         }
     }
     out[tid] = acc;
@@ -59,10 +60,11 @@ int main() {
         cudaMalloc(&buf, n_rec * 32);
         cudaMemset(buf, 1, n_rec * 32);
         cudaMalloc(&out, (size_t)p.multiProcessorCount * 2048 * 4);
-        for (int t : {1024, 2048}) {
+        for (int t : {512, 1024, 2048}) {
             run<1>(buf, n_rec, out, t, p.multiProcessorCount);
             run<2>(buf, n_rec, out, t, p.multiProcessorCount);
             run<4>(buf, n_rec, out, t, p.multiProcessorCount);
+            run<8>(buf, n_rec, out, t, p.multiProcessorCount);
         }
         cudaFree(buf);
         cudaFree(out);
