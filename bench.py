@@ -239,6 +239,11 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="patterns of the cpu_baseline leg")
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lf", action="store_true", help="skip the locate / extractUntilBoundary legs (extra keys of the JSON line)")
+    ap.add_argument("--max-hits", type=int, default=1000)
+    ap.add_argument("--lf-steps", type=int, default=2)
+    ap.add_argument("--n-eub", type=int, default=1_000_000)
+    ap.add_argument("--dst-len", type=int, default=512)
     ap.add_argument("--build-only", action="store_true", help="build + cache the index and the pattern batches, then exit")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
@@ -327,10 +332,40 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(h_counts, d_counts.cpu().numpy())
 
-    times = torch.tensor([ms_total, e2e_s * 1e3, statistics.mean(kernel_ms)], dtype=torch.float64, device=dev)
+    # second half of the metric: located hits/s (BASELINE.json configs[2]) and extractUntilBoundary of located hits
+    # (configs[3]); same patterns, device-resident, timed with CUDA events; max over ranks, hits summed over ranks
+    lf = None
+    if not args.no_lf:
+        from index4j_b200 import workloads
+        loc, d_hit_off, d_pos = workloads.locate_workload(ix, d_chars, d_off, args.max_hits, args.lf_steps, 1)
+        total_hits = loc["hits"]
+        n_eub = min(args.n_eub, total_hits)
+        sel = torch.linspace(0, max(total_hits - 1, 0), max(n_eub, 1), device=dev, dtype=torch.float64).to(torch.int64)
+        d_from = d_pos[sel].contiguous()
+        eub, d_arena, d_len, d_st = workloads.eub_workload(ix, d_from, args.dst_len, args.lf_steps, 1)
+        # end to end through the C ABI: host patterns in, host positions out (one call: ranges, hit scan, LF walks, D2H)
+        p_nh = torch.empty(n_pat, dtype=torch.int32).pin_memory().numpy()
+        p_ho = torch.empty(n_pat + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
+        p_pos = torch.empty(max(total_hits, 1), dtype=torch.int32).pin_memory().numpy()
+        ix.locate_batch_into(h_chars, h_off, args.max_hits, p_nh, p_ho, p_pos, h_status)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.lf_steps):
+            ix.locate_batch_into(h_chars, h_off, args.max_hits, p_nh, p_ho, p_pos, h_status)
+        loc_e2e_s = (time.perf_counter() - t0) / args.lf_steps
+        assert int(p_ho[-1]) == total_hits and np.array_equal(p_pos[:4096], d_pos[:4096].cpu().numpy())
+        lf = {"loc": loc, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
+              "d_hit_off": d_hit_off, "d_pos": d_pos, "h2d": int(chars.nbytes + off.nbytes), "d2h": int(p_nh.nbytes + p_ho.nbytes + p_pos.nbytes + h_status.nbytes)}
+
+    times = torch.tensor([ms_total, e2e_s * 1e3, statistics.mean(kernel_ms), lf["loc"]["ms_per_step"] if lf else 0.0,
+                          lf["eub"]["ms_per_step"] if lf else 0.0, lf["loc_e2e_ms"] if lf else 0.0], dtype=torch.float64, device=dev)
+    sums = torch.tensor([lf["loc"]["hits"] if lf else 0, lf["eub"]["records"] if lf else 0, lf["eub"]["chars"] if lf else 0,
+                         lf["loc"]["lf_steps"] if lf else 0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, kern_ms = [float(x) for x in times.cpu()]
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, kern_ms, loc_ms, eub_ms, loc_e2e_ms = [float(x) for x in times.cpu()]
+    all_hits, all_records, all_chars, all_lf_steps = [float(x) for x in sums.cpu()]
 
     if rank == 0:
         value = world * n_pat * args.steps / (ms_total / 1e3)
@@ -354,6 +389,16 @@ def main():
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3)},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob)},
         }
+        if lf:
+            out["locate"] = {"metric": "located hits/sec (max %d hits per pattern)" % args.max_hits, "value": all_hits / (loc_ms / 1e3),
+                             "unit": "hits/s", "hits_per_step": all_hits, "ms_per_step": loc_ms, "steps": args.lf_steps,
+                             "lf_steps_per_s": all_lf_steps / (loc_ms / 1e3),
+                             "e2e": {"value": all_hits / (loc_e2e_ms / 1e3), "unit": "hits/s", "h2d_bytes_per_step": lf["h2d"],
+                                     "d2h_bytes_per_step": lf["d2h"]},
+                             "alg_gb_per_s_rank0": lf["loc"]["alg_gb_per_s"], "launches_per_step": lf["loc"]["launches"]}
+            out["extract_until_boundary"] = {"metric": "records/sec (extractUntilBoundary('\\n'), dst %d chars, of located hits)" % args.dst_len,
+                                             "value": all_records / (eub_ms / 1e3), "unit": "records/s", "chars_per_s": all_chars / (eub_ms / 1e3),
+                                             "ms_per_step": eub_ms, "records_per_step": all_records, "launches_per_step": lf["eub"]["launches"]}
         traffic_file = os.path.join(ROOT, "profiles", "k_count_traffic.json")
         if os.path.exists(traffic_file):
             try:
@@ -363,8 +408,25 @@ def main():
                 pass
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt, cpu_counts, _ = cpu_count_throughput(blob, chars, off, args.cpu_sample, threads, args.cpu_repeats)
+            v, dt, cpu_counts, oracle_ix = cpu_count_throughput(blob, chars, off, args.cpu_sample, threads, args.cpu_repeats)
             assert np.array_equal(cpu_counts, h_counts[: cpu_counts.size]), "GPU counts differ from the CPU oracle"
+            if lf:  # spot-check the LF legs against the oracle as well (200 patterns / records)
+                k = 200
+                ho = lf["d_hit_off"][: k + 1].cpu().numpy().astype(np.int64)
+                pos = lf["d_pos"][: int(ho[-1])].cpu().numpy()
+                w_n, w_pos, _ = oracle_ix.locate_batch(chars[: int(off[k])], off[: k + 1], args.max_hits, max(args.max_hits, 1), threads=threads)
+                assert np.array_equal(np.diff(ho), w_n), "locate hit counts differ from the CPU oracle"
+                for i in range(k):
+                    assert np.array_equal(pos[ho[i]: ho[i + 1]], w_pos[i, : w_n[i]]), "located positions differ from the CPU oracle"
+                frm = lf["d_from"][:k].cpu().numpy().astype(np.int32)
+                w_arena, w_ln, w_st = oracle_ix.extract_until_boundary_batch(frm, 10, args.dst_len, 0, threads=threads)
+                arena = lf["d_arena"][:k].cpu().numpy().view(np.uint16)
+                assert np.array_equal(lf["d_st"][:k].cpu().numpy(), w_st) and np.array_equal(lf["d_len"][:k].cpu().numpy()[w_st == 0], w_ln[w_st == 0])
+                for i in range(k):
+                    if w_st[i] == 0:
+                        assert np.array_equal(arena[i, : w_ln[i]], w_arena[i, : w_ln[i]]), "extracted record differs from the CPU oracle"
+                out["locate"]["oracle_checked_patterns"] = k
+                out["extract_until_boundary"]["oracle_checked_records"] = k
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": "first %d of the %d patterns, best of %d passes, %.1fs per pass (C++ restatement of the reference's Java loops; no JVM in this image)"
                                              % (cpu_counts.size, n_pat, args.cpu_repeats, dt)}

@@ -198,6 +198,13 @@ class FmIndex:
         self._check(self._lib.fmgpu_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, pat_off.size - 1, counts.ctypes.data,
                                                 status.ctypes.data if status is not None else None))
 
+    def locate_batch_into(self, chars, pat_off, max_hits, n_hits, hit_off, positions, status=None):
+        """``locate_batch`` writing into caller-owned (e.g. pinned) buffers — the raw C-ABI call; ``positions`` must hold all hits."""
+        self._check(self._lib.fmgpu_locate_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, pat_off.size - 1, max_hits,
+                                                 n_hits.ctypes.data, hit_off.ctypes.data, positions.ctypes.data, positions.size,
+                                                 status.ctypes.data if status is not None else None))
+        return int(hit_off[-1])
+
     # --- batched API (host buffers) ----------------------------------------------------------
     def count_batch(self, chars, pat_off, return_status: bool = False):
         chars = _u16(chars)
