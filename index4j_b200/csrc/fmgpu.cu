@@ -93,8 +93,16 @@ struct fmgpu_index {
     static constexpr int PIPE_SLOTS = 8;
     cudaEvent_t pipe_in[PIPE_SLOTS] = {nullptr}, pipe_out[PIPE_SLOTS] = {nullptr};
     Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b, order, bins;
+    // The host-pointer count call runs its chunks on COUNT_CTX compute streams round-robin, each with its own scratch set,
+    // so that the kernel of chunk k+1 fills the SMs as the longest patterns of chunk k drain (context 0 = the members above).
+    static constexpr int COUNT_CTX = 3;
+    struct CountCtx {
+        Scratch pats, ctrl, order, bins;
+    } cctx[COUNT_CTX - 1];
+    cudaStream_t cstream[COUNT_CTX - 1] = {nullptr};
     uint64_t last_launches = 0;
     bool stats_valid = false;
+    uint32_t stats_ctx_mask = 1;  // compute contexts whose counters belong to the most recent call
     // optional per-call timing of the dominant kernel (bench.py's roofline): ring of event pairs
     static constexpr int TIMING_SLOTS = 64;
     bool timing = false;
@@ -136,33 +144,45 @@ int prepass_grid(uint64_t items, int sm_count) {
 // Backward search over n_pat patterns on stream `st`.  `first_of_call` resets the work counters; later
 // chunks of the same call only re-arm the work queue.
 int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars, uint32_t n_pat,
-                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st, bool first_of_call = true) {
+                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st, bool first_of_call = true, int ctx = 0) {
     (void)total_chars;
-    CU(ix->pats.reserve(((size_t)n_pat + 2) * sizeof(PatDesc)));
-    CU(ix->ctrl.reserve(CTRL_WORDS * 4));
-    CU(ix->order.reserve((size_t)n_pat * 4 + 64));
-    CU(ix->bins.reserve(LEN_BINS * 4));
+    Scratch& s_pats = ctx ? ix->cctx[ctx - 1].pats : ix->pats;
+    Scratch& s_ctrl = ctx ? ix->cctx[ctx - 1].ctrl : ix->ctrl;
+    Scratch& s_order = ctx ? ix->cctx[ctx - 1].order : ix->order;
+    Scratch& s_bins = ctx ? ix->cctx[ctx - 1].bins : ix->bins;
+    CU(s_pats.reserve(((size_t)n_pat + 2) * sizeof(PatDesc)));
+    CU(s_ctrl.reserve(CTRL_WORDS * 4));
+    CU(s_order.reserve((size_t)n_pat * 4 + 64));
+    CU(s_bins.reserve(LEN_BINS * 4));
     if (first_of_call) {
-        CU(cudaMemsetAsync(ix->ctrl.p, 0, CTRL_WORDS * 4, st));
-        ix->last_launches = 0;
-        ix->stats_valid = true;
+        CU(cudaMemsetAsync(s_ctrl.p, 0, CTRL_WORDS * 4, st));
+        if (ctx == 0) {
+            ix->last_launches = 0;
+            ix->stats_valid = true;
+            ix->stats_ctx_mask = 1;
+        } else {
+            ix->stats_ctx_mask |= 1u << ctx;
+        }
     } else {
-        CU(cudaMemsetAsync(ix->ctrl.p, 0, 8, st));  // the two queue heads
+        CU(cudaMemsetAsync(s_ctrl.p, 0, 8, st));  // the two queue heads
     }
     if (n_pat == 0) return 0;
-    CU(cudaMemsetAsync(ix->bins.p, 0, LEN_BINS * 4, st));
-    unsigned int* ctrl = (unsigned int*)ix->ctrl.p;
+    CU(cudaMemsetAsync(s_bins.p, 0, LEN_BINS * 4, st));
+    unsigned int* ctrl = (unsigned int*)s_ctrl.p;
     // descriptors + length histogram, then a counting sort by length so that a warp's 32 patterns run in lockstep
     const int pre_grid = prepass_grid(n_pat, ix->sm_count);
-    k_prepass<<<pre_grid, 256, 0, st>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)ix->pats.p, (uint32_t*)ix->bins.p);
-    k_len_scan<<<1, LEN_BINS, 0, st>>>((uint32_t*)ix->bins.p);
+    k_prepass<<<pre_grid, 256, 0, st>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)s_pats.p, (uint32_t*)s_bins.p);
+    k_len_scan<<<1, LEN_BINS, 0, st>>>((uint32_t*)s_bins.p);
     const int sc_grid = prepass_grid(((uint64_t)n_pat + SCATTER_PER_THREAD - 1) / SCATTER_PER_THREAD, ix->sm_count);
-    k_len_scatter<<<sc_grid, 256, 0, st>>>((const PatDesc*)ix->pats.p, n_pat, (uint32_t*)ix->bins.p, (uint32_t*)ix->order.p);
+    k_len_scatter<<<sc_grid, 256, 0, st>>>((const PatDesc*)s_pats.p, n_pat, (uint32_t*)s_bins.p, (uint32_t*)s_order.p);
     const int slot = (int)(ix->timed_calls % fmgpu_index::TIMING_SLOTS);
     if (ix->timing) CU(cudaEventRecord(ix->ev0[slot], st));
-    k_count<<<ix->count_ctas, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)ix->pats.p,
-                                                                  (const uint32_t*)ix->order.p, n_pat, d_counts, d_status, d_ranges,
-                                                                  ctrl + CTRL_QUEUE, (unsigned long long*)(ctrl + CTRL_STATS));
+    int grid = ix->count_ctas;
+    const int need = (int)(((uint64_t)n_pat + CTA_THREADS - 1) / CTA_THREADS);
+    if (need < grid) grid = need;
+    k_count<<<grid, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
+                                                        d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
+                                                        (unsigned long long*)(ctrl + CTRL_STATS));
     if (ix->timing) {
         CU(cudaEventRecord(ix->ev1[slot], st));
         ix->timed_calls++;
@@ -251,6 +271,8 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
                 cudaStreamCreateWithFlags(&ix->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
                 cudaStreamCreateWithFlags(&ix->down_stream, cudaStreamNonBlocking) != cudaSuccess))
         rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreate failed");
+    for (int i = 0; !rc && i < fmgpu_index::COUNT_CTX - 1; ++i)
+        if (cudaStreamCreateWithFlags(&ix->cstream[i], cudaStreamNonBlocking) != cudaSuccess) rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreate failed");
     for (int i = 0; !rc && i < fmgpu_index::PIPE_SLOTS; ++i)
         if (cudaEventCreateWithFlags(&ix->pipe_in[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ix->pipe_out[i], cudaEventDisableTiming) != cudaSuccess)
@@ -275,6 +297,10 @@ void fmgpu_index_free(fmgpu_index* ix) {
     for (Scratch* s : {&ix->codes, &ix->pats, &ix->ctrl, &ix->ranges, &ix->in_a, &ix->in_b, &ix->out_a, &ix->out_b, &ix->out_c,
                        &ix->tmp_a, &ix->tmp_b, &ix->order, &ix->bins})
         s->release();
+    for (int i = 0; i < fmgpu_index::COUNT_CTX - 1; ++i) {
+        for (Scratch* sc : {&ix->cctx[i].pats, &ix->cctx[i].ctrl, &ix->cctx[i].order, &ix->cctx[i].bins}) sc->release();
+        if (ix->cstream[i]) cudaStreamDestroy(ix->cstream[i]);
+    }
     if (ix->stream) cudaStreamDestroy(ix->stream);
     if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     if (ix->down_stream) cudaStreamDestroy(ix->down_stream);
@@ -321,11 +347,15 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     CU(ix->in_b.reserve(((size_t)n_pat + 1) * 8));
     CU(ix->out_a.reserve((size_t)n_pat * 4 + 64));
     CU(ix->out_b.reserve((size_t)n_pat * 4 + 64));
-    // The batch is cut into chunks so that the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels
-    // of chunk k (copy stream + compute stream, events in between).  Chunk chars land at their absolute offsets in the
-    // device buffer, so pattern offsets need no rebasing.
-    uint32_t min_chunk = 350000;
+    // The batch is cut into chunks: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k
+    // (copy stream, COUNT_CTX compute streams round-robin, download stream, events in between).  A launch lasts at least as
+    // long as its longest pattern's dependent chain (~0.2 ms), so consecutive chunks run on different compute streams and the
+    // next chunk's CTAs fill the SMs while the previous chunk's last warps drain.  Chunk chars land at their absolute offsets
+    // in the device buffer, so pattern offsets need no rebasing.
+    uint32_t min_chunk = 125000;
     if (const char* e = getenv("FMGPU_PIPE_CHUNK")) min_chunk = (uint32_t)atoi(e) > 0 ? (uint32_t)atoi(e) : min_chunk;
+    int n_ctx = fmgpu_index::COUNT_CTX;
+    if (const char* e = getenv("FMGPU_PIPE_STREAMS")) n_ctx = atoi(e) >= 1 && atoi(e) <= fmgpu_index::COUNT_CTX ? atoi(e) : n_ctx;
     uint32_t n_chunks = n_pat / min_chunk;
     if (n_chunks > (uint32_t)fmgpu_index::PIPE_SLOTS) n_chunks = fmgpu_index::PIPE_SLOTS;
     if (n_chunks < 1) n_chunks = 1;
@@ -342,10 +372,12 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     }
     for (uint32_t k = 0; k < n_chunks; ++k) {
         const uint32_t lo = (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
-        CU(cudaStreamWaitEvent(st, ix->pipe_in[k], 0));
-        int rc = count_on_stream(ix, d_chars, d_off + lo, total, hi - lo, d_counts + lo, d_status + lo, nullptr, st, k == 0);
+        const int ctx = (int)(k % (uint32_t)n_ctx);
+        cudaStream_t cs = ctx ? ix->cstream[ctx - 1] : st;
+        CU(cudaStreamWaitEvent(cs, ix->pipe_in[k], 0));
+        int rc = count_on_stream(ix, d_chars, d_off + lo, total, hi - lo, d_counts + lo, d_status + lo, nullptr, cs, k < (uint32_t)n_ctx, ctx);
         if (rc) return rc;
-        CU(cudaEventRecord(ix->pipe_out[k], st));
+        CU(cudaEventRecord(ix->pipe_out[k], cs));
         CU(cudaStreamWaitEvent(ix->down_stream, ix->pipe_out[k], 0));
         if (hi > lo) {
             CU(cudaMemcpyAsync(counts_out + lo, d_counts + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ix->down_stream));
@@ -356,6 +388,7 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     CU(cudaStreamSynchronize(ix->down_stream));
     CU(cudaStreamSynchronize(cp));
     CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < fmgpu_index::COUNT_CTX - 1; ++i) CU(cudaStreamSynchronize(ix->cstream[i]));
     return 0;
 }
 
@@ -393,10 +426,17 @@ int fmgpu_last_stats(fmgpu_index* ix, uint64_t out8[8]) {
     memset(out8, 0, 8 * sizeof(uint64_t));
     if (!ix->stats_valid || !ix->ctrl.p) return 0;
     CU(cudaDeviceSynchronize());
-    uint32_t words[CTRL_WORDS];
-    CU(cudaMemcpy(words, ix->ctrl.p, sizeof words, cudaMemcpyDeviceToHost));
-    memcpy(out8, words + CTRL_STATS, 5 * sizeof(uint64_t));
-    memcpy(out8 + 6, words + CTRL_STATS + 12, sizeof(uint64_t));
+    for (int c = 0; c < fmgpu_index::COUNT_CTX; ++c) {
+        if (!(ix->stats_ctx_mask & (1u << c))) continue;
+        void* p = c ? ix->cctx[c - 1].ctrl.p : ix->ctrl.p;
+        if (!p) continue;
+        uint32_t words[CTRL_WORDS];
+        CU(cudaMemcpy(words, p, sizeof words, cudaMemcpyDeviceToHost));
+        uint64_t v[7];
+        memcpy(v, words + CTRL_STATS, 7 * sizeof(uint64_t));
+        for (int i = 0; i < 5; ++i) out8[i] += v[i];
+        out8[6] += v[6];
+    }
     out8[5] = ix->last_launches;
     return 0;
 }

@@ -8,6 +8,8 @@ seconds instead of the minutes a sequential host suffix sorter needs.
 """
 from __future__ import annotations
 
+import sys
+
 import numpy as np
 import torch
 
@@ -43,7 +45,7 @@ def suffix_array(codes: np.ndarray, sigma: int, device=None, verbose: bool = Fal
         rank[idx] = r_sorted
         del r_sorted
         if verbose:
-            print("[gpu_sa] h=%d distinct=%d/%d" % (h, m, n), flush=True)
+            print("[gpu_sa] h=%d distinct=%d/%d" % (h, m, n), file=sys.stderr, flush=True)
         if m == n:
             sa = idx.to(torch.int32)
             del idx, rank
