@@ -145,6 +145,15 @@ void fc_sizes(void* hv, uint64_t* out8) {
     out8[7] = h->F.isa.size() * 32;
 }
 
+// design aid: number of (block, symbol) cells by kind {NORMAL, CONST, RUN, THROW}, and blocks / run blocks
+void fc_cell_kinds(void* hv, uint64_t* out6) {
+    FC* h = (FC*)hv;
+    for (int i = 0; i < 6; ++i) out6[i] = 0;
+    for (const Rec32& c : h->F.cells) out6[(c.w[2] >> 8) & 3u]++;
+    out6[4] = h->F.blocks.size();
+    for (const Rec32& b : h->F.blocks) out6[5] += b.w[1] & 1u;
+}
+
 int fc_rank(void* h, uint32_t pos, uint32_t sym, int64_t* out) {
     uint32_t v = 0;
     const int st = host_rank(*(FC*)h, pos, sym, &v, nullptr, nullptr);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage (under gpurun): bash tools/variants.sh "<nvcc -D flags variant 1>" "<variant 2>" ...   -> bench line per variant
+# usage (under gpurun): bash tools/variants.sh "<nvcc -D flags variant 1>" "<variant 2>" ...   -> count bench line per variant
 cd /root/repo
 mkdir -p gpurun_out
 python bench.py --build-only 2> gpurun_out/variants_build.log
@@ -10,7 +10,7 @@ for flags in "$@"; do
        -I include $flags -o index4j_b200/libfmgpu.so index4j_b200/csrc/fmgpu.cu -lcudart 2> gpurun_out/variant_$i.nvcc.log
   grep -A2 "k_count" gpurun_out/variant_$i.nvcc.log | grep -E "Used|spill" | tr '\n' ' '
   echo "== variant $i: $flags"
-  python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2> gpurun_out/variant_$i.log | python -c "
+  python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-lf 2> gpurun_out/variant_$i.log | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
 print('   value %.1f M/s  step %.3f ms  kernel %.3f ms  frac %.3f  e2e %.1f M/s' % (d['value']/1e6, d['ms_per_step'], r['kernel_ms'], r['frac'], d['e2e']['value']/1e6))"
