@@ -102,7 +102,9 @@ struct BlockTree {
     struct Node {
         uint32_t start, size;  // bit range in the superblock's level bitvector
         int32_t child[2];      // >= 0: internal node id; < 0: -(leaf local index + 1)
-        uint32_t sector;       // first sector (global index), set by the caller
+        uint32_t sector;       // even-depth nodes: first record (global Rec32 index, even), set by the caller
+        uint32_t depth;        // root = 0
+        uint32_t enode;        // even-depth nodes: index of the node record (global), set by the caller
     };
     std::vector<Node> nodes;  // BFS order, node 0 = root
     struct Leaf {
@@ -114,7 +116,7 @@ struct BlockTree {
     std::vector<uint16_t> sym;    // header symbol per leaf
     std::vector<uint32_t> brank;  // rankAtBlockBoundary per leaf
     int h = 0;
-    uint32_t n_sectors = 0, n_ovf_chunks = 0;
+    uint32_t n_sectors = 0, n_ovf_chunks = 0, n_even = 0;  // Rec32 units / chunks / even-depth internal nodes
 };
 
 struct VarReader {
@@ -148,6 +150,7 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
     T.brank.clear();
     T.n_sectors = 0;
     T.n_ovf_chunks = 0;
+    T.n_even = 0;
     if (sig < 1 || h < 0) throw FormatError("block header out of range");
     VarReader R(S.var);
     const int64_t var_off = H.var_off;
@@ -164,7 +167,7 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
     T.leaves.resize((size_t)sig);
     int64_t third = ptr32 + 5 * (int64_t)sig;
     std::vector<uint32_t> level;  // node ids of the current depth, left to right
-    T.nodes.push_back({(uint32_t)H.bv_offset, cur_block_size, {0, 0}, 0});
+    T.nodes.push_back({(uint32_t)H.bv_offset, cur_block_size, {0, 0}, 0, 0, 0});
     level.push_back(0);
     uint32_t level_start = (uint32_t)H.bv_offset;
     int64_t leaves_before = 0;
@@ -198,7 +201,7 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
                 } else {
                     const uint32_t nid = (uint32_t)T.nodes.size();
                     T.nodes[id].child[bit] = (int32_t)nid;
-                    T.nodes.push_back({next_start + run, csize, {0, 0}, 0});
+                    T.nodes.push_back({next_start + run, csize, {0, 0}, 0, (uint32_t)d + 1u, 0});
                     run += csize;
                     next.push_back(nid);
                 }
@@ -233,9 +236,16 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
         if (len > 32) throw FormatError("Huffman code longer than 32 bits");
         L.len = (uint8_t)len;
         L.code = code;  // bit (len-1) = root decision
-        if (len > (int)fmgpu::CELL_INLINE_LEVELS) T.n_ovf_chunks += (uint32_t)((len - 4 + 7) / 8);
+        // the cell holds the records of the even-depth nodes on the path: (len+1)/2 entries, 5 inline
+        const int pairs = (len + 1) / 2;
+        if (pairs > (int)fmgpu::CELL_INLINE_PAIRS) T.n_ovf_chunks += (uint32_t)((pairs - ((int)fmgpu::CELL_INLINE_PAIRS - 1) + 7) / 8);
     }
-    for (auto& n : T.nodes) T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
+    for (auto& n : T.nodes)
+        if ((n.depth & 1u) == 0) {
+            if (n.size > 65536u) throw FormatError("wavelet node larger than a block");
+            T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
+            ++T.n_even;
+        }
 }
 
 struct SbPlan {
@@ -309,52 +319,87 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         }
         block_node_base[b] = node;
         block_ovf_base[b] = ovf;
-        for (auto& n : T.nodes) {
-            n.sector = (uint32_t)sec;
-            const uint32_t nsec = n.size / fmgpu::SECTOR_BITS + 1;
-            if ((uint64_t)n.start + n.size > nbits) throw FormatError("wavelet node exceeds the level bitvector");
-            uint32_t ones = 0;
-            for (uint32_t s = 0; s < nsec; ++s) {
-                Rec32& X = F.sectors[(size_t)sec + s];
-                X.w[0] = ones;
-                const uint32_t lo = s * fmgpu::SECTOR_BITS;
-                for (int k = 0; k < 7; ++k) {
-                    const uint32_t p = lo + 32u * (uint32_t)k;
-                    uint32_t word = 0;
-                    if (p < n.size) {
-                        const int take = (int)std::min<uint32_t>(32, n.size - p);
-                        word = bits_get(bits, (uint64_t)n.start + p, take);
-                    }
-                    X.w[1 + k] = word;
-                    ones += (uint32_t)__builtin_popcount(word);
-                }
+        // record arrays and node-record indices of the even-depth nodes
+        {
+            uint64_t e = node;
+            for (auto& n : T.nodes) {
+                if (n.depth & 1u) continue;
+                n.sector = (uint32_t)sec;
+                n.enode = (uint32_t)e++;
+                sec += n.size / fmgpu::SECTOR_BITS + 1;
             }
-            sec += nsec;
         }
+        auto leaf_entry = [&](int32_t c, uint32_t flag, uint32_t* e) {
+            const size_t li = (size_t)(-c - 1);
+            const uint32_t sy = T.sym[li];
+            const uint64_t base = (uint64_t)W.hyper_rank[sy < (uint32_t)sigma ? sy : 0] +
+                                  (uint64_t)(sy < (uint32_t)sigma ? W.sb_rank[sb * (size_t)sigma + sy] : 0) + T.brank[li];
+            e[0] = flag | sy;
+            e[1] = (uint32_t)base;
+        };
         for (size_t id = 0; id < T.nodes.size(); ++id) {
-            uint32_t rec[4];
-            for (int bit = 0; bit < 2; ++bit) {
-                const int32_t c = T.nodes[id].child[bit];
-                if (c < 0) {
-                    const size_t li = (size_t)(-c - 1);
-                    const uint32_t s = T.sym[li];
-                    const uint64_t base = (uint64_t)W.hyper_rank[s < (uint32_t)sigma ? s : 0] +
-                                          (uint64_t)(s < (uint32_t)sigma ? W.sb_rank[sb * (size_t)sigma + s] : 0) + T.brank[li];
-                    rec[bit] = fmgpu::LEAF_FLAG | s;
-                    rec[2 + bit] = (uint32_t)base;
-                } else {
-                    rec[bit] = (uint32_t)(node + (uint64_t)c);
-                    rec[2 + bit] = T.nodes[(size_t)c].sector;
+            const BlockTree::Node& n = T.nodes[id];
+            if (n.depth & 1u) continue;
+            if ((uint64_t)n.start + n.size > nbits) throw FormatError("wavelet node exceeds the level bitvector");
+            const BlockTree::Node* ch[2] = {n.child[0] >= 0 ? &T.nodes[(size_t)n.child[0]] : nullptr,
+                                            n.child[1] >= 0 ? &T.nodes[(size_t)n.child[1]] : nullptr};
+            for (int t = 0; t < 2; ++t)
+                if (ch[t] && (uint64_t)ch[t]->start + ch[t]->size > nbits) throw FormatError("wavelet node exceeds the level bitvector");
+            // level records (layout.h): {c1, c01 | c11 << 16, 96 bits of this node, for the same 96 positions the bit each
+            // element has one level further down (in the child it goes to; 0 if that child is a leaf)}
+            const uint32_t nrec = n.size / fmgpu::SECTOR_BITS + 1;
+            uint32_t ones = 0, cpos[2] = {0, 0}, cones[2] = {0, 0};
+            for (uint32_t q = 0; q < nrec; ++q) {
+                Rec32& X = F.sectors[(size_t)n.sector + q];
+                memset(&X, 0, sizeof X);
+                if (cones[0] > 0xffffu || cones[1] > 0xffffu) throw FormatError("wavelet child with more than 65535 ones");
+                X.w[0] = ones;
+                X.w[1] = cones[0] | (cones[1] << 16);
+                const uint32_t lo = q * fmgpu::SECTOR_BITS;
+                const uint32_t valid = lo < n.size ? std::min<uint32_t>(fmgpu::SECTOR_BITS, n.size - lo) : 0u;
+                for (uint32_t i = 0; i < valid; ++i) {
+                    const uint32_t t = bits_get(bits, (uint64_t)n.start + lo + i, 1);
+                    uint32_t cb = 0;
+                    if (ch[t]) {
+                        if (cpos[t] >= ch[t]->size) throw FormatError("wavelet child smaller than its parent's share");
+                        cb = bits_get(bits, (uint64_t)ch[t]->start + cpos[t], 1);
+                    }
+                    ++cpos[t];
+                    if (t) {
+                        X.w[2 + (i >> 5)] |= 1u << (i & 31u);
+                        ++ones;
+                    }
+                    if (cb) {
+                        X.w[5 + (i >> 5)] |= 1u << (i & 31u);
+                        ++cones[t];
+                    }
                 }
             }
-            const uint64_t gi = node + id;
-            memcpy(&F.nodes[(size_t)(gi >> 1)].w[(gi & 1) * 4], rec, 16);
+            // node record: entries [t][u] = {c, a}; child t a leaf: [t][0] = {LEAF1 | sym, boundary rank}
+            Rec32& NR = F.nodes[(size_t)n.enode];
+            memset(&NR, 0, sizeof NR);
+            for (int t = 0; t < 2; ++t) {
+                if (!ch[t]) {
+                    leaf_entry(n.child[t], fmgpu::LEAF1_FLAG, &NR.w[4 * t]);
+                    continue;
+                }
+                for (int u = 0; u < 2; ++u) {
+                    const int32_t g = ch[t]->child[u];
+                    uint32_t* e = &NR.w[4 * t + 2 * u];
+                    if (g < 0) {
+                        leaf_entry(g, fmgpu::LEAF_FLAG, e);
+                    } else {
+                        e[0] = T.nodes[(size_t)g].enode;
+                        e[1] = T.nodes[(size_t)g].sector;
+                    }
+                }
+            }
             if (id == 0) {
-                D.w[0] = T.nodes[0].sector;
-                memcpy(&D.w[4], rec, 16);
+                D.w[0] = n.sector;
+                D.w[4] = n.enode;
             }
         }
-        node += T.nodes.size();
+        node += T.n_even;
         ovf += T.n_ovf_chunks;
     }
 
@@ -431,26 +476,28 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                         cell.w[0] = (uint32_t)(rank_hb + rank_sb + rank_blk);
                         cell.w[1] = L.code;
                         cell.w[2] = (uint32_t)L.len | (fmgpu::CELL_NORMAL << 8);
-                        // node ids along the path, root first
-                        uint32_t path[32];
+                        // records of the even-depth nodes along the path, root first
+                        uint32_t path[17];
+                        const int pairs = (L.len + 1) / 2;
                         {
                             int32_t id = 0;
                             for (int d = 0; d < L.len; ++d) {
-                                path[d] = T.nodes[(size_t)id].sector;
+                                if ((d & 1) == 0) path[d >> 1] = T.nodes[(size_t)id].sector;
                                 if (d + 1 < L.len) id = T.nodes[(size_t)id].child[(L.code >> (L.len - 1 - d)) & 1];
                             }
                         }
-                        if (L.len <= (int)fmgpu::CELL_INLINE_LEVELS) {
-                            for (int d = 0; d < L.len; ++d) cell.w[3 + d] = path[d];
+                        if (pairs <= (int)fmgpu::CELL_INLINE_PAIRS) {
+                            for (int k = 0; k < pairs; ++k) cell.w[3 + k] = path[k];
                         } else {
-                            for (int d = 0; d < 4; ++d) cell.w[3 + d] = path[d];
-                            const uint32_t chunks = (uint32_t)((L.len - 4 + 7) / 8);
+                            const int inl = (int)fmgpu::CELL_INLINE_PAIRS - 1;
+                            for (int k = 0; k < inl; ++k) cell.w[3 + k] = path[k];
+                            const uint32_t chunks = (uint32_t)((pairs - inl + 7) / 8);
                             const uint32_t at = ovf_next[(size_t)b];
                             ovf_next[(size_t)b] += chunks;
                             cell.w[7] = at;
                             for (uint32_t k = 0; k < chunks * 8; ++k) {
-                                const int d = 4 + (int)k;
-                                F.ovf[(size_t)at + k / 8].w[k % 8] = d < L.len ? path[d] : 0xffffffffu;
+                                const int q = inl + (int)k;
+                                F.ovf[(size_t)at + k / 8].w[k % 8] = q < pairs ? path[q] : 0xffffffffu;
                             }
                         }
                     }
@@ -567,7 +614,7 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
         for (size_t b = 0; b < S.blocks.size(); ++b) {
             build_block_tree(S, b, sb_block_size(W, sb, b), T);
             P.n_sectors += T.n_sectors;
-            P.n_nodes += T.nodes.size();
+            P.n_nodes += T.n_even;
             P.n_ovf += T.n_ovf_chunks;
         }
     });
@@ -593,7 +640,7 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
         throw FormatError("alphabet x block count too large for the dense cell table (" + std::to_string(cell_bytes >> 20) + " MiB)");
     F.cells.assign((size_t)(blocks_total * (uint64_t)W.sigma), Rec32{});
     F.sectors.assign((size_t)sectors_total + 1, Rec32{});
-    F.nodes.assign((size_t)(nodes_total / 2 + 1), Rec32{});
+    F.nodes.assign((size_t)nodes_total + 1, Rec32{});
     F.ovf.assign((size_t)ovf_total + 1, Rec32{});
     F.blocks.assign((size_t)blocks_total + 1, Rec32{});
 

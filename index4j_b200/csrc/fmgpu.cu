@@ -85,8 +85,7 @@ struct fmgpu_index {
     uint64_t total_bytes = 0;
     int32_t alphabet_length = 0;
     int sm_count = 0;
-    int count_ctas = 0, lf_ctas = 0, locate_ctas = 0, extract_ctas = 0, eub_ctas = 0;
-    bool locate_v1 = false;
+    int count_ctas = 0, locate_ctas = 0, extract_ctas = 0, eub_ctas = 0;
     size_t tables_smem = 0;
     std::mutex mu;  // batch calls on one handle are serialised (v0)
     cudaStream_t stream = nullptr, copy_stream = nullptr, down_stream = nullptr;

@@ -20,6 +20,14 @@
 #include "layout.h"
 #include "ldrec.h"
 
+// experiment knobs (tools/variants.sh): L2 eviction priority of the backward-search loads (ld256 / ld256_keep / ld256_stream)
+#ifndef COUNT_LD_CELL
+#define COUNT_LD_CELL ld256
+#endif
+#ifndef COUNT_LD_SECTOR
+#define COUNT_LD_SECTOR ld256
+#endif
+
 namespace fmgpu {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -149,17 +157,17 @@ struct WalkOut {
     uint32_t a, b, err;
 };
 
-// one wavelet level for two positions of the same node (WaveletFixedBlockBoosting.java:1185-1279)
-__device__ __forceinline__ void level_pair(const DevIndex& ix, uint32_t node, uint32_t bit, uint32_t& ra, uint32_t& rb, uint32_t& n_load) {
+// two wavelet levels (one level record) for two positions of the same even-depth node
+// (WaveletFixedBlockBoosting.java:1185-1279); `two` = the code has a second level below this one
+__device__ __forceinline__ void dlevel_pair(const DevIndex& ix, uint32_t node, uint32_t t, uint32_t u, bool two, uint32_t& ra, uint32_t& rb,
+                                            uint32_t& n_load) {
     const uint32_t qa = ra / SECTOR_BITS, qb = rb / SECTOR_BITS;
-    const Rec32 A = ld256(ix.sectors + (node + qa));
+    const Rec32 A = COUNT_LD_SECTOR(ix.sectors + (node + qa));
     Rec32 B = A;
-    if (qb != qa) B = ld256(ix.sectors + (node + qb));
+    if (qb != qa) B = COUNT_LD_SECTOR(ix.sectors + (node + qb));
     n_load += qb != qa ? 2u : 1u;
-    const uint32_t ones_a = sector_rank(A, ra - qa * SECTOR_BITS);
-    const uint32_t ones_b = sector_rank(B, rb - qb * SECTOR_BITS);
-    ra = bit ? ones_a : ra - ones_a;
-    rb = bit ? ones_b : rb - ones_b;
+    ra = dlevel_rank(A, ra, ra - qa * SECTOR_BITS, t, u, two);
+    rb = dlevel_rank(B, rb, rb - qb * SECTOR_BITS, t, u, two);
 }
 
 // rank(., c) of two positions of ONE block: ra/rb are block-relative positions (rb == ra for a single query)
@@ -168,7 +176,7 @@ __device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, u
     WalkOut o;
     o.a = o.b = o.err = 0;
     if (!on) return o;
-    const Rec32 cell = ld256(ix.cells + ((uint64_t)blk * ix.sigma + c));
+    const Rec32 cell = COUNT_LD_CELL(ix.cells + ((uint64_t)blk * ix.sigma + c));
     ++n_load;
     const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
     const uint32_t base = cell.w[0];
@@ -181,13 +189,16 @@ __device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, u
     }
     const uint32_t code = cell.w[1];
     const uint32_t L = cell.w[2] & 0xffu;
-    const uint32_t inl = L > CELL_INLINE_LEVELS ? 4u : L;
-#pragma unroll
-    for (uint32_t d = 0; d < CELL_INLINE_LEVELS; ++d)
-        if (d < inl) level_pair(ix, cell.w[3 + d], (code >> (L - 1u - d)) & 1u, ra, rb, n_load);
-    if (L > CELL_INLINE_LEVELS) {  // deep codes (rare symbols): the rest of the path is in the overflow array
-        const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);
-        for (uint32_t d = 4; d < L; ++d) level_pair(ix, __ldg(more + (d - 4u)), (code >> (L - 1u - d)) & 1u, ra, rb, n_load);
+    const uint32_t pairs = (L + 1u) >> 1;
+    const uint32_t inl = pairs > CELL_INLINE_PAIRS ? CELL_INLINE_PAIRS - 1u : pairs;
+    const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);  // codes longer than 10 bits: rest of the path
+#pragma unroll 1
+    for (uint32_t k = 0; k < pairs; ++k) {
+        const uint32_t node = k < inl ? rec_word(cell, 3u + k) : __ldg(more + (k - inl));
+        const uint32_t d = 2u * k;
+        const bool two = d + 1u < L;
+        const uint32_t t = (code >> (L - 1u - d)) & 1u;
+        dlevel_pair(ix, node, t, two ? (code >> (L - 2u - d)) & 1u : 0u, two, ra, rb, n_load);
     }
     n_level += L * queries;
     o.a = base + ra;
@@ -196,7 +207,7 @@ __device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, u
 }
 
 #ifndef COUNT_MIN_CTAS
-#define COUNT_MIN_CTAS 5
+#define COUNT_MIN_CTAS 4
 #endif
 __global__ void __launch_bounds__(CTA_THREADS, COUNT_MIN_CTAS)
 k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,

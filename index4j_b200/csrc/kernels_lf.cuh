@@ -1,9 +1,5 @@
-// LF-walk kernels: locate, extract, extractUntilBoundary* (lane machine in walk_lane.h) and the
-// small helper kernels around them (hit counting, exclusive scan, row expansion, left-part
-// assembly).  Divergent walks stay dense because a lane that finishes its item is refilled from a
-// global queue at the next trip (__ballot_sync of the idle lanes, one atomicAdd per warp), and
-// because every lane — whatever phase it is in — issues its 256-bit record loads at the same
-// point of the trip.
+// Helper kernels around the LF-walk kernels of kernels_locate.cuh: hit counting, exclusive scan, row expansion,
+// left-part assembly of extractUntilBoundary.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -12,67 +8,6 @@
 #include "walk_lane.h"
 
 namespace fmgpu {
-
-constexpr uint32_t WALK_SMEM_PREFIX_WORDS = 128;  // 15x16 u16 binomial table lives in the first 480 bytes
-
-template <int MODE>
-__global__ void __launch_bounds__(CTA_THREADS)
-k_walk(const DevIndex ix, WalkParams P, unsigned int* queue, unsigned long long* stats) {
-    extern __shared__ uint32_t smem[];
-    uint16_t* binom = reinterpret_cast<uint16_t*>(smem);
-    if (threadIdx.x == 0) fill_binom(binom);
-    const SmemTables T = stage_tables(ix, smem + WALK_SMEM_PREFIX_WORDS);  // ends with __syncthreads()
-    P.binom = binom;
-    if (MODE == WM_EUB) P.mb = (uint32_t)__ldg(ix.char2code + (P.mb & 0xffffu));
-    const unsigned lane_id = threadIdx.x & 31u;
-
-    WalkLane<MODE> lane;
-    lane.init();
-    WalkCounters cnt;
-    cnt.lf_steps = cnt.lf_levels = cnt.ranks = cnt.rank_levels = cnt.sbits = 0;
-
-    for (;;) {
-        const unsigned idle = __ballot_sync(FULL, lane.phase == W_IDLE);
-        if (idle) {
-            const int leader = __ffs(idle) - 1;
-            unsigned base = 0;
-            if ((int)lane_id == leader) base = atomicAdd(queue, (unsigned)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (lane.phase == W_IDLE) {
-                lane.w = base + __popc(idle & ((1u << lane_id) - 1u));
-                lane.phase = lane.w < P.n_items ? W_ITEM : W_EXIT;
-            }
-        }
-        if (!__any_sync(FULL, lane.phase != W_EXIT)) break;
-
-        ItemRaw raw;
-        raw.a = raw.b = 0;
-        raw.o0 = raw.o1 = 0;
-        if (lane.phase == W_ITEM) raw = walk_load_item<MODE>(P, lane.w);
-        Rec32 A, B;
-        const bool na = lane.needs_a();
-        if (na) A = ld256(lane.addr_a);
-        if (na && lane.need_b) B = ld256(lane.addr_b);
-        lane.step(ix, T, P, raw, A, B, cnt);
-    }
-
-    for (int o = 16; o; o >>= 1) {
-        cnt.ranks += __shfl_xor_sync(FULL, cnt.ranks, o);
-        cnt.rank_levels += __shfl_xor_sync(FULL, cnt.rank_levels, o);
-        cnt.lf_steps += __shfl_xor_sync(FULL, cnt.lf_steps, o);
-        cnt.lf_levels += __shfl_xor_sync(FULL, cnt.lf_levels, o);
-        cnt.sbits += __shfl_xor_sync(FULL, cnt.sbits, o);
-    }
-    if (lane_id == 0 && stats) {
-        atomicAdd(stats + 0, (unsigned long long)cnt.ranks);
-        atomicAdd(stats + 1, (unsigned long long)cnt.rank_levels);
-        atomicAdd(stats + 2, (unsigned long long)cnt.lf_steps);
-        atomicAdd(stats + 3, (unsigned long long)cnt.lf_levels);
-        atomicAdd(stats + 4, (unsigned long long)cnt.sbits);
-    }
-}
-
-inline size_t walk_smem_bytes(const DevIndex& ix) { return WALK_SMEM_PREFIX_WORDS * 4 + tables_smem_bytes(ix); }
 
 // hits per pattern: min(count, maxMatches), maxMatches <= 0 = unlimited (FmIndex.java:544)
 __global__ void k_hits(const int32_t* __restrict__ counts, uint32_t n_pat, int32_t max_hits, int32_t* __restrict__ n_hits) {

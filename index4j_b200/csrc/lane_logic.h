@@ -4,14 +4,15 @@
 // (tests/support/flatcheck.cpp) that replays them against the CPU oracle.
 //
 // Reference semantics restated here (paths under indices/src/main/java/com/dynatrace/):
-//   rank_*   wavelet/WaveletFixedBlockBoosting.java:1010-1285 (rank)
-//   lf_*     wavelet/WaveletFixedBlockBoosting.java:1305-1537 (inverseSelect)
-//   sg_*     bitsequence/RrrVector.java:314-396 (access, rankOnes) + tables :8692-16899
+//   dlevel_rank / rank_single   wavelet/WaveletFixedBlockBoosting.java:1010-1285 (rank)
+//   dlevel_descend              wavelet/WaveletFixedBlockBoosting.java:1305-1537 (inverseSelect)
+//   rrr_*                       bitsequence/RrrVector.java:111-129 + tables :8692-16899
 //   eub_*    fm/FmIndex.java:692-758, 772-831, 844-922 (control flow of extractUntilBoundary*)
 #pragma once
 #include <cstdint>
 
 #include "layout.h"
+#include "ldrec.h"
 
 #if defined(__CUDACC__)
 #define FMGPU_HD __host__ __device__ __forceinline__
@@ -50,234 +51,136 @@ FMGPU_HD uint32_t low_mask_clamped(int width) {
 #endif
 }
 
-// ones among the first `nbits` (< 224) payload bits of a level sector, plus its running count
-FMGPU_HD uint32_t sector_rank(const Rec32& s, uint32_t nbits) {
-    uint32_t ones = s.w[0];
-#pragma unroll
-    for (int k = 0; k < 7; ++k) ones += popc32(s.w[1 + k] & low_mask_clamped((int)nbits - 32 * k));
-    return ones;
-}
-FMGPU_HD uint32_t sector_bit(const Rec32& s, uint32_t b) { return (rec_word(s, 1u + (b >> 5)) >> (b & 31u)) & 1u; }
-
 struct SmemTables {  // C array and superblock descriptors (shared memory when they fit)
     const uint32_t* C;
     const SbDesc* sb;
 };
 
 // ------------------------------------------------------------------------------------------
-// rank(pos, sym)
+// level records (layout.h): two tree levels from one 64-byte record
 // ------------------------------------------------------------------------------------------
-struct RankSt {
-    uint32_t base, code, r, L, d, inl, ovf, bix;
-    uint32_t p0, p1, p2, p3, p4, p5, p6, p7;  // sector of the node at depth d, d+1, ... (shift register)
-};
-enum RankOut : uint32_t { RK_MORE = 0, RK_DONE = 1, RK_THROW = 2 };
+// elements among the first b positions of a level record whose bits at the record's two levels are (t, u): one pass over
+// (plane0 ^ ~T) & (plane1 ^ ~U) & mask.  With `one` set the second level is ignored (count of bit t alone).
+FMGPU_HD uint32_t dlevel_count(const Rec32& x, uint32_t b, uint32_t t, uint32_t u, bool one) {
+    const uint32_t tm = t ? 0u : 0xffffffffu;
+    const uint32_t um = u ? 0u : 0xffffffffu;
+    const uint32_t all = one ? 0xffffffffu : 0u;
+    uint32_t n = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) n += popc32((x.w[2 + k] ^ tm) & ((x.w[5 + k] ^ um) | all) & low_mask_clamped((int)b - 32 * k));
+    return n;
+}
+// elements before the record (P of them) with bits (t) / (t, u)
+FMGPU_HD uint32_t dlevel_base1(const Rec32& x, uint32_t P, uint32_t t) { return t ? x.w[0] : P - x.w[0]; }
+FMGPU_HD uint32_t dlevel_base2(const Rec32& x, uint32_t P, uint32_t t, uint32_t u) {
+    const uint32_t c01 = x.w[1] & 0xffffu, c11 = x.w[1] >> 16;
+    const uint32_t a = t ? c11 : c01;               // (t, 1)
+    const uint32_t tot = t ? x.w[0] : P - x.w[0];   // (t, *)
+    return u ? a : tot - a;
+}
+FMGPU_HD uint32_t plane_bit(const Rec32& x, uint32_t plane, uint32_t b) { return (rec_word(x, 2u + 3u * plane + (b >> 5)) >> (b & 31u)) & 1u; }
 
-// Guards of rank (:1012-1020) and the address of the (block, symbol) cell.  RK_MORE: fetch *addr;
-// RK_DONE: answer in *val; RK_THROW: the reference's ArrayIndexOutOfBounds for position == size
-// on a superblock boundary (:1022-1026).
-FMGPU_HD uint32_t rank_begin(const DevIndex& ix, const SmemTables& T, uint32_t pos, uint32_t sym, RankSt& s, const Rec32** addr,
-                             uint32_t* val) {
-    if (pos == 0) {
-        *val = 0;
-        return RK_DONE;
-    }
-    if (pos > ix.length) pos = ix.length;
-    if (sym >= ix.sigma) {
-        *val = 0;
-        return RK_DONE;
-    }
-    if (ix.q4 && pos == ix.length) return RK_THROW;
-    const SbDesc sd = T.sb[pos >> SB_LOG];
-    const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
-    s.bix = pos & ((1u << sd.block_log) - 1u);
-    *addr = ix.cells + ((uint64_t)blk * ix.sigma + sym);
-    return RK_MORE;
+// The rank walk of WaveletFixedBlockBoosting.rank (:1185-1279) for the two levels a record holds: position r of the
+// even-depth node (b = r mod 96 inside the record), code bits t (this level) and u (next level).
+//   one level : returns the position in child t
+//   two levels: returns the position in grandchild (t, u)
+FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t r, uint32_t b, uint32_t t, uint32_t u, bool two) {
+    const uint32_t n = dlevel_count(x, b, t, u, !two);
+    const uint32_t base = two ? dlevel_base2(x, r - b, t, u) : dlevel_base1(x, r - b, t);
+    return base + n;
 }
 
-FMGPU_HD uint32_t rank_on_cell(const DevIndex& ix, const Rec32& A, RankSt& s, const Rec32** addr, uint32_t* val) {
-    const uint32_t kind = (A.w[2] >> 8) & 0xffu;
+// The descent of WaveletFixedBlockBoosting.inverseSelect (:1386-1505) through the two levels of a record with the node
+// record N of the even-depth node.  Returns true at a leaf (*sym, *rank = rank(pos, sym) incl. the boundary rank);
+// false: continue at node record *nrec / level record *sec with position *r.
+FMGPU_HD bool dlevel_descend(const Rec32& x, const Rec32& N, uint32_t b, uint32_t* r, uint32_t* nrec, uint32_t* sec, uint32_t* sym,
+                             uint32_t* rank, uint32_t* levels) {
+    const uint32_t t = plane_bit(x, 0, b);
+    const uint32_t u = plane_bit(x, 1, b);
+    const uint32_t e0 = t ? N.w[4] : N.w[0];
+    const uint32_t a0 = t ? N.w[5] : N.w[1];
+    const bool leaf1 = (e0 & LEAF1_FLAG) != 0u;
+    const uint32_t n = dlevel_count(x, b, t, u, leaf1);
+    const uint32_t P = *r - b;
+    if (leaf1) {
+        ++*levels;
+        *sym = e0 & 0xffffu;
+        *rank = a0 + dlevel_base1(x, P, t) + n;
+        return true;
+    }
+    *levels += 2;
+    const uint32_t r2 = dlevel_base2(x, P, t, u) + n;
+    const uint32_t e1 = t ? N.w[6] : N.w[2];
+    const uint32_t a1 = t ? N.w[7] : N.w[3];
+    const uint32_t e = u ? e1 : e0;
+    const uint32_t a = u ? a1 : a0;
+    if (e & LEAF_FLAG) {
+        *sym = e & 0xffffu;
+        *rank = a + r2;
+        return true;
+    }
+    *nrec = e;
+    *sec = a;
+    *r = r2;
+    return false;
+}
+
+// ------------------------------------------------------------------------------------------
+// rank(pos, sym), one query (wavelet/WaveletFixedBlockBoosting.java:1010-1285).  Returns 0, or 9 where the reference
+// throws (position == size on a superblock boundary, :1022-1026).  *n_rank / *n_level count cells fetched / levels walked.
+// ------------------------------------------------------------------------------------------
+FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t pos, uint32_t sym, uint32_t* out, uint32_t* n_rank,
+                              uint32_t* n_level) {
+    *out = 0;
+    if (pos == 0) return 0u;            // :1012
+    if (pos > ix.length) pos = ix.length;  // :1015
+    if (sym >= ix.sigma) return 0u;     // :1018
+    if (ix.q4 && pos == ix.length) return 9u;
+    const SbDesc sd = T.sb[pos >> SB_LOG];
+    const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
+    uint32_t r = pos & ((1u << sd.block_log) - 1u);
+    const Rec32 cell = FMGPU_LD256(ix.cells + ((uint64_t)blk * ix.sigma + sym));
+    ++*n_rank;
+    const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
     if (kind == CELL_CONST) {
-        *val = A.w[0];
-        return RK_DONE;
+        *out = cell.w[0];
+        return 0u;
     }
     if (kind == CELL_RUN) {  // :1141-1146
-        *val = A.w[0] + s.bix;
-        return RK_DONE;
+        *out = cell.w[0] + r;
+        return 0u;
     }
-    if (kind == CELL_THROW) return RK_THROW;
-    s.base = A.w[0];
-    s.code = A.w[1];
-    s.L = A.w[2] & 0xffu;
-    s.r = s.bix;
-    s.d = 0;
-    s.p0 = A.w[3];
-    s.p1 = A.w[4];
-    s.p2 = A.w[5];
-    s.p3 = A.w[6];
-    s.p4 = A.w[7];
-    s.ovf = A.w[7];
-    s.inl = s.L > CELL_INLINE_LEVELS ? 4u : s.L;
-    *addr = ix.sectors + (s.p0 + s.r / SECTOR_BITS);
-    return RK_MORE;
+    if (kind == CELL_THROW) return 9u;
+    const uint32_t code = cell.w[1];
+    const uint32_t L = cell.w[2] & 0xffu;
+    const uint32_t pairs = (L + 1u) >> 1;
+    const uint32_t inl = pairs > CELL_INLINE_PAIRS ? CELL_INLINE_PAIRS - 1u : pairs;
+    for (uint32_t k = 0; k < pairs; ++k) {
+        uint32_t node;
+        if (k < inl) {
+            node = rec_word(cell, 3u + k);
+        } else {
+            const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);
+            node = FMGPU_LDG32(more + (k - inl));
+        }
+        const uint32_t d = 2u * k;
+        const bool two = d + 1u < L;
+        const Rec32 x = FMGPU_LD256(ix.sectors + (node + r / SECTOR_BITS));
+        const uint32_t t = (code >> (L - 1u - d)) & 1u;
+        const uint32_t u = two ? (code >> (L - 2u - d)) & 1u : 0u;
+        r = dlevel_rank(x, r, r % SECTOR_BITS, t, u, two);
+    }
+    *n_level += L;
+    *out = cell.w[0] + r;
+    return 0u;
 }
 
-// One level of the walk (:1185-1279).  RK_DONE with *val, or RK_MORE with *addr; *want_ovf says the
-// next fetch is a path chunk rather than a level sector.
-FMGPU_HD uint32_t rank_on_level(const DevIndex& ix, const Rec32& A, RankSt& s, const Rec32** addr, uint32_t* val, bool* want_ovf) {
-    const uint32_t ones = sector_rank(A, s.r % SECTOR_BITS);
-    const uint32_t bit = (s.code >> (s.L - 1u - s.d)) & 1u;
-    s.r = bit ? ones : s.r - ones;
-    ++s.d;
-    *want_ovf = false;
-    if (s.d == s.L) {
-        *val = s.base + s.r;
-        return RK_DONE;
-    }
-    s.p0 = s.p1;
-    s.p1 = s.p2;
-    s.p2 = s.p3;
-    s.p3 = s.p4;
-    s.p4 = s.p5;
-    s.p5 = s.p6;
-    s.p6 = s.p7;
-    --s.inl;
-    if (s.inl == 0) {
-        *addr = ix.ovf + s.ovf;
-        *want_ovf = true;
-    } else {
-        *addr = ix.sectors + (s.p0 + s.r / SECTOR_BITS);
-    }
-    return RK_MORE;
-}
-
-FMGPU_HD void rank_on_ovf(const DevIndex& ix, const Rec32& A, RankSt& s, const Rec32** addr) {
-    s.p0 = A.w[0];
-    s.p1 = A.w[1];
-    s.p2 = A.w[2];
-    s.p3 = A.w[3];
-    s.p4 = A.w[4];
-    s.p5 = A.w[5];
-    s.p6 = A.w[6];
-    s.p7 = A.w[7];
-    s.inl = 8;
-    ++s.ovf;
-    *addr = ix.sectors + (s.p0 + s.r / SECTOR_BITS);
-}
-
-// ------------------------------------------------------------------------------------------
-// inverseSelect(pos): symbol at pos and its rank, walking DOWN the block's tree.
-// ------------------------------------------------------------------------------------------
-struct LfSt {
-    uint32_t r, c0, c1, a0, a1, nrec, bmask;
-};
-enum LfOut : uint32_t { LF_MORE = 0, LF_LEAF = 1, LF_RUN = 2 };
-
-FMGPU_HD void lf_begin(const DevIndex& ix, const SmemTables& T, uint32_t pos, LfSt& s, const Rec32** addr) {
-    const SbDesc sd = T.sb[pos >> SB_LOG];
-    const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
-    s.bmask = (1u << sd.block_log) - 1u;
-    s.r = pos & s.bmask;
-    *addr = ix.blocks + blk;
-}
-// LF_RUN: single-symbol block, *sym = the symbol as inverseSelect decodes it (low byte only, :1329-1332);
-// LF_MORE: fetch the root's level sector at *addr.
-FMGPU_HD uint32_t lf_on_block(const DevIndex& ix, const Rec32& D, LfSt& s, const Rec32** addr, uint32_t* sym) {
-    if (D.w[1] & 1u) {
-        *sym = (D.w[1] >> 8) & 0xffffu;
-        return LF_RUN;
-    }
-    s.c0 = D.w[4];
-    s.c1 = D.w[5];
-    s.a0 = D.w[6];
-    s.a1 = D.w[7];
-    *addr = ix.sectors + (D.w[0] + s.r / SECTOR_BITS);
-    return LF_MORE;
-}
-FMGPU_HD void lf_take_record(const Rec32& B, LfSt& s) {  // node record fetched alongside the level sector
-    const uint32_t h = (s.nrec & 1u) * 4u;
-    s.c0 = h ? B.w[4] : B.w[0];
-    s.c1 = h ? B.w[5] : B.w[1];
-    s.a0 = h ? B.w[6] : B.w[2];
-    s.a1 = h ? B.w[7] : B.w[3];
-}
-// One level (:1386-1505).  LF_LEAF: *sym and *rk = rank(pos, sym); LF_MORE: next level sector at
-// *addr_a and the child's node record at *addr_b.
-FMGPU_HD uint32_t lf_on_level(const DevIndex& ix, const Rec32& A, LfSt& s, const Rec32** addr_a, const Rec32** addr_b, uint32_t* sym,
-                              uint32_t* rk) {
-    const uint32_t b = s.r % SECTOR_BITS;
-    const uint32_t ones = sector_rank(A, b);
-    const uint32_t bit = sector_bit(A, b);
-    const uint32_t cb = bit ? s.c1 : s.c0;
-    const uint32_t ab = bit ? s.a1 : s.a0;
-    s.r = bit ? ones : s.r - ones;
-    if (cb & LEAF_FLAG) {
-        *sym = cb & 0xffffu;
-        *rk = ab + s.r;
-        return LF_LEAF;
-    }
-    s.nrec = cb;
-    *addr_a = ix.sectors + (ab + s.r / SECTOR_BITS);
-    *addr_b = ix.nodes + (cb >> 1);
-    return LF_MORE;
-}
-
-// ------------------------------------------------------------------------------------------
-// sampled-row bitvector (RRR): access(pos) and rankOnes(pos) from one group record (+ offset bits)
-// ------------------------------------------------------------------------------------------
 // BITS_NEEDED_BINOMIAL_COEFFICIENTS (RrrVector.java:111-129), one nibble per class
 // classes 0..15 need 1,4,7,9,11,12,13,13,13,13,12,11,9,7,4,1 bits (nibble c of the constant = class c)
 constexpr unsigned long long RRR_BITS_NEEDED = 0x1479BCDDDDCB9741ULL;
 FMGPU_HD uint32_t rrr_bits(uint32_t cls) { return (uint32_t)(RRR_BITS_NEEDED >> (4u * cls)) & 15u; }
 
-struct SgSt {
-    uint32_t ones, offb, cls, use;
-};
-enum SgOut : uint32_t { SG_DONE = 0, SG_OFFSET = 1 };
-
 FMGPU_HD const Rec32* sg_addr(const DevIndex& ix, uint32_t pos) { return ix.sgroups + ((pos / RRR_BLOCK) >> 5); }
-
-// SG_DONE: *bit = access(pos), *rank = rankOnes(pos).  SG_OFFSET: the block's offset field is
-// needed; fetch offsets record *addr_a (and *addr_b when *straddle).
-FMGPU_HD uint32_t sg_on_group(const DevIndex& ix, const Rec32& G, uint32_t pos, SgSt& s, uint32_t* bit, uint32_t* rank,
-                              const Rec32** addr_a, const Rec32** addr_b, bool* straddle) {
-    const uint32_t blk = pos / RRR_BLOCK;
-    const uint32_t k = blk & 31u, sub = k >> 3, kk = k & 7u;
-    s.use = pos - blk * RRR_BLOCK;
-    uint32_t offb = G.w[1], ones = G.w[0];
-    if (sub) {
-        offb += (G.w[2] >> (10u * (sub - 1u))) & 1023u;
-        ones += (G.w[3] >> (10u * (sub - 1u))) & 1023u;
-    }
-    const uint32_t word = rec_word(G, 4u + sub);
-#pragma unroll
-    for (uint32_t i = 0; i < 7; ++i) {
-        if (i < kk) {
-            const uint32_t c = (word >> (4u * i)) & 15u;
-            ones += c;
-            offb += rrr_bits(c);
-        }
-    }
-    const uint32_t cls = (word >> (4u * kk)) & 15u;
-    s.ones = ones;
-    s.offb = offb;
-    s.cls = cls;
-    if (cls == 0u) {
-        *bit = 0;
-        *rank = ones;
-        return SG_DONE;
-    }
-    if (cls == 15u) {
-        *bit = 1;
-        *rank = ones + s.use;
-        return SG_DONE;
-    }
-    const Rec32* base = reinterpret_cast<const Rec32*>(ix.soffsets);
-    *addr_a = base + (offb >> 8);
-    *addr_b = base + (offb >> 8) + 1;
-    *straddle = ((offb & 255u) + rrr_bits(cls)) > 256u;
-    return SG_OFFSET;
-}
 
 // binom[b*16 + k] = C(b, k) for b, k in 0..14 (0 when k > b)
 FMGPU_HD void fill_binom(uint16_t* binom) {
@@ -305,19 +208,6 @@ FMGPU_HD uint32_t rrr_unrank(const uint16_t* binom, uint32_t cls, uint32_t off, 
         }
     }
     return v;
-}
-
-FMGPU_HD void sg_on_offset(const Rec32& A, const Rec32& B, bool straddle, const uint16_t* binom, const SgSt& s, uint32_t* bit,
-                           uint32_t* rank) {
-    const uint32_t nb = rrr_bits(s.cls);
-    const uint32_t o = s.offb & 255u, wi = o >> 5, sh = o & 31u;
-    const uint32_t lo = rec_word(A, wi);
-    const uint32_t hi = wi == 7u ? (straddle ? B.w[0] : 0u) : rec_word(A, wi + 1u);
-    const unsigned long long both = ((unsigned long long)hi << 32) | lo;
-    const uint32_t off = (uint32_t)(both >> sh) & ((1u << nb) - 1u);
-    const uint32_t block = rrr_unrank(binom, s.cls, off, s.use + 1u);
-    *bit = (block >> s.use) & 1u;
-    *rank = s.ones + popc32(block & ((1u << s.use) - 1u));
 }
 
 // ------------------------------------------------------------------------------------------

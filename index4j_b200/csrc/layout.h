@@ -8,7 +8,7 @@ namespace fmgpu {
 
 constexpr uint32_t SB_LOG = 20;                   // WaveletFixedBlockBoosting.SUPER_BLOCK_SIZE = 2^20
 constexpr uint32_t SB_MASK = (1u << SB_LOG) - 1;
-constexpr uint32_t SECTOR_BITS = 224;             // payload bits of a level sector (7 words)
+constexpr uint32_t SECTOR_BITS = 96;              // positions covered by one level record (3 words per bit plane)
 constexpr uint32_t RRR_BLOCK = 15;                // RrrVector.BLOCK_SIZE
 constexpr uint32_t SGROUP_BLOCKS = 32;            // RRR blocks per sampled-row group (480 bits)
 
@@ -21,23 +21,34 @@ struct alignas(32) Rec32 {
 //   w0 value : hyper+super+block boundary rank (NORMAL/RUN) or the complete answer (CONST)
 //   w1 code  : canonical Huffman code of sym in this block, MSB = root decision
 //   w2       : codeLen (bits 0-7) | kind (bits 8-15)
-//   w3..w7   : sector index of the node visited at depth 0..4; when codeLen > 5, w3..w6 hold depth
-//              0..3 and w7 is an index into the overflow array (chunks of 8 sector indices, depth 4..)
+//   w3..w7   : first record of the even-depth node visited at depth 0, 2, 4, 6, 8 (one record resolves two levels);
+//              when codeLen > 10, w3..w6 hold depth 0..6 and w7 is an index into the overflow array (chunks of 8
+//              record indices, depth 8, 10, ..)
 enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3 };
-constexpr uint32_t CELL_INLINE_LEVELS = 5;
+constexpr uint32_t CELL_INLINE_PAIRS = 5;
 
-// --- level sector: w0 = ones in this node's bitvector before the sector, w1..w7 = 224 bits.
-// Every wavelet-tree node starts on a fresh sector, so w0 is node-relative and a rank inside a
-// node touches exactly one sector.
+// --- level record (32 bytes): TWO tree levels of 96 positions.  Only the wavelet-tree nodes at EVEN depth own records;
+// record q of a node covers its positions [96q, 96q + 96):
+//   w0 = c1  : ones in this node's bitvector before the record
+//   w1 = c01 | c11 << 16 : elements before the record whose bits at this level and the next are (0,1) / (1,1)
+//   w2..w4 = plane 0: this node's 96 bits
+//   w5..w7 = plane 1: for the SAME 96 positions the bit each element has one level further down, i.e. in the child it
+//            descends to (0 where that child is a leaf)
+// With P = 96q elements before the record, c00 = P - c1 - c01 and c10 = c1 - c11, so the rank of any 2-bit code prefix
+// (t,u) is ONE fetch and one masked-popcount pass over (plane0 ^ ~T) & (plane1 ^ ~U): a rank / inverseSelect takes one
+// record per TWO tree levels.  (v1 kept one 224-bit level per 32-byte sector: one DRAM access per level, and the popcount
+// passes over 7 words made the two-level variant of that format ALU-bound — profiles/experiments.)
+// Every node starts on a fresh record, so the counters are node-relative (nodes hold <= 65536 elements).
 
 // --- block descriptor (LF / inverseSelect entry, :1305-1537):
-//   w0 root sector, w1 info (bit0 = run block, bits 8-23 = run symbol c' as inverseSelect decodes it),
+//   w0 first level record of the root, w1 info (bit0 = run block, bits 8-23 = run symbol c' as inverseSelect decodes it),
 //   run blocks: w2 / w3 = value / kind of the (block, c') cell, i.e. rank(j, c') for j inside the block;
-//   w4..w7 = node record of the root.
-// --- node record (16 B, two per sector): c0, c1, a0, a1.  Child b: c_b bit31 set => leaf, low 16
-// bits = symbol, a_b = boundary rank of that symbol; else c_b = record index of the child node
-// and a_b = its first sector.
+//   w4 = node record of the root.
+// --- node record of an even-depth node (32 B): entries [t][u] = {c, a} at w[4t + 2u], t = bit at this depth, u = bit at
+// the next.  Child t is a leaf: entry [t][0] = {LEAF1_FLAG | symbol, boundary rank of the symbol}.  Else grandchild [t][u]:
+// leaf => {LEAF_FLAG | symbol, boundary rank}; internal => {its node record, its first level record}.
 constexpr uint32_t LEAF_FLAG = 0x80000000u;
+constexpr uint32_t LEAF1_FLAG = 0x40000000u;
 
 // --- sampled-row group (RrrVector restated for one 32-block group, bitsequence/RrrVector.java:314-396):
 //   w0 ones before the group, w1 bit position of the group's first offset in the offset stream,
@@ -74,10 +85,10 @@ struct DevIndex {
     const uint16_t* code2char;  // monotonicLookUp
     const SbDesc* sb;
     const Rec32* cells;    // [n_blocks_total][sigma]
-    const Rec32* sectors;
+    const Rec32* sectors;  // level records (two Rec32 each)
     const Rec32* ovf;      // chunks of 8 sector indices
     const Rec32* blocks;   // block descriptors
-    const Rec32* nodes;    // node records, two per Rec32
+    const Rec32* nodes;    // node records of the even-depth nodes
     const Rec32* sgroups;
     const uint32_t* soffsets;
     const uint16_t* rrr_inv;    // [32768] (class, offset) -> 15-bit block, RrrVector.java:8705-16899 regenerated

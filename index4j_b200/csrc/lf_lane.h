@@ -7,7 +7,6 @@
 //
 // Reference semantics (paths under indices/src/main/java/com/dynatrace/):
 //   sampled_access_rank  bitsequence/RrrVector.java:314-349 (access) and :358-396 (rankOnes)
-//   rank_generic         wavelet/WaveletFixedBlockBoosting.java:1010-1285 (rank)
 //   lf_step              fm/FmIndex.java:532-535 / :597-599  c = (short) inverseSelect(j-1); j = C[c] + rank(j, c)
 //                        with inverseSelect = wavelet/WaveletFixedBlockBoosting.java:1305-1537
 #pragma once
@@ -71,43 +70,11 @@ FMGPU_HD void sampled_access_rank(const DevIndex& ix, const RrrTab& R, const Rec
     *rank = ones + popc32(block & ((1u << use) - 1u));
 }
 
-// rank(pos, sym) through the cell / level / overflow records.  Returns 0, or 9 where the reference throws.
-FMGPU_HD uint32_t rank_generic(const DevIndex& ix, const SmemTables& T, uint32_t pos, uint32_t sym, uint32_t* out, LfCounters& cnt) {
-    RankSt s;
-    s.p5 = s.p6 = s.p7 = 0;
-    const Rec32* addr = nullptr;
-    uint32_t val = 0;
-    uint32_t o = rank_begin(ix, T, pos, sym, s, &addr, &val);
-    if (o == RK_THROW) return 9u;
-    if (o == RK_DONE) {
-        *out = val;
-        return 0u;
-    }
-    ++cnt.ranks;
-    {
-        const Rec32 cell = FMGPU_LD256(addr);
-        o = rank_on_cell(ix, cell, s, &addr, &val);
-    }
-    if (o == RK_THROW) return 9u;
-    while (o == RK_MORE) {
-        bool want = false;
-        ++cnt.rank_levels;
-        const Rec32 A = FMGPU_LD256(addr);
-        o = rank_on_level(ix, A, s, &addr, &val, &want);
-        if (o == RK_MORE && want) {
-            const Rec32 V = FMGPU_LD256(addr);
-            rank_on_ovf(ix, V, s, &addr);
-        }
-    }
-    *out = val;
-    return 0u;
-}
-
 // One LF step from row j (Java's 1-based j): returns the new j.  D is the block descriptor of position j-1
 // (already fetched), bmask the block-size mask of that position's superblock.
-//   * tree block: inverseSelect walks DOWN the block's tree — per level one level sector and the node record of
-//     the child — and its leaf gives the symbol AND rank(j-1, c); bwt[j-1] == c, so rank(j, c) = rank(j-1, c) + 1
-//     whenever j lies in the same block;
+//   * tree block: inverseSelect walks DOWN the block's tree, two levels per level record (plus the node record of
+//     the even-depth node, fetched alongside), and its leaf gives the symbol AND rank(j-1, c); bwt[j-1] == c, so
+//     rank(j, c) = rank(j-1, c) + 1 whenever j lies in the same block;
 //   * single-symbol block: the descriptor carries the symbol as inverseSelect decodes it (low byte only,
 //     :1329-1332) and the pre-evaluated (block, symbol) cell, so rank(j, c) = value [+ (j mod block)] needs no
 //     further record when j lies in the same block;
@@ -116,7 +83,7 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
                           uint32_t* err, LfCounters& cnt) {
     const uint32_t pos = j - 1u;
     const uint32_t jrel = j & bmask;
-    uint32_t sym, rank_j = 0;
+    uint32_t sym = 0, rank_j = 0;
     bool have = false;
     ++cnt.lf_steps;
     if (D.w[1] & 1u) {
@@ -133,35 +100,21 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
         }
     } else {
         uint32_t r = pos & bmask;
-        uint32_t c0 = D.w[4], c1 = D.w[5], a0 = D.w[6], a1 = D.w[7];
-        uint32_t sec = D.w[0];
+        uint32_t sec = D.w[0], nrec = D.w[4];
         for (;;) {
-            const Rec32 S = FMGPU_LD256(ix.sectors + (sec + r / SECTOR_BITS));
-            ++cnt.lf_levels;
-            const uint32_t b = r % SECTOR_BITS;
-            const uint32_t ones = sector_rank(S, b);
-            const uint32_t bit = sector_bit(S, b);
-            const uint32_t cb = bit ? c1 : c0;
-            const uint32_t ab = bit ? a1 : a0;
-            r = bit ? ones : r - ones;
-            if (cb & LEAF_FLAG) {
-                sym = cb & 0xffffu;
-                rank_j = ab + r + 1u;
+            const Rec32 X = FMGPU_LD256(ix.sectors + (sec + r / SECTOR_BITS));
+            const Rec32 N = FMGPU_LD256(ix.nodes + nrec);
+            uint32_t rk = 0;
+            if (dlevel_descend(X, N, r % SECTOR_BITS, &r, &nrec, &sec, &sym, &rk, &cnt.lf_levels)) {
+                rank_j = rk + 1u;
                 break;
             }
-            sec = ab;
-            const Rec32 N = FMGPU_LD256(ix.nodes + (cb >> 1));
-            const bool hi = (cb & 1u) != 0u;
-            c0 = hi ? N.w[4] : N.w[0];
-            c1 = hi ? N.w[5] : N.w[1];
-            a0 = hi ? N.w[6] : N.w[2];
-            a1 = hi ? N.w[7] : N.w[3];
         }
         have = jrel != 0u;
     }
     *sym_out = sym;
     if (!have) {
-        const uint32_t st = rank_generic(ix, T, j, sym, &rank_j, cnt);
+        const uint32_t st = rank_single(ix, T, j, sym, &rank_j, &cnt.ranks, &cnt.rank_levels);
         if (st) {
             *err = 1;
             return j;

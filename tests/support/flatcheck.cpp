@@ -1,5 +1,5 @@
 // TEST SUPPORT (not product code): replays the product's host re-layout (flatten.hpp) and the
-// per-lane logic of the kernels (lane_logic.h, walk_lane.h) on the CPU, one lane at a time, so that
+// per-lane logic of the kernels (lane_logic.h, lf_lane.h) on the CPU, one lane at a time, so that
 // tests can compare the device data layout and lane state machines with the oracle without a GPU.
 // The kernels run exactly these functions per lane; only the warp-level scheduling differs.
 #include <cstdint>
@@ -10,7 +10,6 @@
 #include "../../index4j_b200/csrc/flatten.hpp"
 #include "../../index4j_b200/csrc/jstream.hpp"
 #include "../../index4j_b200/csrc/lf_lane.h"
-#include "../../index4j_b200/csrc/walk_lane.h"
 
 using namespace fmgpu;
 
@@ -24,35 +23,17 @@ struct FC {
 };
 const Rec32 ZERO{};
 
-// rank(pos, sym) through the cell / level / overflow records; returns status (0 or 9)
+// rank(pos, sym) through the cell / level records; returns status (0 or 9)
 int host_rank(const FC& h, uint32_t pos, uint32_t sym, uint32_t* out, uint64_t* n_rank, uint64_t* n_level) {
-    RankSt s;
-    s.p5 = s.p6 = s.p7 = 0;
-    const Rec32* addr = nullptr;
-    uint32_t val = 0;
-    uint32_t o = rank_begin(h.ix, h.T, pos, sym, s, &addr, &val);
-    if (o == RK_THROW) return 9;
-    if (o == RK_DONE) {
-        *out = val;
-        return 0;
-    }
-    if (n_rank) ++*n_rank;
-    o = rank_on_cell(h.ix, *addr, s, &addr, &val);
-    if (o == RK_THROW) return 9;
-    while (o == RK_MORE) {
-        bool want = false;
-        if (n_level) ++*n_level;
-        o = rank_on_level(h.ix, *addr, s, &addr, &val, &want);
-        if (o == RK_MORE && want) rank_on_ovf(h.ix, *addr, s, &addr);
-    }
-    *out = val;
-    return 0;
+    uint32_t nr = 0, nl = 0;
+    const uint32_t st = rank_single(h.ix, h.T, pos, sym, out, &nr, &nl);
+    if (n_rank) *n_rank += nr;
+    if (n_level) *n_level += nl;
+    return (int)st;
 }
 
-bool g_v2 = false;  // replay the lockstep lanes of lf_lane.h (k_extract) instead of the phase machine of walk_lane.h (k_walk)
-
 template <int MODE>
-void run_walk_v2(const FC& h, const WalkParams& P, uint64_t* counters) {
+void run_walk(const FC& h, const WalkParams& P, uint64_t* counters) {
     LfCounters cnt{};
     for (uint32_t w = 0; w < P.n_items; ++w) {
         ExLane<MODE> lane;
@@ -65,32 +46,6 @@ void run_walk_v2(const FC& h, const WalkParams& P, uint64_t* counters) {
         counters[1] += cnt.rank_levels;
         counters[2] += cnt.lf_steps;
         counters[3] += cnt.lf_levels;
-    }
-}
-
-template <int MODE>
-void run_walk(const FC& h, const WalkParams& P, uint64_t* counters) {
-    if (g_v2 && MODE != WM_LOCATE) return run_walk_v2<MODE == WM_LOCATE ? WM_EXTRACT : MODE>(h, P, counters);
-    WalkCounters cnt{};
-    for (uint32_t w = 0; w < P.n_items; ++w) {
-        WalkLane<MODE> lane;
-        lane.init();
-        lane.w = w;
-        lane.phase = W_ITEM;
-        while (lane.phase != W_IDLE) {
-            ItemRaw raw{};
-            if (lane.phase == W_ITEM) raw = walk_load_item<MODE>(P, w);
-            const Rec32 A = lane.needs_a() ? *lane.addr_a : ZERO;
-            const Rec32 B = (lane.needs_a() && lane.need_b) ? *lane.addr_b : ZERO;
-            lane.step(h.ix, h.T, P, raw, A, B, cnt);
-        }
-    }
-    if (counters) {
-        counters[0] += cnt.ranks;
-        counters[1] += cnt.rank_levels;
-        counters[2] += cnt.lf_steps;
-        counters[3] += cnt.lf_levels;
-        counters[4] += cnt.sbits;
     }
 }
 }  // namespace
@@ -131,7 +86,6 @@ int fc_load(const uint8_t* buf, uint64_t len, int threads, void** out) {
     }
 }
 void fc_free(void* h) { delete (FC*)h; }
-void fc_set_v2(int on) { g_v2 = on != 0; }
 int32_t fc_alphabet_length(void* h) { return ((FC*)h)->F.alphabet_length; }
 void fc_sizes(void* hv, uint64_t* out8) {
     FC* h = (FC*)hv;
@@ -212,16 +166,6 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
     }
 }
 
-void fc_locate_rows(void* hv, uint32_t* rows_pos, uint32_t n, int32_t* status, uint64_t* counters) {
-    FC& h = *(FC*)hv;
-    WalkParams P{};
-    P.n_items = n;
-    P.rows_pos = rows_pos;
-    P.status_out = status;
-    P.binom = h.binom;
-    run_walk<WM_LOCATE>(h, P, counters);
-}
-
 void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena, const uint64_t* arena_off,
                 int32_t* len_out, int32_t* status, uint64_t* counters) {
     FC& h = *(FC*)hv;
@@ -233,7 +177,6 @@ void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n,
     P.arena = arena;
     P.len_out = len_out;
     P.status_out = status;
-    P.binom = h.binom;
     run_walk<WM_EXTRACT>(h, P, counters);
 }
 
@@ -253,7 +196,6 @@ void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_
     P.arena = arena;
     P.len_out = len_out;
     P.status_out = status;
-    P.binom = h.binom;
     run_walk<WM_EUB>(h, P, counters);
     if (mode != 2)
         for (uint32_t w = 0; w < n; ++w)  // what k_eub_assemble does
@@ -261,22 +203,8 @@ void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_
                 arena[(size_t)w * dst_len + q] = left[(size_t)w * dst_len + (down[w] - 1 - q)];
 }
 
-// sampled-row access/rank through the group records
-void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
-    FC& h = *(FC*)hv;
-    SgSt s;
-    uint32_t b = 0, r = 0;
-    const Rec32* oa = nullptr;
-    const Rec32* ob = nullptr;
-    bool st = false;
-    const uint32_t o = sg_on_group(h.ix, *sg_addr(h.ix, pos), pos, s, &b, &r, &oa, &ob, &st);
-    if (o == SG_OFFSET) sg_on_offset(*oa, st ? *ob : ZERO, st, h.binom, s, &b, &r);
-    *bit = (int32_t)b;
-    *rank = (int32_t)r;
-}
-
-// locate v2 (k_locate): the straight-line lane code of lf_lane.h, one hit at a time
-void fc_locate_rows_v2(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* counters) {
+// locate (k_locate): the straight-line lane code of lf_lane.h, one hit at a time
+void fc_locate_rows(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* counters) {
     FC& h = *(FC*)hv;
     const fmgpu_host::RrrTables& RT = fmgpu_host::rrr_tables();
     RrrTab R;
@@ -315,7 +243,7 @@ void fc_locate_rows_v2(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* count
         counters[4] += cnt.sbits;
     }
 }
-void fc_sampled_v2(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
+void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
     FC& h = *(FC*)hv;
     const fmgpu_host::RrrTables& RT = fmgpu_host::rrr_tables();
     RrrTab R;

@@ -35,12 +35,10 @@ def lib():
         L.fc_sizes.argtypes = [vp, vp]
         L.fc_rank.argtypes = [vp, u32, u32, C.POINTER(C.c_int64)]
         L.fc_count_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
-        L.fc_locate_rows.argtypes = [vp, vp, u32, vp, vp]
+        L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
         L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp]
         L.fc_sampled.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
-        L.fc_sampled_v2.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
-        L.fc_locate_rows_v2.argtypes = [vp, vp, u32, vp]
         L.fc_unrank_table.argtypes = [vp]
         _lib = L
     return _lib
@@ -59,11 +57,6 @@ class FlatIndexHost:
         if getattr(self, "_h", None):
             lib().fc_free(self._h)
             self._h = None
-
-    @staticmethod
-    def set_v2(on: bool):
-        """extract / extractUntilBoundary replay: lockstep lanes of lf_lane.h (True) or the phase machine of walk_lane.h"""
-        lib().fc_set_v2(int(on))
 
     def sizes(self):
         out = np.zeros(8, dtype=np.uint64)
@@ -88,19 +81,8 @@ class FlatIndexHost:
 
     def locate_rows(self, rows):
         rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()
-        st = np.zeros(rp.size, dtype=np.int32)
-        lib().fc_locate_rows(self._h, rp.ctypes.data, rp.size, st.ctypes.data, self.counters.ctypes.data)
-        return rp.astype(np.int64), st
-
-    def locate_rows_v2(self, rows):
-        rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()
-        lib().fc_locate_rows_v2(self._h, rp.ctypes.data, rp.size, self.counters.ctypes.data)
+        lib().fc_locate_rows(self._h, rp.ctypes.data, rp.size, self.counters.ctypes.data)
         return rp.astype(np.int64)
-
-    def sampled_v2(self, pos):
-        b, r = C.c_int32(), C.c_int32()
-        lib().fc_sampled_v2(self._h, pos, C.byref(b), C.byref(r))
-        return b.value, r.value
 
     def extract(self, start, stop, arena_off):
         start = np.ascontiguousarray(start, dtype=np.int32)

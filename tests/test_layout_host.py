@@ -1,5 +1,5 @@
 """CPU tests of the product's host re-layout (flatten.hpp) and per-lane logic (lane_logic.h,
-walk_lane.h): tests/support/libflatcheck.so replays exactly the functions every GPU lane runs, one
+lf_lane.h): tests/support/libflatcheck.so replays exactly the functions every GPU lane runs, one
 lane at a time with plain memory reads, and the results must be bit-exact with the oracle.
 """
 import numpy as np
@@ -55,7 +55,6 @@ def test_sampled_rows_match_oracle(flats, name):
     for p in np.concatenate([rng.integers(0, L, 20000), [0, L - 1]]):
         b, r = f.sampled(int(p))
         assert b == case.oracle.sampled_access(int(p)) and r == case.oracle.sampled_rank(int(p)), int(p)
-        assert (b, r) == f.sampled_v2(int(p)), int(p)  # table decode of k_locate (lf_lane.h)
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
@@ -70,21 +69,12 @@ def test_count_and_locate_lanes(flats, name):
     for i in range(n_hits.size):
         rows += list(range(int(ranges[i, 0]), int(ranges[i, 0]) + int(n_hits[i])))
         exp += list(pos[i, : n_hits[i]])
-    got_pos, _ = f.locate_rows(np.array(rows, dtype=np.uint32))
+    got_pos = f.locate_rows(np.array(rows, dtype=np.uint32))  # lane code of k_locate (lf_lane.h)
     assert np.array_equal(got_pos, np.array(exp, dtype=np.int64))
-    got_v2 = f.locate_rows_v2(np.array(rows, dtype=np.uint32))  # lane code of k_locate (lf_lane.h)
-    assert np.array_equal(got_v2, np.array(exp, dtype=np.int64))
-
-
-@pytest.fixture(params=["phase_machine", "lockstep"])
-def lane_impl(request):
-    flatcheck.FlatIndexHost.set_v2(request.param == "lockstep")
-    yield request.param
-    flatcheck.FlatIndexHost.set_v2(False)
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
-def test_extract_lanes(flats, name, lane_impl):
+def test_extract_lanes(flats, name):
     case, f = get_case(name), flats(name)
     rng = np.random.default_rng(4)
     n = case.text.size
@@ -104,7 +94,7 @@ def test_extract_lanes(flats, name, lane_impl):
 
 @pytest.mark.parametrize("name", CASE_NAMES)
 @pytest.mark.parametrize("mode", [0, 1, 2])
-def test_extract_until_boundary_lanes(flats, name, mode, lane_impl):
+def test_extract_until_boundary_lanes(flats, name, mode):
     case, f = get_case(name), flats(name)
     n = case.text.size
     rng = np.random.default_rng(5 + mode)
