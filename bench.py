@@ -372,8 +372,8 @@ def main():
         e2e_value = world * n_pat * args.steps / (e2e_ms / 1e3)
         peak, peak_src = hbm_peak()
         # algorithmic bytes of one k_count launch: every rank query reads one 32-byte cell and one 32-byte level
-        # sector per wavelet level; plus the pattern codes and descriptors it streams.
-        alg_bytes = 32.0 * (stats["ranks"] + stats["rank_levels"]) + 2.0 * chars.size + 16.0 * n_pat + 8.0 * n_pat
+        # record per TWO wavelet levels; plus the pattern chars and descriptors it streams.
+        alg_bytes = 32.0 * (stats["ranks"] + stats["level_records"]) + 2.0 * chars.size + 16.0 * n_pat + 8.0 * n_pat
         achieved = alg_bytes / (kern_ms / 1e3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -385,7 +385,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,
                          "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
-                         "sectors_per_rank": (stats["ranks"] + stats["rank_levels"]) / max(1, stats["ranks"]),
+                         "level_records_per_launch": stats["level_records"],
+                         "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3)},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob)},
         }

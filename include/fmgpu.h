@@ -121,9 +121,10 @@ int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d
 /* Work counters of the most recent batch call on this index (device-side counted, read back here):
  * [0] rank queries that touched memory  [1] wavelet levels walked by rank queries
  * [2] LF steps (inverseSelect walks)     [3] wavelet levels walked by LF steps
-  * [4] sampled-row bit tests              [5] kernels launched by the call
+ * [4] sampled-row bit tests              [5] kernels launched by the call
  * [6] 32-byte records actually loaded by the backward-search kernel (two positions of one pattern
- *     that fall into the same sector share one load)      [7] reserved
+ *     that fall into the same level record share one load)
+ * [7] level records a query needs (one per TWO wavelet levels): by rank queries and by LF steps
  * Used by bench.py for the roofline's algorithmic-bytes figure. */
 int fmgpu_last_stats(fmgpu_index* idx, uint64_t out8[8]);
 

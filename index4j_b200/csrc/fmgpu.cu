@@ -431,10 +431,11 @@ int fmgpu_last_stats(fmgpu_index* ix, uint64_t out8[8]) {
         if (!p) continue;
         uint32_t words[CTRL_WORDS];
         CU(cudaMemcpy(words, p, sizeof words, cudaMemcpyDeviceToHost));
-        uint64_t v[7];
-        memcpy(v, words + CTRL_STATS, 7 * sizeof(uint64_t));
+        uint64_t v[8];
+        memcpy(v, words + CTRL_STATS, 8 * sizeof(uint64_t));
         for (int i = 0; i < 5; ++i) out8[i] += v[i];
         out8[6] += v[6];
+        out8[7] += v[7];
     }
     out8[5] = ix->last_launches;
     return 0;

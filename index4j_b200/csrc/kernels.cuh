@@ -31,7 +31,10 @@
 namespace fmgpu {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int CTA_THREADS = 256;
+#ifndef COUNT_THREADS
+#define COUNT_THREADS 512
+#endif
+constexpr int CTA_THREADS = COUNT_THREADS;
 constexpr uint32_t SMEM_C_MAX = 4096;   // entries of C kept in shared memory
 constexpr uint32_t SMEM_SB_MAX = 2048;  // superblock descriptors kept in shared memory
 
@@ -172,7 +175,7 @@ __device__ __forceinline__ void dlevel_pair(const DevIndex& ix, uint32_t node, u
 
 // rank(., c) of two positions of ONE block: ra/rb are block-relative positions (rb == ra for a single query)
 __device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, uint32_t c, uint32_t ra, uint32_t rb, bool on,
-                                             uint32_t queries, uint32_t& n_level, uint32_t& n_load) {
+                                             uint32_t queries, uint32_t& n_level, uint32_t& n_load, uint32_t& n_rec) {
     WalkOut o;
     o.a = o.b = o.err = 0;
     if (!on) return o;
@@ -192,22 +195,28 @@ __device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, u
     const uint32_t pairs = (L + 1u) >> 1;
     const uint32_t inl = pairs > CELL_INLINE_PAIRS ? CELL_INLINE_PAIRS - 1u : pairs;
     const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);  // codes longer than 10 bits: rest of the path
+#pragma unroll
+    for (uint32_t k = 0; k < CELL_INLINE_PAIRS; ++k)
+        if (k < inl) {
+            const uint32_t d = 2u * k;
+            const bool two = d + 1u < L;
+            dlevel_pair(ix, cell.w[3 + k], (code >> (L - 1u - d)) & 1u, two ? (code >> (L - 2u - d)) & 1u : 0u, two, ra, rb, n_load);
+        }
 #pragma unroll 1
-    for (uint32_t k = 0; k < pairs; ++k) {
-        const uint32_t node = k < inl ? rec_word(cell, 3u + k) : __ldg(more + (k - inl));
+    for (uint32_t k = inl; k < pairs; ++k) {
         const uint32_t d = 2u * k;
         const bool two = d + 1u < L;
-        const uint32_t t = (code >> (L - 1u - d)) & 1u;
-        dlevel_pair(ix, node, t, two ? (code >> (L - 2u - d)) & 1u : 0u, two, ra, rb, n_load);
+        dlevel_pair(ix, __ldg(more + (k - inl)), (code >> (L - 1u - d)) & 1u, two ? (code >> (L - 2u - d)) & 1u : 0u, two, ra, rb, n_load);
     }
     n_level += L * queries;
+    n_rec += pairs * queries;
     o.a = base + ra;
     o.b = base + rb;
     return o;
 }
 
 #ifndef COUNT_MIN_CTAS
-#define COUNT_MIN_CTAS 4
+#define COUNT_MIN_CTAS 2
 #endif
 __global__ void __launch_bounds__(CTA_THREADS, COUNT_MIN_CTAS)
 k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,
@@ -216,7 +225,7 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
     extern __shared__ uint32_t smem[];
     const SmemTables T = stage_tables(ix, smem);
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t n_rank = 0, n_level = 0, n_load = 0;
+    uint32_t n_rank = 0, n_level = 0, n_load = 0, n_rec = 0;
 
     for (;;) {
         unsigned batch = 0;
@@ -283,12 +292,12 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
             const bool second = go && sp != 0u && blk_s != blk_e;
             n_rank += go ? (sp != 0u ? 2u : 1u) : 0u;
 
-            const WalkOut w1 = walk_pair(ix, blk_e, c, with_s ? rs : re, re, go, with_s ? 2u : 1u, n_level, n_load);
+            const WalkOut w1 = walk_pair(ix, blk_e, c, with_s ? rs : re, re, go, with_s ? 2u : 1u, n_level, n_load, n_rec);
             uint32_t val_s = with_s ? w1.a : 0u;
             const uint32_t val_e = w1.b;
             uint32_t e2 = 0;
             if (__any_sync(FULL, second)) {
-                const WalkOut w2 = walk_pair(ix, blk_s, c, rs, rs, second, 1u, n_level, n_load);
+                const WalkOut w2 = walk_pair(ix, blk_s, c, rs, rs, second, 1u, n_level, n_load, n_rec);
                 if (second) val_s = w2.a;
                 e2 = w2.err;
             }
@@ -317,11 +326,13 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
         n_rank += __shfl_xor_sync(FULL, n_rank, o);
         n_level += __shfl_xor_sync(FULL, n_level, o);
         n_load += __shfl_xor_sync(FULL, n_load, o);
+        n_rec += __shfl_xor_sync(FULL, n_rec, o);
     }
     if (lane == 0 && stats) {
         atomicAdd(stats + 0, (unsigned long long)n_rank);
         atomicAdd(stats + 1, (unsigned long long)n_level);
         atomicAdd(stats + 6, (unsigned long long)n_load);
+        atomicAdd(stats + 7, (unsigned long long)n_rec);
     }
 }
 

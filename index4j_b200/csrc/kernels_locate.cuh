@@ -48,7 +48,7 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
     const unsigned lt_mask = (1u << lane) - 1u;
 
     LfCounters cnt;
-    cnt.lf_steps = cnt.lf_levels = cnt.ranks = cnt.rank_levels = cnt.sbits = 0;
+    cnt.lf_steps = cnt.lf_levels = cnt.ranks = cnt.rank_levels = cnt.sbits = cnt.recs = 0;
 
     uint32_t j = 0, dist = 0, w = 0;
     bool active = false;
@@ -119,6 +119,7 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
         cnt.rank_levels += __shfl_xor_sync(FULL, cnt.rank_levels, o);
         cnt.lf_steps += __shfl_xor_sync(FULL, cnt.lf_steps, o);
         cnt.lf_levels += __shfl_xor_sync(FULL, cnt.lf_levels, o);
+        cnt.recs += __shfl_xor_sync(FULL, cnt.recs, o);
         cnt.sbits += __shfl_xor_sync(FULL, cnt.sbits, o);
     }
     if (lane == 0 && stats) {
@@ -126,6 +127,7 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
         atomicAdd(stats + 1, (unsigned long long)cnt.rank_levels);
         atomicAdd(stats + 2, (unsigned long long)cnt.lf_steps);
         atomicAdd(stats + 3, (unsigned long long)cnt.lf_levels);
+        atomicAdd(stats + 7, (unsigned long long)cnt.recs);
         atomicAdd(stats + 4, (unsigned long long)cnt.sbits);
     }
 }
@@ -146,7 +148,7 @@ k_extract(const DevIndex ix, WalkParams P, uint32_t chunk, unsigned int* queue, 
     const unsigned lt_mask = (1u << lane_id) - 1u;
 
     LfCounters cnt;
-    cnt.lf_steps = cnt.lf_levels = cnt.ranks = cnt.rank_levels = cnt.sbits = 0;
+    cnt.lf_steps = cnt.lf_levels = cnt.ranks = cnt.rank_levels = cnt.sbits = cnt.recs = 0;
     ExLane<MODE> lane;
     lane.init();
     uint32_t next = 0, end = 0;
@@ -188,12 +190,14 @@ k_extract(const DevIndex ix, WalkParams P, uint32_t chunk, unsigned int* queue, 
         cnt.rank_levels += __shfl_xor_sync(FULL, cnt.rank_levels, o);
         cnt.lf_steps += __shfl_xor_sync(FULL, cnt.lf_steps, o);
         cnt.lf_levels += __shfl_xor_sync(FULL, cnt.lf_levels, o);
+        cnt.recs += __shfl_xor_sync(FULL, cnt.recs, o);
     }
     if (lane_id == 0 && stats) {
         atomicAdd(stats + 0, (unsigned long long)cnt.ranks);
         atomicAdd(stats + 1, (unsigned long long)cnt.rank_levels);
         atomicAdd(stats + 2, (unsigned long long)cnt.lf_steps);
         atomicAdd(stats + 3, (unsigned long long)cnt.lf_levels);
+        atomicAdd(stats + 7, (unsigned long long)cnt.recs);
     }
 }
 

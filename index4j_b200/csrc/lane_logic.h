@@ -127,10 +127,10 @@ FMGPU_HD bool dlevel_descend(const Rec32& x, const Rec32& N, uint32_t b, uint32_
 
 // ------------------------------------------------------------------------------------------
 // rank(pos, sym), one query (wavelet/WaveletFixedBlockBoosting.java:1010-1285).  Returns 0, or 9 where the reference
-// throws (position == size on a superblock boundary, :1022-1026).  *n_rank / *n_level count cells fetched / levels walked.
+// throws (position == size on a superblock boundary, :1022-1026).  *n_rank / *n_level / *n_rec count cells fetched / tree levels walked / level records fetched.
 // ------------------------------------------------------------------------------------------
 FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t pos, uint32_t sym, uint32_t* out, uint32_t* n_rank,
-                              uint32_t* n_level) {
+                              uint32_t* n_level, uint32_t* n_rec) {
     *out = 0;
     if (pos == 0) return 0u;            // :1012
     if (pos > ix.length) pos = ix.length;  // :1015
@@ -171,6 +171,7 @@ FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t 
         r = dlevel_rank(x, r, r % SECTOR_BITS, t, u, two);
     }
     *n_level += L;
+    *n_rec += pairs;
     *out = cell.w[0] + r;
     return 0u;
 }

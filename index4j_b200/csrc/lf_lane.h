@@ -26,7 +26,7 @@ struct RrrTab {
 };
 
 struct LfCounters {
-    uint32_t lf_steps, lf_levels, ranks, rank_levels, sbits;
+    uint32_t lf_steps, lf_levels, ranks, rank_levels, sbits, recs;  // recs: level records fetched (descents + generic ranks)
 };
 
 // access(pos) and rankOnes(pos) of the sampled-row vector from its group record G (already fetched)
@@ -105,6 +105,7 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
             const Rec32 X = FMGPU_LD256(ix.sectors + (sec + r / SECTOR_BITS));
             const Rec32 N = FMGPU_LD256(ix.nodes + nrec);
             uint32_t rk = 0;
+            ++cnt.recs;
             if (dlevel_descend(X, N, r % SECTOR_BITS, &r, &nrec, &sec, &sym, &rk, &cnt.lf_levels)) {
                 rank_j = rk + 1u;
                 break;
@@ -114,7 +115,7 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
     }
     *sym_out = sym;
     if (!have) {
-        const uint32_t st = rank_single(ix, T, j, sym, &rank_j, &cnt.ranks, &cnt.rank_levels);
+        const uint32_t st = rank_single(ix, T, j, sym, &rank_j, &cnt.ranks, &cnt.rank_levels, &cnt.recs);
         if (st) {
             *err = 1;
             return j;

@@ -182,7 +182,7 @@ class FmIndex:
     def last_stats(self) -> dict:
         out = np.zeros(8, dtype=np.uint64)
         self._check(self._lib.fmgpu_last_stats(self._h, out.ctypes.data))
-        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "reserved"]
+        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "level_records"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def set_timing(self, enable: bool = True):

@@ -33,9 +33,9 @@ def locate_workload(ix, d_chars, d_off, max_hits: int, steps: int, warmup: int):
     d_pos = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     ms = _timed(lambda: ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, d_pos, d_status), steps, warmup)
     st = ix.last_stats()
-    # algorithmic 32-byte records: per sampled-row test 1 group record; per LF step 1 block descriptor; per wavelet level 1
-    # level sector (+1 node record below the root); per generic rank 1 cell + its levels; per hit 1 SA record
-    recs = st["sampled_tests"] + st["lf_steps"] + 2 * st["lf_levels"] - st["lf_steps"] + st["ranks"] + st["rank_levels"] + total
+    # algorithmic 32-byte records: per sampled-row test 1 group record; per LF step 1 block descriptor; per TWO wavelet levels
+    # 1 level record + 1 node record; per generic rank 1 cell; per hit 1 SA record
+    recs = st["sampled_tests"] + st["lf_steps"] + 2 * st["level_records"] + st["ranks"] + total
     out = {"patterns": n_pat, "max_hits": max_hits, "hits": int(total), "ms_per_step": ms, "hits_per_s": total / (ms / 1e3),
            "lf_steps": st["lf_steps"], "lf_steps_per_s": st["lf_steps"] / (ms / 1e3), "lf_levels": st["lf_levels"],
            "sampled_tests": st["sampled_tests"], "generic_ranks": st["ranks"], "launches": st["launches"],

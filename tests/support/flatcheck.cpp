@@ -25,8 +25,8 @@ const Rec32 ZERO{};
 
 // rank(pos, sym) through the cell / level records; returns status (0 or 9)
 int host_rank(const FC& h, uint32_t pos, uint32_t sym, uint32_t* out, uint64_t* n_rank, uint64_t* n_level) {
-    uint32_t nr = 0, nl = 0;
-    const uint32_t st = rank_single(h.ix, h.T, pos, sym, out, &nr, &nl);
+    uint32_t nr = 0, nl = 0, nrec = 0;
+    const uint32_t st = rank_single(h.ix, h.T, pos, sym, out, &nr, &nl, &nrec);
     if (n_rank) *n_rank += nr;
     if (n_level) *n_level += nl;
     return (int)st;
