@@ -20,7 +20,7 @@
 namespace fmgpu {
 
 #ifndef LOCATE_THREADS
-#define LOCATE_THREADS 512
+#define LOCATE_THREADS 640
 #endif
 #ifndef LOCATE_MIN_CTAS
 #define LOCATE_MIN_CTAS 2
