@@ -386,6 +386,8 @@ def main():
                          "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,
                          "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
                          "level_records_per_launch": stats["level_records"],
+                         "records_loaded_per_launch": stats["search_records_loaded"],
+                         "spec_root_loads_wasted_per_launch": stats.get("spec_root_wasted", 0),
                          "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3)},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob)},

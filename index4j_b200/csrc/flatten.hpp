@@ -91,6 +91,7 @@ struct FlatIndex {
     std::vector<uint32_t> C;
     std::vector<uint16_t> char2code, code2char;
     std::vector<fmgpu::SbDesc> sb;
+    std::vector<fmgpu::U32x2> sbroot, blkmap;  // root-record directory (layout.h)
     std::vector<Rec32> cells, sectors, ovf, blocks, nodes, sgroups, sa, isa;
     std::vector<uint32_t> soffsets;
     int32_t alphabet_length = 0;
@@ -116,7 +117,7 @@ struct BlockTree {
     std::vector<uint16_t> sym;    // header symbol per leaf
     std::vector<uint32_t> brank;  // rankAtBlockBoundary per leaf
     int h = 0;
-    uint32_t n_sectors = 0, n_ovf_chunks = 0, n_even = 0;  // Rec32 units / chunks / even-depth internal nodes
+    uint32_t n_sectors = 0, n_ovf_chunks = 0, n_even = 0;  // Rec32 units (root excluded) / chunks / even-depth internal nodes
 };
 
 struct VarReader {
@@ -240,19 +241,26 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
         const int pairs = (len + 1) / 2;
         if (pairs > (int)fmgpu::CELL_INLINE_PAIRS) T.n_ovf_chunks += (uint32_t)((pairs - ((int)fmgpu::CELL_INLINE_PAIRS - 1) + 7) / 8);
     }
-    for (auto& n : T.nodes)
+    // records of the even-depth nodes; the root's records live in the superblock's root area (fixed stride per block)
+    for (size_t id = 0; id < T.nodes.size(); ++id) {
+        const auto& n = T.nodes[id];
         if ((n.depth & 1u) == 0) {
             if (n.size > 65536u) throw FormatError("wavelet node larger than a block");
-            T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
+            if (id != 0) T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
             ++T.n_even;
         }
+    }
 }
 
 struct SbPlan {
     uint32_t first_block = 0, rows = 0;
     uint64_t sector_base = 0, node_base = 0, ovf_base = 0;
-    uint64_t n_sectors = 0, n_nodes = 0, n_ovf = 0;
+    uint64_t n_sectors = 0, n_nodes = 0, n_ovf = 0;  // n_sectors includes the root area (n_tree_blocks * root_stride)
+    uint32_t n_tree_blocks = 0, root_stride = 0;
+    std::vector<uint8_t> has_tree;  // per block
 };
+
+inline uint32_t root_stride_of(int block_size_log) { return (1u << block_size_log) / fmgpu::SECTOR_BITS + 1u; }
 
 inline uint32_t sb_block_size(const WfbbStream& W, size_t sb, size_t b) {
     const int64_t bs = 1LL << W.sbs[sb].block_size_log;
@@ -306,7 +314,9 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
 
     // --- per block: tree, sectors, node records, descriptors
     std::vector<BlockTree> trees(nblk);
-    uint64_t sec = P.sector_base, node = P.node_base, ovf = P.ovf_base;
+    // root records first (fixed stride per tree block, block order), the other even-depth nodes after them
+    uint64_t root_sec = P.sector_base, sec = P.sector_base + (uint64_t)P.n_tree_blocks * P.root_stride;
+    uint64_t node = P.node_base, ovf = P.ovf_base;
     std::vector<uint64_t> block_node_base(nblk, 0), block_ovf_base(nblk, 0);
     for (size_t b = 0; b < nblk; ++b) {
         BlockTree& T = trees[b];
@@ -322,11 +332,18 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         // record arrays and node-record indices of the even-depth nodes
         {
             uint64_t e = node;
-            for (auto& n : T.nodes) {
+            for (size_t id = 0; id < T.nodes.size(); ++id) {
+                auto& n = T.nodes[id];
                 if (n.depth & 1u) continue;
-                n.sector = (uint32_t)sec;
                 n.enode = (uint32_t)e++;
-                sec += n.size / fmgpu::SECTOR_BITS + 1;
+                if (id == 0) {
+                    if (n.size / fmgpu::SECTOR_BITS + 1 > P.root_stride) throw FormatError("root node larger than its block");
+                    n.sector = (uint32_t)root_sec;
+                    root_sec += P.root_stride;
+                } else {
+                    n.sector = (uint32_t)sec;
+                    sec += n.size / fmgpu::SECTOR_BITS + 1;
+                }
             }
         }
         auto leaf_entry = [&](int32_t c, uint32_t flag, uint32_t* e) {
@@ -610,13 +627,20 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
         SbPlan& P = plan[sb];
         P.rows = (uint32_t)expect;
         if (sb + 1 == nsb && (sb_size % bs) == 0 && sb_size != (1LL << 20)) P.rows += 1;  // row for position == size
+        P.root_stride = root_stride_of(S.block_size_log);
+        P.has_tree.assign(P.rows, 0);
         BlockTree T;
         for (size_t b = 0; b < S.blocks.size(); ++b) {
             build_block_tree(S, b, sb_block_size(W, sb, b), T);
+            if (T.h != 0) {
+                P.has_tree[b] = 1;
+                ++P.n_tree_blocks;
+            }
             P.n_sectors += T.n_sectors;
             P.n_nodes += T.n_even;
             P.n_ovf += T.n_ovf_chunks;
         }
+        P.n_sectors += (uint64_t)P.n_tree_blocks * P.root_stride;
     });
     uint64_t blocks_total = 0, sectors_total = 0, nodes_total = 0, ovf_total = 0;
     F.sb.assign(nsb + 1, fmgpu::SbDesc{0, 16});  // +1: a lane may form the (unused) descriptor address of position == length
@@ -633,6 +657,32 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
         F.sb[sb].first_block = P.first_block;
         F.sb[sb].block_log = (uint32_t)W.sbs[sb].block_size_log;
     }
+    // root-record directory: blkmap[w] = {tree-block bits of blocks 32w.., tree blocks before block 32w},
+    // sbroot[sb] = {root area base - G(first block) * stride, stride}
+    F.blkmap.assign((size_t)(blocks_total / 32 + 2), fmgpu::U32x2{0, 0});
+    F.sbroot.assign(nsb + 1, fmgpu::U32x2{0, 1});
+    {
+        uint64_t g = 0;
+        std::vector<uint32_t> gfirst(nsb, 0);
+        for (size_t sb = 0; sb < nsb; ++sb) {
+            const SbPlan& P = plan[sb];
+            gfirst[sb] = (uint32_t)g;
+            for (uint32_t b = 0; b < P.rows; ++b)
+                if (P.has_tree[b]) {
+                    const uint64_t blk = (uint64_t)P.first_block + b;
+                    F.blkmap[(size_t)(blk >> 5)].x |= 1u << (blk & 31u);
+                    ++g;
+                }
+            F.sbroot[sb].y = P.root_stride;
+            F.sbroot[sb].x = (uint32_t)P.sector_base - gfirst[sb] * P.root_stride;  // wraps; undone by + G(block) * stride
+        }
+        uint32_t acc = 0;
+        for (auto& m : F.blkmap) {
+            m.y = acc;
+            acc += (uint32_t)__builtin_popcount(m.x);
+        }
+    }
+    M.n_blkmap = (uint32_t)F.blkmap.size();
     if (sectors_total >= 0xffffffffULL || nodes_total >= 0x7fffffffULL || ovf_total >= 0xffffffffULL || blocks_total >= 0xffffffffULL)
         throw FormatError("index too large for 32-bit record indices");
     const uint64_t cell_bytes = blocks_total * (uint64_t)W.sigma * 32;

@@ -73,7 +73,7 @@ struct Scratch {
     }
 };
 
-enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x 6 at word 2.. */, CTRL_WORDS = 32 };
+enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x 9 at word 2.. */, CTRL_WORDS = 32 };
 
 }  // namespace
 
@@ -241,6 +241,8 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
     up(upload(ix, F.char2code, &ix->dev.char2code, nullptr));
     up(upload(ix, F.code2char, &ix->dev.code2char, nullptr));
     up(upload(ix, F.sb, &ix->dev.sb, nullptr));
+    up(upload(ix, F.sbroot, &ix->dev.sbroot, nullptr));
+    up(upload(ix, F.blkmap, &ix->dev.blkmap, nullptr));
     up(upload(ix, F.cells, &ix->dev.cells, &ix->layout_bytes[0]));
     up(upload(ix, F.sectors, &ix->dev.sectors, &ix->layout_bytes[1]));
     up(upload(ix, F.nodes, &ix->dev.nodes, &ix->layout_bytes[2]));
@@ -262,8 +264,11 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
         else ix->sm_count = prop.multiProcessorCount;
     }
     if (!rc) {
-        ix->tables_smem = tables_smem_bytes(ix->dev);
-        rc = grid_for((const void*)k_count, ix->sm_count, ix->tables_smem, &ix->count_ctas);
+        ix->tables_smem = count_smem_bytes(ix->dev);
+        // the attribute is per function, not per index: always the largest table set any index can stage
+        if (cudaFuncSetAttribute((const void*)k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess)
+            rc = fail(FMGPU_ERR_CUDA, "k_count: cannot reserve %zu bytes of shared memory", ix->tables_smem);
+        if (!rc) rc = grid_for((const void*)k_count, ix->sm_count, ix->tables_smem, &ix->count_ctas);
     }
     if (!rc) rc = lf_setup(ix);
     if (!rc && (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -419,10 +424,18 @@ int fmgpu_search_kernel_ms(fmgpu_index* ix, uint32_t calls_back, float* ms_out) 
 }
 
 int fmgpu_last_stats(fmgpu_index* ix, uint64_t out8[8]) {
-    if (!ix || !out8) return fail(FMGPU_ERR_ARG, "null argument");
+    uint64_t v[FMGPU_N_STATS];
+    if (!out8) return fail(FMGPU_ERR_ARG, "null argument");
+    const int rc = fmgpu_last_stats_ex(ix, v, FMGPU_N_STATS);
+    if (!rc) memcpy(out8, v, 8 * sizeof(uint64_t));
+    return rc;
+}
+
+int fmgpu_last_stats_ex(fmgpu_index* ix, uint64_t* out8, uint32_t n_out) {
+    if (!ix || !out8 || n_out < FMGPU_N_STATS) return fail(FMGPU_ERR_ARG, "null argument or fewer than FMGPU_N_STATS slots");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
-    memset(out8, 0, 8 * sizeof(uint64_t));
+    memset(out8, 0, FMGPU_N_STATS * sizeof(uint64_t));
     if (!ix->stats_valid || !ix->ctrl.p) return 0;
     CU(cudaDeviceSynchronize());
     for (int c = 0; c < fmgpu_index::COUNT_CTX; ++c) {
@@ -431,11 +444,10 @@ int fmgpu_last_stats(fmgpu_index* ix, uint64_t out8[8]) {
         if (!p) continue;
         uint32_t words[CTRL_WORDS];
         CU(cudaMemcpy(words, p, sizeof words, cudaMemcpyDeviceToHost));
-        uint64_t v[8];
-        memcpy(v, words + CTRL_STATS, 8 * sizeof(uint64_t));
-        for (int i = 0; i < 5; ++i) out8[i] += v[i];
-        out8[6] += v[6];
-        out8[7] += v[7];
+        uint64_t v[FMGPU_N_STATS];
+        memcpy(v, words + CTRL_STATS, FMGPU_N_STATS * sizeof(uint64_t));
+        for (int i = 0; i < FMGPU_N_STATS; ++i)
+            if (i != 5) out8[i] += v[i];
     }
     out8[5] = ix->last_launches;
     return 0;

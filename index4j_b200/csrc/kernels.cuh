@@ -1,32 +1,19 @@
 // sm_100a kernels of the FM-index query path (hand-written; no library calls on the hot path).
 //
 // Execution model.  Every memory access of the query path is ONE 32-byte record =
-// one DRAM sector, fetched with a single 256-bit load (LDG.E.256).  A lane runs a small state
-// machine: each trip of the warp loop every lane issues at most one such load for whatever state
-// it is in (pattern descriptor, (block,symbol) cell, wavelet level sector, path overflow chunk),
-// then all lanes post-process their record with a few ALU ops.  Loads of all 32 lanes are in
-// flight together regardless of how their states diverge, which is what a dependent-gather
-// workload needs: memory-level parallelism, not lock-step control flow.
-//
-// Backward search (FmIndex.count, fm/FmIndex.java:455-474): a PAIR of adjacent lanes owns one
-// pattern — the even lane carries `start`, the odd lane `end`; their two rank queries per step run
-// concurrently and meet through warp shuffles.  Finished pairs are refilled from a global queue
-// with one __ballot_sync + one atomicAdd per warp.
+// one DRAM sector, fetched with a single 256-bit load (LDG.E.256); a record carries everything the
+// operation needs from that address.  Backward search (FmIndex.count, fm/FmIndex.java:455-474) runs
+// warp-lockstep: the batch is ordered by pattern length (k_prepass / k_len_scan / k_len_scatter), a
+// warp takes 32 patterns of equal length, lane = pattern, and every lane executes count_step
+// (count_lane.h) once per pattern char.  Work is taken from a global queue, one atomic per warp batch.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "count_lane.h"
 #include "lane_logic.h"
 #include "layout.h"
 #include "ldrec.h"
-
-// experiment knobs (tools/variants.sh): L2 eviction priority of the backward-search loads (ld256 / ld256_keep / ld256_stream)
-#ifndef COUNT_LD_CELL
-#define COUNT_LD_CELL ld256
-#endif
-#ifndef COUNT_LD_SECTOR
-#define COUNT_LD_SECTOR ld256
-#endif
 
 namespace fmgpu {
 
@@ -146,73 +133,45 @@ __global__ void __launch_bounds__(256) k_len_scatter(const PatDesc* __restrict__
 // ---------------------------------------------------------------------------------------------
 // Backward search (FmIndex.count, fm/FmIndex.java:455-474) — warp-lockstep.
 //
-// A warp takes 32 patterns of equal length from the length-ordered batch; lane = pattern.  All
-// lanes perform step k of their pattern together: one (block, symbol) cell fetch, then the level
-// loop.  The two rank queries of a step, rank(start, c) and rank(end, c), walk the SAME tree path
-// when start and end lie in the same block, so a lane carries both positions down one walk (one
-// sector fetch per level when they share a 224-bit sector, two otherwise); when the blocks differ
-// the lane runs a second walk.  The code is plain SIMT loops — the hardware reconverges the warp
-// after each level loop — which costs ~5x fewer issued instructions per rank than the lane state
-// machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...: issue-bound at 43-47 %
-// lane utilisation); the price is that a step lasts as long as its deepest walk.
+// A warp takes 32 patterns of equal length from the length-ordered batch; lane = pattern.  All lanes perform step k of
+// their pattern together; what a lane does in a step is count_step (count_lane.h): the two rank queries rank(start, c) and
+// rank(end, c) as two tracks of one fused walk, cells and speculative root records issued together.  The code is plain
+// SIMT loops — the hardware reconverges the warp after each level — which costs ~5x fewer issued instructions per rank
+// than the lane state machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...); the price is that a step
+// lasts as long as its deepest walk.
 // ---------------------------------------------------------------------------------------------
-struct WalkOut {
-    uint32_t a, b, err;
-};
+constexpr uint32_t SMEM_BLKMAP_MAX = 8192;  // blkmap entries (32 blocks each) kept in shared memory
 
-// two wavelet levels (one level record) for two positions of the same even-depth node
-// (WaveletFixedBlockBoosting.java:1185-1279); `two` = the code has a second level below this one
-__device__ __forceinline__ void dlevel_pair(const DevIndex& ix, uint32_t node, uint32_t t, uint32_t u, bool two, uint32_t& ra, uint32_t& rb,
-                                            uint32_t& n_load) {
-    const uint32_t qa = ra / SECTOR_BITS, qb = rb / SECTOR_BITS;
-    const Rec32 A = COUNT_LD_SECTOR(ix.sectors + (node + qa));
-    Rec32 B = A;
-    if (qb != qa) B = COUNT_LD_SECTOR(ix.sectors + (node + qb));
-    n_load += qb != qa ? 2u : 1u;
-    ra = dlevel_rank(A, ra, ra - qa * SECTOR_BITS, t, u, two);
-    rb = dlevel_rank(B, rb, rb - qb * SECTOR_BITS, t, u, two);
+// C, superblock descriptors and the root-record directory, in shared memory when they fit
+__device__ __forceinline__ CountTables stage_count_tables(const DevIndex& ix, uint32_t* smem) {
+    CountTables t;
+    uint32_t used = 0;
+    auto stage = [&](const uint32_t* src, uint32_t words, bool fits) -> const uint32_t* {
+        if (!fits) return src;
+        uint32_t* d = smem + used;
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) d[i] = src[i];
+        used += (words + 1u) & ~1u;  // keep 8-byte alignment for the 64-bit entries
+        return d;
+    };
+    t.C = stage(ix.C, ix.n_c, ix.n_c <= SMEM_C_MAX);
+    t.sb = reinterpret_cast<const SbDesc*>(stage(reinterpret_cast<const uint32_t*>(ix.sb), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
+#if COUNT_SPEC_ROOT
+    t.sbroot = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.sbroot), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
+    t.blkmap = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.blkmap), 2 * ix.n_blkmap, ix.n_blkmap <= SMEM_BLKMAP_MAX));
+#else
+    t.sbroot = ix.sbroot;
+    t.blkmap = ix.blkmap;
+#endif
+    __syncthreads();
+    return t;
 }
-
-// rank(., c) of two positions of ONE block: ra/rb are block-relative positions (rb == ra for a single query)
-__device__ __forceinline__ WalkOut walk_pair(const DevIndex& ix, uint32_t blk, uint32_t c, uint32_t ra, uint32_t rb, bool on,
-                                             uint32_t queries, uint32_t& n_level, uint32_t& n_load, uint32_t& n_rec) {
-    WalkOut o;
-    o.a = o.b = o.err = 0;
-    if (!on) return o;
-    const Rec32 cell = COUNT_LD_CELL(ix.cells + ((uint64_t)blk * ix.sigma + c));
-    ++n_load;
-    const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
-    const uint32_t base = cell.w[0];
-    if (kind != CELL_NORMAL) {
-        const uint32_t run = kind == CELL_RUN ? 0xffffffffu : 0u;  // :1141-1146
-        o.a = base + (ra & run);
-        o.b = base + (rb & run);
-        o.err = kind == CELL_THROW;
-        return o;
-    }
-    const uint32_t code = cell.w[1];
-    const uint32_t L = cell.w[2] & 0xffu;
-    const uint32_t pairs = (L + 1u) >> 1;
-    const uint32_t inl = pairs > CELL_INLINE_PAIRS ? CELL_INLINE_PAIRS - 1u : pairs;
-    const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);  // codes longer than 10 bits: rest of the path
-#pragma unroll
-    for (uint32_t k = 0; k < CELL_INLINE_PAIRS; ++k)
-        if (k < inl) {
-            const uint32_t d = 2u * k;
-            const bool two = d + 1u < L;
-            dlevel_pair(ix, cell.w[3 + k], (code >> (L - 1u - d)) & 1u, two ? (code >> (L - 2u - d)) & 1u : 0u, two, ra, rb, n_load);
-        }
-#pragma unroll 1
-    for (uint32_t k = inl; k < pairs; ++k) {
-        const uint32_t d = 2u * k;
-        const bool two = d + 1u < L;
-        dlevel_pair(ix, __ldg(more + (k - inl)), (code >> (L - 1u - d)) & 1u, two ? (code >> (L - 2u - d)) & 1u : 0u, two, ra, rb, n_load);
-    }
-    n_level += L * queries;
-    n_rec += pairs * queries;
-    o.a = base + ra;
-    o.b = base + rb;
-    return o;
+constexpr size_t COUNT_SMEM_MAX_BYTES = (SMEM_C_MAX + 4 * (size_t)SMEM_SB_MAX + 2 * (size_t)SMEM_BLKMAP_MAX) * 4 + 16;
+inline size_t count_smem_bytes(const DevIndex& ix) {
+    size_t n = 0;
+    if (ix.n_c <= SMEM_C_MAX) n += (ix.n_c + 1u) & ~1u;
+    if (ix.n_sb <= SMEM_SB_MAX) n += (COUNT_SPEC_ROOT ? 4 : 2) * (size_t)ix.n_sb;
+    if (COUNT_SPEC_ROOT && ix.n_blkmap <= SMEM_BLKMAP_MAX) n += 2 * (size_t)ix.n_blkmap;
+    return n * 4 + 16;
 }
 
 #ifndef COUNT_MIN_CTAS
@@ -222,10 +181,11 @@ __global__ void __launch_bounds__(CTA_THREADS, COUNT_MIN_CTAS)
 k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,
         uint32_t n_pat, int32_t* __restrict__ counts, int32_t* __restrict__ status, uint32_t* __restrict__ ranges, unsigned int* queue,
         unsigned long long* stats) {
-    extern __shared__ uint32_t smem[];
-    const SmemTables T = stage_tables(ix, smem);
+    extern __shared__ __align__(8) uint32_t smem[];
+    const CountTables T = stage_count_tables(ix, smem);
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t n_rank = 0, n_level = 0, n_load = 0, n_rec = 0;
+    CountCounters cnt;
+    cnt.ranks = cnt.levels = cnt.loads = cnt.recs = cnt.spec_wasted = 0;
 
     for (;;) {
         unsigned batch = 0;
@@ -281,28 +241,10 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
             if (go && i >= 1) cnext = (uint32_t)__ldg(ix.char2code + raw2);
             if (go && i >= 2) raw2 = (uint32_t)__ldg(pch + (i - 2));
 
-            // block of each position; start == 0 needs no query (rank(0, c) == 0, :1012)
-            const SbDesc se = T.sb[ep >> SB_LOG];
-            const uint32_t blk_e = se.first_block + ((ep & SB_MASK) >> se.block_log);
-            const uint32_t re = ep & ((1u << se.block_log) - 1u);
-            const SbDesc ss = T.sb[sp >> SB_LOG];
-            const uint32_t blk_s = ss.first_block + ((sp & SB_MASK) >> ss.block_log);
-            const uint32_t rs = sp & ((1u << ss.block_log) - 1u);
-            const bool with_s = sp != 0u && blk_s == blk_e;
-            const bool second = go && sp != 0u && blk_s != blk_e;
-            n_rank += go ? (sp != 0u ? 2u : 1u) : 0u;
-
-            const WalkOut w1 = walk_pair(ix, blk_e, c, with_s ? rs : re, re, go, with_s ? 2u : 1u, n_level, n_load, n_rec);
-            uint32_t val_s = with_s ? w1.a : 0u;
-            const uint32_t val_e = w1.b;
-            uint32_t e2 = 0;
-            if (__any_sync(FULL, second)) {
-                const WalkOut w2 = walk_pair(ix, blk_s, c, rs, rs, second, 1u, n_level, n_load, n_rec);
-                if (second) val_s = w2.a;
-                e2 = w2.err;
-            }
+            uint32_t val_s = sp, val_e = ep;
+            const uint32_t e1 = count_step(ix, T, c, &val_s, &val_e, go, cnt);
             if (go) {
-                if (w1.err | e2) {
+                if (e1) {
                     err = 1;
                     alive = false;
                 } else {
@@ -323,16 +265,18 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
     }
 
     for (int o = 16; o; o >>= 1) {
-        n_rank += __shfl_xor_sync(FULL, n_rank, o);
-        n_level += __shfl_xor_sync(FULL, n_level, o);
-        n_load += __shfl_xor_sync(FULL, n_load, o);
-        n_rec += __shfl_xor_sync(FULL, n_rec, o);
+        cnt.ranks += __shfl_xor_sync(FULL, cnt.ranks, o);
+        cnt.levels += __shfl_xor_sync(FULL, cnt.levels, o);
+        cnt.loads += __shfl_xor_sync(FULL, cnt.loads, o);
+        cnt.recs += __shfl_xor_sync(FULL, cnt.recs, o);
+        cnt.spec_wasted += __shfl_xor_sync(FULL, cnt.spec_wasted, o);
     }
     if (lane == 0 && stats) {
-        atomicAdd(stats + 0, (unsigned long long)n_rank);
-        atomicAdd(stats + 1, (unsigned long long)n_level);
-        atomicAdd(stats + 6, (unsigned long long)n_load);
-        atomicAdd(stats + 7, (unsigned long long)n_rec);
+        atomicAdd(stats + 0, (unsigned long long)cnt.ranks);
+        atomicAdd(stats + 1, (unsigned long long)cnt.levels);
+        atomicAdd(stats + 6, (unsigned long long)cnt.loads);
+        atomicAdd(stats + 7, (unsigned long long)cnt.recs);
+        atomicAdd(stats + 8, (unsigned long long)cnt.spec_wasted);
     }
 }
 

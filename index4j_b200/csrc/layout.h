@@ -60,6 +60,18 @@ struct SbDesc {
     uint32_t block_log;    // blockSizeLog
 };
 
+struct U32x2 {
+    uint32_t x, y;
+};
+
+// --- root-record directory (speculative root fetch of the backward search, count_lane.h).  The level records of the
+// ROOT nodes of a superblock's tree blocks are stored first in the superblock's record range, `root_stride` records per
+// block (every block of a superblock has 2^block_log positions, so every root has the same number of records), in block
+// order, single-symbol blocks skipped.  The root record of (block, position r) is therefore computable without touching
+// memory:  sbroot[sb].x + G(block) * sbroot[sb].y + r / 96,  G(block) = number of tree blocks before `block` (global),
+// from blkmap[block / 32] = {bit k set <=> block 32w + k has a tree, tree blocks before block 32w}.
+// sbroot[sb].x is stored pre-biased by -G(first block of sb) * stride (wrapping 32-bit arithmetic).
+
 struct PatDesc {  // one per pattern, written by the pre-pass
     uint64_t off;     // offset of the pattern's first char in the concatenated code array
     uint32_t len;
@@ -79,8 +91,10 @@ struct DevIndex {
     uint32_t n_isa;        // entries of positions (ISA samples)
     uint32_t n_sa;
     uint32_t s_total_ones;
-    uint32_t pad0;
+    uint32_t n_blkmap;     // entries of blkmap
     const uint32_t* C;
+    const U32x2* sbroot;        // [n_sb + 1] root-record directory (see above)
+    const U32x2* blkmap;        // [n_blkmap]
     const uint16_t* char2code;  // [65536], 0 = not in alphabet (monotonicMap.getOrDefault(c, 0))
     const uint16_t* code2char;  // monotonicLookUp
     const SbDesc* sb;

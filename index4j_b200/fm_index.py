@@ -91,6 +91,7 @@ def native():
         L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp, vp]
         L.fmgpu_last_stats.argtypes = [vp, vp]
+        L.fmgpu_last_stats_ex.argtypes = [vp, vp, C.c_uint32]
         L.fmgpu_set_timing.argtypes = [vp, i32]
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         _lib = L
@@ -180,9 +181,10 @@ class FmIndex:
         return {k: int(v) for k, v in zip(names, out)}
 
     def last_stats(self) -> dict:
-        out = np.zeros(8, dtype=np.uint64)
-        self._check(self._lib.fmgpu_last_stats(self._h, out.ctypes.data))
-        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "level_records"]
+        out = np.zeros(9, dtype=np.uint64)
+        self._check(self._lib.fmgpu_last_stats_ex(self._h, out.ctypes.data, out.size))
+        names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "level_records",
+                 "spec_root_wasted"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def set_timing(self, enable: bool = True):

@@ -9,6 +9,7 @@
 
 #include "../../index4j_b200/csrc/flatten.hpp"
 #include "../../index4j_b200/csrc/jstream.hpp"
+#include "../../index4j_b200/csrc/count_lane.h"
 #include "../../index4j_b200/csrc/lf_lane.h"
 
 using namespace fmgpu;
@@ -19,6 +20,7 @@ struct FC {
     fmgpu_host::FlatIndex F;
     DevIndex ix;
     SmemTables T;
+    CountTables CT;
     uint16_t binom[15 * 16];
 };
 const Rec32 ZERO{};
@@ -75,8 +77,14 @@ int fc_load(const uint8_t* buf, uint64_t len, int threads, void** out) {
         h->ix.soffsets = h->F.soffsets.data();
         h->ix.sa = h->F.sa.data();
         h->ix.isa = h->F.isa.data();
+        h->ix.sbroot = h->F.sbroot.data();
+        h->ix.blkmap = h->F.blkmap.data();
         h->T.C = h->ix.C;
         h->T.sb = h->ix.sb;
+        h->CT.C = h->ix.C;
+        h->CT.sb = h->ix.sb;
+        h->CT.sbroot = h->ix.sbroot;
+        h->CT.blkmap = h->ix.blkmap;
         fill_binom(h->binom);
         *out = h;
         return 0;
@@ -115,11 +123,12 @@ int fc_rank(void* h, uint32_t pos, uint32_t sym, int64_t* out) {
     return st;
 }
 
-// FmIndex.count over the flat layout (sequential restatement of what a lane pair does)
+// FmIndex.count over the flat layout: the kernel's per-lane step (count_step, count_lane.h) driven sequentially
 void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
                     uint32_t* ranges, uint64_t* counters) {
     FC& h = *(FC*)hv;
-    uint64_t n_rank = 0, n_level = 0;
+    CountCounters cnt{0, 0, 0, 0, 0};
+    uint64_t n_rank = 0, n_level = 0, n_rec = 0, n_load = 0, n_waste = 0;
     for (uint32_t p = 0; p < n_pat; ++p) {
         const uint16_t* pat = chars + pat_off[p];
         const int64_t len = (int64_t)(pat_off[p + 1] - pat_off[p]);
@@ -136,14 +145,17 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
                 bool zero = false;
                 while (sp < ep && i >= 1) {
                     c = h.ix.char2code[pat[--i]];
-                    if (c == 0) {
+                    if (c == 0 || c >= h.ix.sigma) {
                         zero = true;
+                        sp = ep = 0;
                         break;
                     }
-                    uint32_t a = 0, b = 0;
-                    const int s1 = host_rank(h, sp, c, &a, &n_rank, &n_level);
-                    const int s2 = host_rank(h, ep, c, &b, &n_rank, &n_level);
-                    if (s1 || s2) {
+                    if (h.ix.q4 && ep >= h.ix.length) {
+                        st = 9;
+                        break;
+                    }
+                    uint32_t a = sp, b = ep;
+                    if (count_step(h.ix, h.CT, c, &a, &b, true, cnt)) {
                         st = 9;
                         break;
                     }
@@ -159,11 +171,43 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
             ranges[2 * p] = sp;
             ranges[2 * p + 1] = (!st && result > 0) ? ep : sp;
         }
+        n_rank += cnt.ranks;
+        n_level += cnt.levels;
+        n_rec += cnt.recs;
+        n_load += cnt.loads;
+        n_waste += cnt.spec_wasted;
+        cnt = CountCounters{0, 0, 0, 0, 0};
     }
     if (counters) {
         counters[0] += n_rank;
         counters[1] += n_level;
+        counters[5] += n_waste;
+        counters[6] += n_load;
+        counters[7] += n_rec;
     }
+}
+
+// every NORMAL cell's first record must be the root record the directory computes (speculative root fetch); returns the
+// number of violations
+uint64_t fc_check_roots(void* hv) {
+    FC& h = *(FC*)hv;
+    uint64_t bad = 0;
+    for (uint32_t sb = 0; sb < h.ix.n_sb; ++sb) {
+        const uint32_t lo = h.ix.sb[sb].first_block;
+        const uint32_t hi = sb + 1 < h.ix.n_sb ? h.ix.sb[sb + 1].first_block : (uint32_t)(h.F.blocks.size() - 1);
+        for (uint32_t blk = lo; blk < hi; ++blk) {
+            uint32_t root = 0;
+            const bool tree = root_record(h.CT, sb, blk, &root);
+            const bool run = (h.F.blocks[blk].w[1] & 1u) != 0u;
+            if (tree && h.F.blocks[blk].w[0] != root) ++bad;
+            for (uint32_t sym = 0; sym < h.ix.sigma; ++sym) {
+                const Rec32& cell = h.F.cells[(size_t)blk * h.ix.sigma + sym];
+                if (((cell.w[2] >> 8) & 0xffu) != CELL_NORMAL) continue;
+                if (!tree || run || cell.w[3] != root || (cell.w[2] & 0xffu) == 0u) ++bad;
+            }
+        }
+    }
+    return bad;
 }
 
 void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena, const uint64_t* arena_off,

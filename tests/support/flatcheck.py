@@ -35,6 +35,8 @@ def lib():
         L.fc_sizes.argtypes = [vp, vp]
         L.fc_rank.argtypes = [vp, u32, u32, C.POINTER(C.c_int64)]
         L.fc_count_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
+        L.fc_check_roots.argtypes = [vp]
+        L.fc_check_roots.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
         L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp]
@@ -78,6 +80,9 @@ class FlatIndexHost:
         lib().fc_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data,
                              ranges.ctypes.data, self.counters.ctypes.data)
         return counts, status, ranges.reshape(n, 2)
+
+    def check_roots(self) -> int:
+        return int(lib().fc_check_roots(self._h))
 
     def locate_rows(self, rows):
         rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()

@@ -48,6 +48,13 @@ def test_rank_cells_match_oracle(flats, name):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
+def test_root_record_directory(flats, name):
+    """The speculative root fetch of count_step computes a block's root record from shared-memory tables alone: it must be the
+    first record of every NORMAL cell of the block (and the block descriptor's root)."""
+    assert flats(name).check_roots() == 0
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
 def test_sampled_rows_match_oracle(flats, name):
     case, f = get_case(name), flats(name)
     rng = np.random.default_rng(2)
