@@ -127,6 +127,9 @@ int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d
  * [7] level records a query needs (one per TWO wavelet levels): by rank queries and by LF steps
  * Used by bench.py for the roofline's algorithmic-bytes figure. */
 int fmgpu_last_stats(fmgpu_index* idx, uint64_t out8[8]);
+/* The kernels keep these counters only while enabled (default: off — the production instantiations carry none;
+ * [5], the launch count, is always kept). */
+int fmgpu_set_stats(fmgpu_index* idx, int enable);
 /* Same, all FMGPU_N_STATS counters (n_out >= FMGPU_N_STATS):
  * [8] speculative root-record loads of the backward-search kernel that turned out unnecessary (the
  *     cell was CONST / RUN): traffic on top of the algorithmic figure. */

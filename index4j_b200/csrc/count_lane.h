@@ -25,6 +25,13 @@
 #define COUNT_SPEC_ROOT 0
 #endif
 
+// a record variable that is only read after a (conditional) load: left uninitialised on the device, zeroed on the host
+#if defined(__CUDA_ARCH__)
+#define FMGPU_UNSET
+#else
+#define FMGPU_UNSET {}
+#endif
+
 namespace fmgpu {
 
 struct CountTables {  // SmemTables + the root-record directory (shared memory when it fits)
@@ -65,15 +72,15 @@ FMGPU_HD void track_open(Track& t, const Rec32& cell, uint32_t r, bool on, uint3
 
 // the two levels of one record for one track
 FMGPU_HD void track_levels(Track& t, const Rec32& x) {
-    const bool two = t.len >= 2u;
-    const uint32_t b = t.r % SECTOR_BITS;
-    t.r = dlevel_rank(x, t.r, b, t.code >> 31, (t.code >> 30) & 1u, two);
+    // a code that ends at the record's first level has u == 0: the left-aligned code shifts in zeros
+    t.r = dlevel_rank(x, t.r % SECTOR_BITS, t.code >> 31, (t.code >> 30) & 1u);
     t.code <<= 2;
-    t.len = two ? t.len - 2u : 0u;
+    t.len = t.len >= 2u ? t.len - 2u : 0u;
 }
 
 // One backward-search step for the lane: on return *sp / *ep hold rank(start, c) / rank(end, c) (NOT yet offset by C[c]).
 // Returns 1 where the reference throws (THROW cells).  `on` = the lane takes part in this step.
+template <bool STATS>
 FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t c, uint32_t* sp, uint32_t* ep, bool on, CountCounters& cnt) {
     if (!on) return 0u;
     const uint32_t s = *sp, e = *ep;
@@ -86,7 +93,7 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
     const uint32_t rb = e & ((1u << db.block_log) - 1u);
     const uint32_t ra = s & ((1u << da.block_log) - 1u);
     const bool split = on_a && blk_a != blk_b;
-    cnt.ranks += on_a ? 2u : 1u;
+    if (STATS) cnt.ranks += on_a ? 2u : 1u;
 
     // stage 0: cells and speculative root records, all issued before any is consumed
     uint32_t root_b = 0, root_a = 0;
@@ -103,19 +110,21 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
     const Rec32 cell_b = FMGPU_LD256(ix.cells + ((uint64_t)blk_b * ix.sigma + c));
     Rec32 cell_a = cell_b;
     if (split) cell_a = FMGPU_LD256(ix.cells + ((uint64_t)blk_a * ix.sigma + c));
-    Rec32 xb = cell_b, xa = cell_b;  // placeholders, never interpreted unless loaded
+    Rec32 xb FMGPU_UNSET, xa FMGPU_UNSET;  // never interpreted unless loaded
     if (tree_b) xb = FMGPU_LD256(pb);
     if (ld_a) xa = FMGPU_LD256(pa);
-    cnt.loads += (split ? 2u : 1u) + (tree_b ? 1u : 0u) + (ld_a ? 1u : 0u);
+    if (STATS) cnt.loads += (split ? 2u : 1u) + (tree_b ? 1u : 0u) + (ld_a ? 1u : 0u);
 
     uint32_t err = 0;
     Track A, B;
     track_open(B, cell_b, rb, true, &err);
     track_open(A, cell_a, ra, on_a, &err);
-    cnt.levels += A.len + B.len;
     const uint32_t pairs_b = (B.len + 1u) >> 1, pairs_a = (A.len + 1u) >> 1;
-    cnt.recs += pairs_a + pairs_b;
-    cnt.spec_wasted += (tree_b && !B.len ? 1u : 0u) + (ld_a && !A.len ? 1u : 0u);
+    if (STATS) {
+        cnt.levels += A.len + B.len;
+        cnt.recs += pairs_a + pairs_b;
+        cnt.spec_wasted += (tree_b && !B.len ? 1u : 0u) + (ld_a && !A.len ? 1u : 0u);
+    }
 
     // levels 0-1: the speculative root records (a NORMAL cell's first record is its block's root: cell.w[3] == root)
 #if COUNT_SPEC_ROOT
@@ -135,10 +144,10 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
             const Rec32* qb = ix.sectors + (cell_b.w[3 + k] + B.r / SECTOR_BITS);
             const Rec32* qa = ix.sectors + (cell_a.w[3 + k] + A.r / SECTOR_BITS);
             const bool l_a = go_a && !(go_b && qa == qb);
-            Rec32 yb = cell_b, ya = cell_b;
+            Rec32 yb FMGPU_UNSET, ya FMGPU_UNSET;
             if (go_b) yb = FMGPU_LD256(qb);
             if (l_a) ya = FMGPU_LD256(qa);
-            cnt.loads += (go_b ? 1u : 0u) + (l_a ? 1u : 0u);
+            if (STATS) cnt.loads += (go_b ? 1u : 0u) + (l_a ? 1u : 0u);
             if (go_b) track_levels(B, yb);
             if (go_a) track_levels(A, l_a ? ya : yb);
         }
@@ -162,7 +171,7 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
                 const Rec32 y = FMGPU_LD256(ix.sectors + (FMGPU_LDG32(more_a + (k - (CELL_INLINE_PAIRS - 1u))) + A.r / SECTOR_BITS));
                 track_levels(A, y);
             }
-            cnt.loads += (go_b ? 1u : 0u) + (go_a ? 1u : 0u);
+            if (STATS) cnt.loads += (go_b ? 1u : 0u) + (go_a ? 1u : 0u);
         }
     }
     *sp = on_a ? A.base + A.r : 0u;

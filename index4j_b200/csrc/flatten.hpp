@@ -365,13 +365,15 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
             // level records (layout.h): {c1, c01 | c11 << 16, 96 bits of this node, for the same 96 positions the bit each
             // element has one level further down (in the child it goes to; 0 if that child is a leaf)}
             const uint32_t nrec = n.size / fmgpu::SECTOR_BITS + 1;
-            uint32_t ones = 0, cpos[2] = {0, 0}, cones[2] = {0, 0};
+            uint32_t cnt2[2][2] = {{0, 0}, {0, 0}}, cpos[2] = {0, 0};  // elements so far by (bit here, bit one level down)
             for (uint32_t q = 0; q < nrec; ++q) {
                 Rec32& X = F.sectors[(size_t)n.sector + q];
                 memset(&X, 0, sizeof X);
-                if (cones[0] > 0xffffu || cones[1] > 0xffffu) throw FormatError("wavelet child with more than 65535 ones");
-                X.w[0] = ones;
-                X.w[1] = cones[0] | (cones[1] << 16);
+                for (int t = 0; t < 2; ++t)
+                    for (int u = 0; u < 2; ++u)
+                        if (cnt2[t][u] > 0xffffu) throw FormatError("wavelet node prefix count exceeds 16 bits");
+                X.w[0] = cnt2[0][0] | (cnt2[0][1] << 16);
+                X.w[1] = cnt2[1][0] | (cnt2[1][1] << 16);
                 const uint32_t lo = q * fmgpu::SECTOR_BITS;
                 const uint32_t valid = lo < n.size ? std::min<uint32_t>(fmgpu::SECTOR_BITS, n.size - lo) : 0u;
                 for (uint32_t i = 0; i < valid; ++i) {
@@ -382,14 +384,9 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                         cb = bits_get(bits, (uint64_t)ch[t]->start + cpos[t], 1);
                     }
                     ++cpos[t];
-                    if (t) {
-                        X.w[2 + (i >> 5)] |= 1u << (i & 31u);
-                        ++ones;
-                    }
-                    if (cb) {
-                        X.w[5 + (i >> 5)] |= 1u << (i & 31u);
-                        ++cones[t];
-                    }
+                    ++cnt2[t][cb];
+                    if (t) X.w[2 + (i >> 5)] |= 1u << (i & 31u);
+                    if (cb) X.w[5 + (i >> 5)] |= 1u << (i & 31u);
                 }
             }
             // node record: entries [t][u] = {c, a}; child t a leaf: [t][0] = {LEAF1 | sym, boundary rank}

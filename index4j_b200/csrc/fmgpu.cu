@@ -101,6 +101,7 @@ struct fmgpu_index {
     cudaStream_t cstream[COUNT_CTX - 1] = {nullptr};
     uint64_t last_launches = 0;
     bool stats_valid = false;
+    bool count_stats = false;  // fmgpu_set_stats: backward-search kernel with work counters
     uint32_t stats_ctx_mask = 1;  // compute contexts whose counters belong to the most recent call
     // optional per-call timing of the dominant kernel (bench.py's roofline): ring of event pairs
     static constexpr int TIMING_SLOTS = 64;
@@ -179,9 +180,14 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
     int grid = ix->count_ctas;
     const int need = (int)(((uint64_t)n_pat + CTA_THREADS - 1) / CTA_THREADS);
     if (need < grid) grid = need;
-    k_count<<<grid, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
-                                                        d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
-                                                        (unsigned long long*)(ctrl + CTRL_STATS));
+    if (ix->count_stats)
+        k_count<true><<<grid, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
+                                                                  d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
+                                                                  (unsigned long long*)(ctrl + CTRL_STATS));
+    else
+        k_count<false><<<grid, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
+                                                                   d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
+                                                                   (unsigned long long*)(ctrl + CTRL_STATS));
     if (ix->timing) {
         CU(cudaEventRecord(ix->ev1[slot], st));
         ix->timed_calls++;
@@ -266,9 +272,13 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
     if (!rc) {
         ix->tables_smem = count_smem_bytes(ix->dev);
         // the attribute is per function, not per index: always the largest table set any index can stage
-        if (cudaFuncSetAttribute((const void*)k_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess)
+        if (cudaFuncSetAttribute((const void*)k_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute((const void*)k_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess)
             rc = fail(FMGPU_ERR_CUDA, "k_count: cannot reserve %zu bytes of shared memory", ix->tables_smem);
-        if (!rc) rc = grid_for((const void*)k_count, ix->sm_count, ix->tables_smem, &ix->count_ctas);
+        int g0 = 0, g1 = 0;
+        if (!rc) rc = grid_for((const void*)k_count<false>, ix->sm_count, ix->tables_smem, &g0);
+        if (!rc) rc = grid_for((const void*)k_count<true>, ix->sm_count, ix->tables_smem, &g1);
+        ix->count_ctas = g0 < g1 ? g0 : g1;
     }
     if (!rc) rc = lf_setup(ix);
     if (!rc && (cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -393,6 +403,13 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     CU(cudaStreamSynchronize(cp));
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < fmgpu_index::COUNT_CTX - 1; ++i) CU(cudaStreamSynchronize(ix->cstream[i]));
+    return 0;
+}
+
+int fmgpu_set_stats(fmgpu_index* ix, int enable) {
+    if (!ix) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->count_stats = enable != 0;
     return 0;
 }
 

@@ -177,6 +177,8 @@ inline size_t count_smem_bytes(const DevIndex& ix) {
 #ifndef COUNT_MIN_CTAS
 #define COUNT_MIN_CTAS 2
 #endif
+// STATS: count rank queries / levels / records (fmgpu_set_stats; bench.py's roofline accounting and the tests) — off in production
+template <bool STATS>
 __global__ void __launch_bounds__(CTA_THREADS, COUNT_MIN_CTAS)
 k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __restrict__ pats, const uint32_t* __restrict__ order,
         uint32_t n_pat, int32_t* __restrict__ counts, int32_t* __restrict__ status, uint32_t* __restrict__ ranges, unsigned int* queue,
@@ -242,7 +244,7 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
             if (go && i >= 2) raw2 = (uint32_t)__ldg(pch + (i - 2));
 
             uint32_t val_s = sp, val_e = ep;
-            const uint32_t e1 = count_step(ix, T, c, &val_s, &val_e, go, cnt);
+            const uint32_t e1 = count_step<STATS>(ix, T, c, &val_s, &val_e, go, cnt);
             if (go) {
                 if (e1) {
                     err = 1;
@@ -264,6 +266,7 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
         }
     }
 
+    if (!STATS) return;
     for (int o = 16; o; o >>= 1) {
         cnt.ranks += __shfl_xor_sync(FULL, cnt.ranks, o);
         cnt.levels += __shfl_xor_sync(FULL, cnt.levels, o);

@@ -29,6 +29,8 @@ constexpr uint32_t LOCATE_TAB_WORDS = (32768u * 2u + 16u * 2u) / 4u;  // inverse
 
 inline size_t locate_smem_bytes(const DevIndex& ix) { return LOCATE_TAB_WORDS * 4 + tables_smem_bytes(ix); }
 
+// STATS: keep the work counters (fmgpu_set_stats); the production instantiation carries none
+template <bool STATS>
 __global__ void __launch_bounds__(LOCATE_THREADS, LOCATE_MIN_CTAS)
 k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, uint32_t chunk, unsigned int* queue,
          unsigned long long* stats) {
@@ -114,6 +116,7 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
         }
     }
 
+    if (!STATS) return;
     for (int o = 16; o; o >>= 1) {
         cnt.ranks += __shfl_xor_sync(FULL, cnt.ranks, o);
         cnt.rank_levels += __shfl_xor_sync(FULL, cnt.rank_levels, o);
@@ -138,7 +141,7 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
 #ifndef EXTRACT_THREADS
 #define EXTRACT_THREADS 256
 #endif
-template <int MODE>
+template <int MODE, bool STATS>
 __global__ void __launch_bounds__(EXTRACT_THREADS)
 k_extract(const DevIndex ix, WalkParams P, uint32_t chunk, unsigned int* queue, unsigned long long* stats) {
     extern __shared__ uint32_t smem[];
@@ -185,6 +188,7 @@ k_extract(const DevIndex ix, WalkParams P, uint32_t chunk, unsigned int* queue, 
         if (lane.active) lane.trip(ix, T, P, cnt);
     }
 
+    if (!STATS) return;
     for (int o = 16; o; o >>= 1) {
         cnt.ranks += __shfl_xor_sync(FULL, cnt.ranks, o);
         cnt.rank_levels += __shfl_xor_sync(FULL, cnt.rank_levels, o);

@@ -60,35 +60,29 @@ struct SmemTables {  // C array and superblock descriptors (shared memory when t
 // level records (layout.h): two tree levels from one 64-byte record
 // ------------------------------------------------------------------------------------------
 // elements among the first b positions of a level record whose bits at the record's two levels are (t, u): one pass over
-// (plane0 ^ ~T) & (plane1 ^ ~U) & mask.  With `one` set the second level is ignored (count of bit t alone).
-FMGPU_HD uint32_t dlevel_count(const Rec32& x, uint32_t b, uint32_t t, uint32_t u, bool one) {
+// (plane0 ^ ~T) & (plane1 ^ ~U) & mask.  A code that ends at the record's first level (child t is a leaf) is the case u = 0:
+// plane 1 holds 0 for every element that goes to a leaf child, so the same expression counts "bit t at this level".
+FMGPU_HD uint32_t dlevel_count(const Rec32& x, uint32_t b, uint32_t t, uint32_t u) {
     const uint32_t tm = t ? 0u : 0xffffffffu;
     const uint32_t um = u ? 0u : 0xffffffffu;
-    const uint32_t all = one ? 0xffffffffu : 0u;
     uint32_t n = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) n += popc32((x.w[2 + k] ^ tm) & ((x.w[5 + k] ^ um) | all) & low_mask_clamped((int)b - 32 * k));
+    for (int k = 0; k < 3; ++k) n += popc32((x.w[2 + k] ^ tm) & (x.w[5 + k] ^ um) & low_mask_clamped((int)b - 32 * k));
     return n;
 }
-// elements before the record (P of them) with bits (t) / (t, u)
-FMGPU_HD uint32_t dlevel_base1(const Rec32& x, uint32_t P, uint32_t t) { return t ? x.w[0] : P - x.w[0]; }
-FMGPU_HD uint32_t dlevel_base2(const Rec32& x, uint32_t P, uint32_t t, uint32_t u) {
-    const uint32_t c01 = x.w[1] & 0xffffu, c11 = x.w[1] >> 16;
-    const uint32_t a = t ? c11 : c01;               // (t, 1)
-    const uint32_t tot = t ? x.w[0] : P - x.w[0];   // (t, *)
-    return u ? a : tot - a;
+// elements before the record with bits (t, u): w0 = c00 | c01 << 16, w1 = c10 | c11 << 16 (node-relative, < 65536)
+FMGPU_HD uint32_t dlevel_base(const Rec32& x, uint32_t t, uint32_t u) { return ((t ? x.w[1] : x.w[0]) >> (u << 4)) & 0xffffu; }
+// bit b (0..95) of plane 0 / plane 1
+FMGPU_HD uint32_t plane_bit(const Rec32& x, uint32_t plane, uint32_t b) {
+    const uint32_t wi = b >> 5;
+    const uint32_t w = plane ? (wi == 0u ? x.w[5] : (wi == 1u ? x.w[6] : x.w[7])) : (wi == 0u ? x.w[2] : (wi == 1u ? x.w[3] : x.w[4]));
+    return (w >> (b & 31u)) & 1u;
 }
-FMGPU_HD uint32_t plane_bit(const Rec32& x, uint32_t plane, uint32_t b) { return (rec_word(x, 2u + 3u * plane + (b >> 5)) >> (b & 31u)) & 1u; }
 
-// The rank walk of WaveletFixedBlockBoosting.rank (:1185-1279) for the two levels a record holds: position r of the
-// even-depth node (b = r mod 96 inside the record), code bits t (this level) and u (next level).
-//   one level : returns the position in child t
-//   two levels: returns the position in grandchild (t, u)
-FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t r, uint32_t b, uint32_t t, uint32_t u, bool two) {
-    const uint32_t n = dlevel_count(x, b, t, u, !two);
-    const uint32_t base = two ? dlevel_base2(x, r - b, t, u) : dlevel_base1(x, r - b, t);
-    return base + n;
-}
+// The rank walk of WaveletFixedBlockBoosting.rank (:1185-1279) for the two levels a record holds: position b inside the
+// record (b = r mod 96, r = position in the even-depth node), code bits t (this level) and u (next level; 0 when the code
+// ends at this level).  Returns the position in grandchild (t, u) — in child t when the code ends here.
+FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t b, uint32_t t, uint32_t u) { return dlevel_base(x, t, u) + dlevel_count(x, b, t, u); }
 
 // The descent of WaveletFixedBlockBoosting.inverseSelect (:1386-1505) through the two levels of a record with the node
 // record N of the even-depth node.  Returns true at a leaf (*sym, *rank = rank(pos, sym) incl. the boundary rank);
@@ -100,16 +94,14 @@ FMGPU_HD bool dlevel_descend(const Rec32& x, const Rec32& N, uint32_t b, uint32_
     const uint32_t e0 = t ? N.w[4] : N.w[0];
     const uint32_t a0 = t ? N.w[5] : N.w[1];
     const bool leaf1 = (e0 & LEAF1_FLAG) != 0u;
-    const uint32_t n = dlevel_count(x, b, t, u, leaf1);
-    const uint32_t P = *r - b;
+    const uint32_t r2 = dlevel_rank(x, b, t, u);  // leaf child: u == 0 and the count is that of bit t alone
     if (leaf1) {
         ++*levels;
         *sym = e0 & 0xffffu;
-        *rank = a0 + dlevel_base1(x, P, t) + n;
+        *rank = a0 + r2;
         return true;
     }
     *levels += 2;
-    const uint32_t r2 = dlevel_base2(x, P, t, u) + n;
     const uint32_t e1 = t ? N.w[6] : N.w[2];
     const uint32_t a1 = t ? N.w[7] : N.w[3];
     const uint32_t e = u ? e1 : e0;
@@ -168,7 +160,7 @@ FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t 
         const Rec32 x = FMGPU_LD256(ix.sectors + (node + r / SECTOR_BITS));
         const uint32_t t = (code >> (L - 1u - d)) & 1u;
         const uint32_t u = two ? (code >> (L - 2u - d)) & 1u : 0u;
-        r = dlevel_rank(x, r, r % SECTOR_BITS, t, u, two);
+        r = dlevel_rank(x, r % SECTOR_BITS, t, u);
     }
     *n_level += L;
     *n_rec += pairs;

@@ -29,15 +29,16 @@ constexpr uint32_t CELL_INLINE_PAIRS = 5;
 
 // --- level record (32 bytes): TWO tree levels of 96 positions.  Only the wavelet-tree nodes at EVEN depth own records;
 // record q of a node covers its positions [96q, 96q + 96):
-//   w0 = c1  : ones in this node's bitvector before the record
-//   w1 = c01 | c11 << 16 : elements before the record whose bits at this level and the next are (0,1) / (1,1)
+//   w0 = c00 | c01 << 16, w1 = c10 | c11 << 16 : elements before the record whose bits at this level and the next are
+//            (t, u) = (0,0), (0,1), (1,0), (1,1)  (node-relative, 16 bits each)
 //   w2..w4 = plane 0: this node's 96 bits
 //   w5..w7 = plane 1: for the SAME 96 positions the bit each element has one level further down, i.e. in the child it
 //            descends to (0 where that child is a leaf)
-// With P = 96q elements before the record, c00 = P - c1 - c01 and c10 = c1 - c11, so the rank of any 2-bit code prefix
-// (t,u) is ONE fetch and one masked-popcount pass over (plane0 ^ ~T) & (plane1 ^ ~U): a rank / inverseSelect takes one
-// record per TWO tree levels.  (v1 kept one 224-bit level per 32-byte sector: one DRAM access per level, and the popcount
-// passes over 7 words made the two-level variant of that format ALU-bound — profiles/experiments.)
+// The rank of any 2-bit code prefix (t, u) is ONE fetch, one 16-bit field and one masked-popcount pass over
+// (plane0 ^ ~T) & (plane1 ^ ~U): a rank / inverseSelect takes one record per TWO tree levels.  A code that ends at the
+// record's first level is the case u = 0 (plane 1 is 0 for elements that go to a leaf child), so there is no special case.
+// (v1 kept one 224-bit level per 32-byte sector: one DRAM access per level, and the popcount passes over 7 words made the
+// two-level variant of that format ALU-bound — profiles/experiments.)
 // Every node starts on a fresh record, so the counters are node-relative (nodes hold <= 65536 elements).
 
 // --- block descriptor (LF / inverseSelect entry, :1305-1537):

@@ -93,6 +93,7 @@ def native():
         L.fmgpu_last_stats.argtypes = [vp, vp]
         L.fmgpu_last_stats_ex.argtypes = [vp, vp, C.c_uint32]
         L.fmgpu_set_timing.argtypes = [vp, i32]
+        L.fmgpu_set_stats.argtypes = [vp, i32]
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         _lib = L
     return _lib
@@ -186,6 +187,10 @@ class FmIndex:
         names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "level_records",
                  "spec_root_wasted"]
         return {k: int(v) for k, v in zip(names, out)}
+
+    def set_stats(self, enable: bool = True):
+        """Work counters of the kernels (``last_stats``) on/off; off by default (production kernels carry none)."""
+        self._check(self._lib.fmgpu_set_stats(self._h, int(enable)))
 
     def set_timing(self, enable: bool = True):
         self._check(self._lib.fmgpu_set_timing(self._h, int(enable)))

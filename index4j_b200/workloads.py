@@ -22,6 +22,17 @@ def _timed(fn, steps: int, warmup: int) -> float:
     return e0.elapsed_time(e1) / steps
 
 
+def _counted(ix, fn) -> dict:
+    """Work counters of one extra, untimed pass with the instrumented kernels (the timed passes run the production ones)."""
+    ix.set_stats(True)
+    try:
+        fn()
+        torch.cuda.synchronize()
+        return ix.last_stats()
+    finally:
+        ix.set_stats(False)
+
+
 def locate_workload(ix, d_chars, d_off, max_hits: int, steps: int, warmup: int):
     """FmIndex.locate over the whole batch (count kernels + hit scan + LF walks).  -> (stats dict, d_hit_off, d_pos)"""
     dev = d_chars.device
@@ -31,8 +42,9 @@ def locate_workload(ix, d_chars, d_off, max_hits: int, steps: int, warmup: int):
     d_status = torch.empty(n_pat, dtype=torch.int32, device=dev)
     total = ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, None, d_status)  # sizing pass
     d_pos = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-    ms = _timed(lambda: ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, d_pos, d_status), steps, warmup)
-    st = ix.last_stats()
+    fn = lambda: ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, d_pos, d_status)  # noqa: E731
+    ms = _timed(fn, steps, warmup)
+    st = _counted(ix, fn)
     # algorithmic 32-byte records: per sampled-row test 1 group record; per LF step 1 block descriptor; per TWO wavelet levels
     # 1 level record + 1 node record; per generic rank 1 cell; per hit 1 SA record
     recs = st["sampled_tests"] + st["lf_steps"] + 2 * st["level_records"] + st["ranks"] + total
@@ -50,8 +62,9 @@ def eub_workload(ix, d_from, dst_len: int, steps: int, warmup: int, boundary="\n
     d_arena = torch.empty((n, dst_len), dtype=torch.int16, device=dev)
     d_len = torch.empty(n, dtype=torch.int32, device=dev)
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
-    ms = _timed(lambda: ix.extract_until_boundary_batch_device(d_from, boundary, dst_len, mode, d_arena, d_len, d_st), steps, warmup)
-    st = ix.last_stats()
+    fn = lambda: ix.extract_until_boundary_batch_device(d_from, boundary, dst_len, mode, d_arena, d_len, d_st)  # noqa: E731
+    ms = _timed(fn, steps, warmup)
+    st = _counted(ix, fn)
     ok_chars = int(d_len[d_st == 0].sum().item())
     out = {"records": n, "dst_len": dst_len, "ms_per_step": ms, "records_per_s": n / (ms / 1e3), "chars": ok_chars,
            "chars_per_s": ok_chars / (ms / 1e3), "status_nonzero": int((d_st != 0).sum().item()), "lf_steps": st["lf_steps"],
@@ -71,8 +84,9 @@ def extract_workload(ix, n_text: int, n_ext: int, chars_each: int, steps: int, w
     d_arena = torch.empty(n_ext * chars_each, dtype=torch.int16, device=dev)
     d_len = torch.empty(n_ext, dtype=torch.int32, device=dev)
     d_st = torch.empty(n_ext, dtype=torch.int32, device=dev)
-    ms = _timed(lambda: ix.extract_batch_device(d_start, d_stop, d_arena, d_aoff, d_len, d_st), steps, warmup)
-    st = ix.last_stats()
+    fn = lambda: ix.extract_batch_device(d_start, d_stop, d_arena, d_aoff, d_len, d_st)  # noqa: E731
+    ms = _timed(fn, steps, warmup)
+    st = _counted(ix, fn)
     out = {"ranges": n_ext, "chars_each": chars_each, "ms_per_step": ms, "ranges_per_s": n_ext / (ms / 1e3),
            "chars_per_s": float(chars_each) * n_ext / (ms / 1e3), "lf_steps": st["lf_steps"], "lf_steps_per_s": st["lf_steps"] / (ms / 1e3)}
     return out, start, stop, d_arena

@@ -155,7 +155,7 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
                         break;
                     }
                     uint32_t a = sp, b = ep;
-                    if (count_step(h.ix, h.CT, c, &a, &b, true, cnt)) {
+                    if (count_step<true>(h.ix, h.CT, c, &a, &b, true, cnt)) {
                         st = 9;
                         break;
                     }
@@ -381,4 +381,129 @@ extern "C" void fc_lockstep_sim(void* hv, const uint16_t* chars, const uint64_t*
     out8[3] = sum_levels;
     out8[4] = diff_steps;
     for (int k = 0; k < 16; ++k) out8[8 + k] = hist[k];
+}
+
+// ---- design aid (not a test): structure of the lockstep backward search over a length-ordered batch.
+// out[0] warp steps, [1] lane steps, [2] sum over warp steps of the deepest lane's record count, [3] single-row lane steps
+// (end - start == 1, same block), [4] warp steps whose active lanes are ALL single-row, [5] split lane steps (two blocks),
+// [6] lane steps with both positions in one root record, [7] sum of per-lane record counts (track B),
+// [16..31] histogram of per-lane records (track B), [32..47] histogram of the per-warp-step maximum,
+// [64..127] single-row lane steps by step index, [128..191] lane steps by step index, [192..255] all-single warp steps by step index,
+// [256..319] warp steps by step index
+extern "C" void fc_warp_sim2(void* hv, const uint16_t* chars, const uint64_t* pat_off, const uint32_t* order, uint32_t n_pat, uint64_t* out) {
+    FC& h = *(FC*)hv;
+    for (int k = 0; k < 320; ++k) out[k] = 0;
+    for (uint32_t g = 0; g < n_pat; g += 32) {
+        const uint32_t m = std::min<uint32_t>(32, n_pat - g);
+        uint32_t sp[32], ep[32];
+        int64_t i[32];
+        bool alive[32];
+        int64_t maxlen = 0;
+        for (uint32_t l = 0; l < m; ++l) {
+            const uint32_t p = order[g + l];
+            const uint64_t a = pat_off[p], b = pat_off[p + 1];
+            i[l] = (int64_t)(b - a) - 1;
+            alive[l] = i[l] >= 0;
+            if (alive[l]) {
+                const uint32_t c = h.ix.char2code[chars[b - 1]];
+                if (!c) alive[l] = false;
+                else {
+                    sp[l] = h.ix.C[c];
+                    ep[l] = h.ix.C[c + 1];
+                }
+            }
+            maxlen = std::max<int64_t>(maxlen, i[l]);
+        }
+        for (int64_t s = 0; s < maxlen; ++s) {
+            uint32_t mx = 0, n_act = 0, n_single = 0;
+            const int sk = (int)std::min<int64_t>(s, 63);
+            for (uint32_t l = 0; l < m; ++l) {
+                if (!alive[l]) continue;
+                if (!(sp[l] < ep[l] && i[l] >= 1)) {
+                    alive[l] = false;
+                    continue;
+                }
+                const uint32_t p = order[g + l];
+                const uint32_t c = h.ix.char2code[chars[pat_off[p] + (uint64_t)(--i[l])]];
+                if (!c) {
+                    alive[l] = false;
+                    continue;
+                }
+                ++n_act;
+                const SbDesc da = h.T.sb[sp[l] >> SB_LOG], db = h.T.sb[ep[l] >> SB_LOG];
+                const uint32_t blk_a = da.first_block + ((sp[l] & SB_MASK) >> da.block_log);
+                const uint32_t blk_b = db.first_block + ((ep[l] & SB_MASK) >> db.block_log);
+                const bool same_blk = blk_a == blk_b || sp[l] == 0;
+                const bool single = ep[l] - sp[l] == 1 && blk_a == blk_b;
+                uint64_t r1 = 0, l1 = 0, r2 = 0, l2 = 0;
+                uint32_t a = 0, b = 0;
+                host_rank(h, sp[l], c, &a, &r1, &l1);
+                host_rank(h, ep[l], c, &b, &r2, &l2);
+                const uint32_t pb = (uint32_t)((l2 + 1) / 2), pa = (uint32_t)((l1 + 1) / 2);
+                mx = std::max(mx, std::max(pa, pb));
+                out[7] += pb;
+                out[16 + std::min<uint32_t>(15, pb)]++;
+                if (single) {
+                    ++n_single;
+                    out[3]++;
+                    out[64 + sk]++;
+                }
+                if (!same_blk) out[5]++;
+                if (same_blk && sp[l] != 0 &&
+                    (sp[l] & ((1u << da.block_log) - 1u)) / SECTOR_BITS == (ep[l] & ((1u << db.block_log) - 1u)) / SECTOR_BITS)
+                    out[6]++;
+                out[1]++;
+                out[128 + sk]++;
+                sp[l] = h.ix.C[c] + a;
+                ep[l] = h.ix.C[c] + b;
+            }
+            if (!n_act) break;
+            out[0]++;
+            out[2] += mx;
+            out[32 + std::min<uint32_t>(15, mx)]++;
+            out[256 + sk]++;
+            if (n_single == n_act) {
+                out[4]++;
+                out[192 + sk]++;
+            }
+        }
+    }
+}
+
+// ---- design aid: for every rank query of the backward search (track B of each lane step), the record count of its walk
+// and how often the symbol occurs in its block: out[pairs * 8 + bucket], buckets <=10, <=26, <=42, <=100, <=1000, more;
+// out[64 + blockSizeLog] = lane steps by block size
+extern "C" void fc_sparse_sim(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, uint64_t* out) {
+    FC& h = *(FC*)hv;
+    for (int k = 0; k < 96; ++k) out[k] = 0;
+    for (uint32_t p = 0; p < n_pat; ++p) {
+        const uint64_t a0 = pat_off[p], b0 = pat_off[p + 1];
+        if (b0 <= a0) continue;
+        int64_t i = (int64_t)(b0 - a0) - 1;
+        uint32_t c = h.ix.char2code[chars[b0 - 1]];
+        if (!c) continue;
+        uint32_t sp = h.ix.C[c], ep = h.ix.C[c + 1];
+        while (sp < ep && i >= 1) {
+            c = h.ix.char2code[chars[a0 + (uint64_t)(--i)]];
+            if (!c) break;
+            uint64_t r1 = 0, l1 = 0, r2 = 0, l2 = 0;
+            uint32_t a = 0, b = 0;
+            host_rank(h, sp, c, &a, &r1, &l1);
+            host_rank(h, ep, c, &b, &r2, &l2);
+            const SbDesc db = h.T.sb[ep >> SB_LOG];
+            const uint32_t lo = ep & ~((1u << db.block_log) - 1u);
+            uint32_t hi = lo + (1u << db.block_log);
+            if (hi > h.ix.length) hi = h.ix.length;
+            uint32_t x0 = 0, x1 = 0;
+            uint64_t d0 = 0, d1 = 0;
+            host_rank(h, lo, c, &x0, &d0, &d1);
+            host_rank(h, hi, c, &x1, &d0, &d1);
+            const uint32_t occ = x1 - x0;
+            const int bucket = occ <= 10 ? 0 : occ <= 26 ? 1 : occ <= 42 ? 2 : occ <= 100 ? 3 : occ <= 1000 ? 4 : 5;
+            out[std::min<uint64_t>(7, (l2 + 1) / 2) * 8 + bucket]++;
+            out[64 + db.block_log]++;
+            sp = h.ix.C[c] + a;
+            ep = h.ix.C[c] + b;
+        }
+    }
 }

@@ -35,10 +35,16 @@ def test_count_matches_oracle(gpu_indexes, name):
     assert g.getAlphabetLength() == case.oracle.getAlphabetLength()
     chars, off = make_patterns(case.text, 6000, 1, 48, seed=11)
     want, want_st = case.oracle.count_batch(chars, off, threads=4)
-    got, got_st = g.count_batch(chars, off, return_status=True)
+    got, got_st = g.count_batch(chars, off, return_status=True)  # production kernel (no work counters)
     assert np.array_equal(got_st, want_st)
     assert np.array_equal(got, want)
     assert int((want > 0).sum()) > 1000
+    g.set_stats(True)
+    try:
+        got, got_st = g.count_batch(chars, off, return_status=True)
+    finally:
+        g.set_stats(False)
+    assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
     # work counters agree with the oracle's instrumentation
     case.oracle.stats(reset=True)
     case.oracle.count_batch(chars, off, threads=1)
@@ -84,7 +90,14 @@ def test_locate_matches_oracle(gpu_indexes, name, max_hits):
     for i in range(want_n.size):
         a = pos[int(hit_off[i]): int(hit_off[i + 1])]
         assert np.array_equal(a, want_pos[i, : want_n[i]]), (i, a[:5], want_pos[i, :5])  # same order as Java fills its array
-    assert g.last_stats()["lf_steps"] > 0 or case.sample_rate == 1
+    # the instrumented kernels give the same answer and count their LF steps
+    g.set_stats(True)
+    try:
+        n2, off2, pos2, st2 = g.locate_batch(chars, off, max_hits)
+        assert g.last_stats()["lf_steps"] > 0 or case.sample_rate == 1
+    finally:
+        g.set_stats(False)
+    assert np.array_equal(n2, n_hits) and np.array_equal(pos2, pos) and np.array_equal(st2, st)
 
 
 def test_locate_single_query_api(gpu_indexes):

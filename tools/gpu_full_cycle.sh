@@ -21,7 +21,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file
 ncu --set full --clock-control none --import-source on -k regex:k_count -s 3 -c 1 -f -o gpurun_out/${TAG}_k_count \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-lf > /dev/null 2> gpurun_out/${TAG}_ncu2.log
 tail -2 gpurun_out/${TAG}_ncu2.log
-ncu --set full --clock-control none --import-source on -k regex:"k_locate|k_extract" -c 3 -f -o gpurun_out/${TAG}_k_lf \
+ncu --set full --clock-control none --import-source on -k regex:"k_locate|k_extract" -c 6 -f -o gpurun_out/${TAG}_k_lf \
     python tools/bench_lf.py --steps 1 --warmup 0 --check 0 --n-pat 200000 --n-eub 200000 --n-ext 200000 > /dev/null 2> gpurun_out/${TAG}_ncu3.log
 tail -2 gpurun_out/${TAG}_ncu3.log
 ls -la gpurun_out
