@@ -340,6 +340,23 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(h_counts, d_counts.cpu().numpy())
 
+    # the same batch as UTF-8 byte patterns through fmgpu_count_batch_utf8 (the reference's convertBytePatternToCharPattern +
+    # count, FmIndex.java:239-298): 1 byte per char crosses PCIe, decoding happens in the device pre-pass
+    utf8 = None
+    if int(chars.max(initial=0)) < 128:
+        p_bytes = torch.from_numpy(chars.astype(np.uint8)).pin_memory()
+        h_bytes = p_bytes.numpy()
+        p_counts8 = torch.empty(n_pat, dtype=torch.int32).pin_memory()
+        h_counts8 = p_counts8.numpy()
+        for _ in range(2):
+            ix.count_batch_utf8_into(h_bytes, h_off, h_counts8, h_status)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ix.count_batch_utf8_into(h_bytes, h_off, h_counts8, h_status)
+        utf8 = {"s": time.perf_counter() - t0, "h2d": int(h_bytes.nbytes + off.nbytes)}
+        assert np.array_equal(h_counts8, h_counts)
+
     # second half of the metric: located hits/s (BASELINE.json configs[2]) and extractUntilBoundary of located hits
     # (configs[3]); same patterns, device-resident, timed with CUDA events; max over ranks, hits summed over ranks
     lf = None
@@ -366,13 +383,14 @@ def main():
               "d_hit_off": d_hit_off, "d_pos": d_pos, "h2d": int(chars.nbytes + off.nbytes), "d2h": int(p_nh.nbytes + p_ho.nbytes + p_pos.nbytes + h_status.nbytes)}
 
     times = torch.tensor([ms_total, e2e_s * 1e3, statistics.mean(kernel_ms), lf["loc"]["ms_per_step"] if lf else 0.0,
-                          lf["eub"]["ms_per_step"] if lf else 0.0, lf["loc_e2e_ms"] if lf else 0.0], dtype=torch.float64, device=dev)
+                          lf["eub"]["ms_per_step"] if lf else 0.0, lf["loc_e2e_ms"] if lf else 0.0, utf8["s"] * 1e3 if utf8 else 0.0],
+                         dtype=torch.float64, device=dev)
     sums = torch.tensor([lf["loc"]["hits"] if lf else 0, lf["eub"]["records"] if lf else 0, lf["eub"]["chars"] if lf else 0,
                          lf["loc"]["lf_steps"] if lf else 0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, kern_ms, loc_ms, eub_ms, loc_e2e_ms = [float(x) for x in times.cpu()]
+    ms_total, e2e_ms, kern_ms, loc_ms, eub_ms, loc_e2e_ms, utf8_ms = [float(x) for x in times.cpu()]
     all_hits, all_records, all_chars, all_lf_steps = [float(x) for x in sums.cpu()]
 
     if rank == 0:
@@ -389,6 +407,10 @@ def main():
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(chars.nbytes + off.nbytes),
                     "d2h_bytes_per_step": int(h_counts.nbytes + h_status.nbytes)},
+            "e2e_utf8": ({"value": world * n_pat * args.steps / (utf8_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": utf8["h2d"],
+                          "d2h_bytes_per_step": int(h_counts.nbytes + h_status.nbytes),
+                          "call": "fmgpu_count_batch_utf8: the same patterns as UTF-8 bytes (1 byte per char), decoded on the device"}
+                         if utf8 else None),
             "gpu_launches": int(stats["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,

@@ -45,6 +45,7 @@ extern "C" {
 #define FMGPU_ST_DST_ZERO 6       /* IllegalArgumentException("Supplied destination for extraction has size zero") FM:623 */
 #define FMGPU_ST_NO_BOUNDARY 7    /* IllegalArgumentException("Boundary does not exist")           FM:659,792,849 */
 #define FMGPU_ST_DOES_NOT_FIT 8   /* RuntimeException("Extraction does not fit in the supplied destination. Currently extracted: N") FM:733,817,894; N in len_out */
+#define FMGPU_ST_CHAR_EXCEEDS 10  /* RuntimeException("Found a character that exceeds (32767): it was N") FM:261-267 (UTF-8 entry points; N in counts_out) */
 #define FMGPU_ST_INDEX_OOB 9      /* ArrayIndexOutOfBoundsException (empty pattern FM:456; rank(size,.) on a superblock boundary, wavelet/WaveletFixedBlockBoosting.java:1022-1026) */
 
 #define FMGPU_MODE_BOTH 0  /* FmIndex.extractUntilBoundary       FM:640 */
@@ -85,6 +86,20 @@ int fmgpu_count_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* p
                       int32_t* counts_out, int32_t* status_out);
 int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars,
                              uint32_t n_pat, int32_t* d_counts_out, int32_t* d_status_out, void* cuda_stream);
+
+/* UTF-8 byte patterns: FmIndex.convertBytePatternToCharPattern(byte[] p, 0, p.length, dst) FM:239-298 followed by
+ * count(dst, 0, n) / locate(dst, 0, n, ...).  Pattern i is the byte[] bytes[pat_off[i], pat_off[i+1]) — pat_off are BYTE
+ * offsets.  The bytes (1 per char for ASCII / Latin-1 logs instead of the 2 of a char[]) cross PCIe and are decoded on
+ * the device with the reference's branch structure.  Status FMGPU_ST_CHAR_EXCEEDS (offending code point in counts_out)
+ * where the converter throws; FMGPU_ST_INDEX_OOB where a multi-byte sequence runs past the end of its byte[]
+ * (ArrayIndexOutOfBoundsException) and, as for char[] patterns, for an empty pattern. */
+int fmgpu_count_batch_utf8(fmgpu_index* idx, const uint8_t* bytes, const uint64_t* pat_off, uint32_t n_pat,
+                           int32_t* counts_out, int32_t* status_out);
+int fmgpu_count_batch_utf8_device(fmgpu_index* idx, const uint8_t* d_bytes, const uint64_t* d_pat_off, uint64_t total_bytes,
+                                  uint32_t n_pat, int32_t* d_counts_out, int32_t* d_status_out, void* cuda_stream);
+int fmgpu_locate_batch_utf8(fmgpu_index* idx, const uint8_t* bytes, const uint64_t* pat_off, uint32_t n_pat, int32_t max_hits,
+                            int32_t* n_hits_out, uint64_t* hit_off_out, int32_t* positions_out, uint64_t positions_cap,
+                            int32_t* status_out);
 
 /* FmIndex.locate(char[] p, int off, int len, int[] out, int max)  FM:504-552.
  * max_hits <= 0 means unlimited (FM:544).  Hits of pattern i are written to

@@ -17,6 +17,7 @@
 #include "kernels.cuh"
 #include "kernels_lf.cuh"
 #include "kernels_locate.cuh"
+#include "kernels_utf8.cuh"
 #include "layout.h"
 
 using namespace fmgpu;
@@ -91,14 +92,18 @@ struct fmgpu_index {
     cudaStream_t stream = nullptr, copy_stream = nullptr, down_stream = nullptr;
     static constexpr int PIPE_SLOTS = 8;
     cudaEvent_t pipe_in[PIPE_SLOTS] = {nullptr}, pipe_out[PIPE_SLOTS] = {nullptr};
-    Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b, order, bins;
+    Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b, order, bins, u8conv;
     // The host-pointer count call runs its chunks on COUNT_CTX compute streams round-robin, each with its own scratch set,
     // so that the kernel of chunk k+1 fills the SMs as the longest patterns of chunk k drain (context 0 = the members above).
-    static constexpr int COUNT_CTX = 3;
+    static constexpr int COUNT_CTX = 4;
     struct CountCtx {
         Scratch pats, ctrl, order, bins;
     } cctx[COUNT_CTX - 1];
     cudaStream_t cstream[COUNT_CTX - 1] = {nullptr};
+    // High-priority streams for the pre-pass kernels of a chunk (descriptors + length sort): they must not queue behind the
+    // backward-search CTAs of earlier chunks, or the next search launch is late and the SMs drain.
+    cudaStream_t pstream[COUNT_CTX] = {nullptr};
+    cudaEvent_t pre_done[PIPE_SLOTS] = {nullptr};
     uint64_t last_launches = 0;
     bool stats_valid = false;
     bool count_stats = false;  // fmgpu_set_stats: backward-search kernel with work counters
@@ -141,11 +146,22 @@ int prepass_grid(uint64_t items, int sm_count) {
     return (int)g;
 }
 
+// UTF-8 byte patterns: the pre-pass decodes d_bytes[pat_off[i], pat_off[i+1]) into d_chars at the same offsets (kernels_utf8.cuh)
+struct Utf8Src {
+    const uint8_t* d_bytes;
+    uint16_t* d_chars;
+    int32_t* d_conv_status;  // per pattern of this call: status of the conversion (0, 9, 10) ...
+    int32_t* d_conv_value;   // ... and the offending code point
+};
+
 // Backward search over n_pat patterns on stream `st`.  `first_of_call` resets the work counters; later
 // chunks of the same call only re-arm the work queue.
 int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars, uint32_t n_pat,
-                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st, bool first_of_call = true, int ctx = 0) {
+                    int32_t* d_counts, int32_t* d_status, uint32_t* d_ranges, cudaStream_t st, bool first_of_call = true, int ctx = 0,
+                    const Utf8Src* u8 = nullptr, cudaStream_t pre = nullptr, cudaEvent_t pre_ev = nullptr, int threads = CTA_THREADS) {
+    // `pre` (optional): stream for the pre-pass kernels, joined into `st` through pre_ev before the search kernel
     (void)total_chars;
+    if (u8) d_chars = u8->d_chars;
     Scratch& s_pats = ctx ? ix->cctx[ctx - 1].pats : ix->pats;
     Scratch& s_ctrl = ctx ? ix->cctx[ctx - 1].ctrl : ix->ctrl;
     Scratch& s_order = ctx ? ix->cctx[ctx - 1].order : ix->order;
@@ -154,8 +170,9 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
     CU(s_ctrl.reserve(CTRL_WORDS * 4));
     CU(s_order.reserve((size_t)n_pat * 4 + 64));
     CU(s_bins.reserve(LEN_BINS * 4));
+    if (!pre) pre = st;
     if (first_of_call) {
-        CU(cudaMemsetAsync(s_ctrl.p, 0, CTRL_WORDS * 4, st));
+        CU(cudaMemsetAsync(s_ctrl.p, 0, CTRL_WORDS * 4, pre));
         if (ctx == 0) {
             ix->last_launches = 0;
             ix->stats_valid = true;
@@ -164,28 +181,42 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
             ix->stats_ctx_mask |= 1u << ctx;
         }
     } else {
-        CU(cudaMemsetAsync(s_ctrl.p, 0, 8, st));  // the two queue heads
+        CU(cudaMemsetAsync(s_ctrl.p, 0, 8, pre));  // the two queue heads
     }
-    if (n_pat == 0) return 0;
-    CU(cudaMemsetAsync(s_bins.p, 0, LEN_BINS * 4, st));
+    if (n_pat == 0) {
+        if (pre != st) {
+            CU(cudaEventRecord(pre_ev, pre));
+            CU(cudaStreamWaitEvent(st, pre_ev, 0));
+        }
+        return 0;
+    }
+    CU(cudaMemsetAsync(s_bins.p, 0, LEN_BINS * 4, pre));
     unsigned int* ctrl = (unsigned int*)s_ctrl.p;
     // descriptors + length histogram, then a counting sort by length so that a warp's 32 patterns run in lockstep
     const int pre_grid = prepass_grid(n_pat, ix->sm_count);
-    k_prepass<<<pre_grid, 256, 0, st>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)s_pats.p, (uint32_t*)s_bins.p);
-    k_len_scan<<<1, LEN_BINS, 0, st>>>((uint32_t*)s_bins.p);
+    if (u8)
+        k_prepass_utf8<<<pre_grid, 256, 0, pre>>>(u8->d_bytes, d_pat_off, n_pat, ix->dev.char2code, u8->d_chars, (PatDesc*)s_pats.p,
+                                                 (uint32_t*)s_bins.p, u8->d_conv_status, u8->d_conv_value);
+    else
+        k_prepass<<<pre_grid, 256, 0, pre>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)s_pats.p, (uint32_t*)s_bins.p);
+    k_len_scan<<<1, SCAN_THREADS, 0, pre>>>((uint32_t*)s_bins.p);
     const int sc_grid = prepass_grid(((uint64_t)n_pat + SCATTER_PER_THREAD - 1) / SCATTER_PER_THREAD, ix->sm_count);
-    k_len_scatter<<<sc_grid, 256, 0, st>>>((const PatDesc*)s_pats.p, n_pat, (uint32_t*)s_bins.p, (uint32_t*)s_order.p);
+    k_len_scatter<<<sc_grid, 256, 0, pre>>>((const PatDesc*)s_pats.p, n_pat, (uint32_t*)s_bins.p, (uint32_t*)s_order.p);
+    if (pre != st) {
+        CU(cudaEventRecord(pre_ev, pre));
+        CU(cudaStreamWaitEvent(st, pre_ev, 0));
+    }
     const int slot = (int)(ix->timed_calls % fmgpu_index::TIMING_SLOTS);
     if (ix->timing) CU(cudaEventRecord(ix->ev0[slot], st));
     int grid = ix->count_ctas;
-    const int need = (int)(((uint64_t)n_pat + CTA_THREADS - 1) / CTA_THREADS);
+    const int need = (int)(((uint64_t)n_pat + threads - 1) / threads);
     if (need < grid) grid = need;
     if (ix->count_stats)
-        k_count<true><<<grid, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
+        k_count<true><<<grid, threads, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
                                                                   d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
                                                                   (unsigned long long*)(ctrl + CTRL_STATS));
     else
-        k_count<false><<<grid, CTA_THREADS, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
+        k_count<false><<<grid, threads, ix->tables_smem, st>>>(ix->dev, d_chars, (const PatDesc*)s_pats.p, (const uint32_t*)s_order.p, n_pat,
                                                                    d_counts, d_status, d_ranges, ctrl + CTRL_QUEUE,
                                                                    (unsigned long long*)(ctrl + CTRL_STATS));
     if (ix->timing) {
@@ -193,6 +224,10 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
         ix->timed_calls++;
     }
     ix->last_launches += 4;
+    if (u8) {  // a pattern whose conversion throws never reaches the search in the reference: its status wins
+        k_utf8_merge<<<(n_pat + 255) / 256, 256, 0, st>>>(u8->d_conv_status, u8->d_conv_value, n_pat, d_counts, d_status, d_ranges ? 0 : 1);
+        ix->last_launches += 1;
+    }
     CU(cudaGetLastError());
     return 0;
 }
@@ -287,8 +322,16 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
         rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreate failed");
     for (int i = 0; !rc && i < fmgpu_index::COUNT_CTX - 1; ++i)
         if (cudaStreamCreateWithFlags(&ix->cstream[i], cudaStreamNonBlocking) != cudaSuccess) rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreate failed");
+    if (!rc) {
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // numerically lower = higher priority
+        for (int i = 0; !rc && i < fmgpu_index::COUNT_CTX; ++i)
+            if (cudaStreamCreateWithPriority(&ix->pstream[i], cudaStreamNonBlocking, prio_hi) != cudaSuccess)
+                rc = fail(FMGPU_ERR_CUDA, "cudaStreamCreateWithPriority failed");
+    }
     for (int i = 0; !rc && i < fmgpu_index::PIPE_SLOTS; ++i)
         if (cudaEventCreateWithFlags(&ix->pipe_in[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ix->pre_done[i], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ix->pipe_out[i], cudaEventDisableTiming) != cudaSuccess)
             rc = fail(FMGPU_ERR_CUDA, "cudaEventCreate failed");
     if (!rc) {
@@ -309,18 +352,21 @@ void fmgpu_index_free(fmgpu_index* ix) {
     DeviceGuard g(ix->device);
     for (void* p : ix->allocs) cudaFree(p);
     for (Scratch* s : {&ix->codes, &ix->pats, &ix->ctrl, &ix->ranges, &ix->in_a, &ix->in_b, &ix->out_a, &ix->out_b, &ix->out_c,
-                       &ix->tmp_a, &ix->tmp_b, &ix->order, &ix->bins})
+                       &ix->tmp_a, &ix->tmp_b, &ix->order, &ix->bins, &ix->u8conv})
         s->release();
     for (int i = 0; i < fmgpu_index::COUNT_CTX - 1; ++i) {
         for (Scratch* sc : {&ix->cctx[i].pats, &ix->cctx[i].ctrl, &ix->cctx[i].order, &ix->cctx[i].bins}) sc->release();
         if (ix->cstream[i]) cudaStreamDestroy(ix->cstream[i]);
     }
+    for (int i = 0; i < fmgpu_index::COUNT_CTX; ++i)
+        if (ix->pstream[i]) cudaStreamDestroy(ix->pstream[i]);
     if (ix->stream) cudaStreamDestroy(ix->stream);
     if (ix->copy_stream) cudaStreamDestroy(ix->copy_stream);
     if (ix->down_stream) cudaStreamDestroy(ix->down_stream);
     for (int i = 0; i < fmgpu_index::PIPE_SLOTS; ++i) {
         if (ix->pipe_in[i]) cudaEventDestroy(ix->pipe_in[i]);
         if (ix->pipe_out[i]) cudaEventDestroy(ix->pipe_out[i]);
+        if (ix->pre_done[i]) cudaEventDestroy(ix->pre_done[i]);
     }
     for (int i = 0; i < fmgpu_index::TIMING_SLOTS; ++i) {
         if (ix->ev0[i]) cudaEventDestroy(ix->ev0[i]);
@@ -348,11 +394,13 @@ int fmgpu_count_batch_device(fmgpu_index* ix, const uint16_t* d_chars, const uin
     return count_on_stream(ix, d_chars, d_pat_off, total_chars, n_pat, d_counts_out, d_status_out, nullptr, (cudaStream_t)cuda_stream);
 }
 
-int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts_out,
-                      int32_t* status_out) {
+namespace {
+// Host-pointer count call for char[] patterns (unit 2) or UTF-8 byte patterns (unit 1).
+int count_host(fmgpu_index* ix, const void* in, size_t unit, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts_out, int32_t* status_out) {
     if (!ix || !pat_off || !counts_out) return fail(FMGPU_ERR_ARG, "null argument");
     const uint64_t total = pat_off[n_pat];
-    if (total && !chars) return fail(FMGPU_ERR_ARG, "null argument");
+    if (total && !in) return fail(FMGPU_ERR_ARG, "null argument");
+    const bool utf8 = unit == 1;
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", ix->device);
@@ -361,6 +409,10 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     CU(ix->in_b.reserve(((size_t)n_pat + 1) * 8));
     CU(ix->out_a.reserve((size_t)n_pat * 4 + 64));
     CU(ix->out_b.reserve((size_t)n_pat * 4 + 64));
+    if (utf8) {
+        CU(ix->codes.reserve((size_t)total + 64));
+        CU(ix->u8conv.reserve((size_t)n_pat * 8 + 64));
+    }
     // The batch is cut into chunks: the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlap the kernels of chunk k
     // (copy stream, COUNT_CTX compute streams round-robin, download stream, events in between).  A launch lasts at least as
     // long as its longest pattern's dependent chain (~0.2 ms), so consecutive chunks run on different compute streams and the
@@ -373,37 +425,105 @@ int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pa
     uint32_t n_chunks = n_pat / min_chunk;
     if (n_chunks > (uint32_t)fmgpu_index::PIPE_SLOTS) n_chunks = fmgpu_index::PIPE_SLOTS;
     if (n_chunks < 1) n_chunks = 1;
+    // search CTAs of the chunked call are a little smaller than CTA_THREADS so that two of them leave registers and thread
+    // slots on the SM for the (small) pre-pass CTAs of the next chunks
+    int pipe_threads = n_chunks > 1 ? PIPE_CTA_THREADS : CTA_THREADS;
+    if (const char* e = getenv("FMGPU_PIPE_THREADS")) pipe_threads = atoi(e) >= 32 && atoi(e) <= CTA_THREADS ? (atoi(e) / 32) * 32 : pipe_threads;
     uint16_t* d_chars = (uint16_t*)ix->in_a.p;
+    uint8_t* d_in = utf8 ? (uint8_t*)ix->codes.p : (uint8_t*)ix->in_a.p;
     uint64_t* d_off = (uint64_t*)ix->in_b.p;
     int32_t* d_counts = (int32_t*)ix->out_a.p;
     int32_t* d_status = (int32_t*)ix->out_b.p;
+    const uint8_t* h_in = (const uint8_t*)in;
+    // FMGPU_PIPE_TRACE=1: per-chunk timeline of the call on stderr (timing events; diagnostic only)
+    const bool trace = getenv("FMGPU_PIPE_TRACE") != nullptr;
+    cudaEvent_t t0 = nullptr, t_in[fmgpu_index::PIPE_SLOTS], t_k0[fmgpu_index::PIPE_SLOTS], t_k1[fmgpu_index::PIPE_SLOTS], t_out[fmgpu_index::PIPE_SLOTS];
+    if (trace) {
+        CU(cudaEventCreate(&t0));
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            CU(cudaEventCreate(&t_in[k]));
+            CU(cudaEventCreate(&t_k0[k]));
+            CU(cudaEventCreate(&t_k1[k]));
+            CU(cudaEventCreate(&t_out[k]));
+        }
+        CU(cudaEventRecord(t0, cp));
+    }
     for (uint32_t k = 0; k < n_chunks; ++k) {  // all uploads are queued first: they only depend on the host buffers
         const uint32_t lo = (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
         const uint64_t c0 = pat_off[lo], c1 = pat_off[hi];
-        if (c1 > c0) CU(cudaMemcpyAsync(d_chars + c0, chars + c0, (size_t)(c1 - c0) * 2, cudaMemcpyHostToDevice, cp));
+        if (c1 > c0) CU(cudaMemcpyAsync(d_in + c0 * unit, h_in + c0 * unit, (size_t)(c1 - c0) * unit, cudaMemcpyHostToDevice, cp));
         CU(cudaMemcpyAsync(d_off + lo, pat_off + lo, ((size_t)(hi - lo) + 1) * 8, cudaMemcpyHostToDevice, cp));
         CU(cudaEventRecord(ix->pipe_in[k], cp));
+        if (trace) CU(cudaEventRecord(t_in[k], cp));
     }
     for (uint32_t k = 0; k < n_chunks; ++k) {
         const uint32_t lo = (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
         const int ctx = (int)(k % (uint32_t)n_ctx);
         cudaStream_t cs = ctx ? ix->cstream[ctx - 1] : st;
-        CU(cudaStreamWaitEvent(cs, ix->pipe_in[k], 0));
-        int rc = count_on_stream(ix, d_chars, d_off + lo, total, hi - lo, d_counts + lo, d_status + lo, nullptr, cs, k < (uint32_t)n_ctx, ctx);
+        cudaStream_t ps = ix->pstream[ctx];
+        // the pre-pass of chunk k runs on the context's high-priority stream as soon as the chunk has arrived and the previous
+        // search of this context (chunk k - n_ctx, same scratch buffers) is done
+        CU(cudaStreamWaitEvent(ps, ix->pipe_in[k], 0));
+        if (k >= (uint32_t)n_ctx) CU(cudaStreamWaitEvent(ps, ix->pipe_out[k - n_ctx], 0));
+        Utf8Src u8{d_in, d_chars, (int32_t*)ix->u8conv.p + lo, (int32_t*)ix->u8conv.p + n_pat + lo};
+        if (trace) CU(cudaEventRecord(t_k0[k], ps));
+        int rc = count_on_stream(ix, d_chars, d_off + lo, total, hi - lo, d_counts + lo, d_status + lo, nullptr, cs, k < (uint32_t)n_ctx, ctx,
+                                 utf8 ? &u8 : nullptr, ps, ix->pre_done[k], pipe_threads);
         if (rc) return rc;
         CU(cudaEventRecord(ix->pipe_out[k], cs));
+        if (trace) CU(cudaEventRecord(t_k1[k], cs));
         CU(cudaStreamWaitEvent(ix->down_stream, ix->pipe_out[k], 0));
         if (hi > lo) {
             CU(cudaMemcpyAsync(counts_out + lo, d_counts + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ix->down_stream));
             if (status_out)
                 CU(cudaMemcpyAsync(status_out + lo, d_status + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, ix->down_stream));
         }
+        if (trace) CU(cudaEventRecord(t_out[k], ix->down_stream));
     }
     CU(cudaStreamSynchronize(ix->down_stream));
     CU(cudaStreamSynchronize(cp));
     CU(cudaStreamSynchronize(st));
     for (int i = 0; i < fmgpu_index::COUNT_CTX - 1; ++i) CU(cudaStreamSynchronize(ix->cstream[i]));
+    for (int i = 0; i < fmgpu_index::COUNT_CTX; ++i) CU(cudaStreamSynchronize(ix->pstream[i]));
+    if (trace) {
+        for (uint32_t k = 0; k < n_chunks; ++k) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, t0, t_in[k]);
+            cudaEventElapsedTime(&b, t0, t_k0[k]);
+            cudaEventElapsedTime(&c, t0, t_k1[k]);
+            cudaEventElapsedTime(&d, t0, t_out[k]);
+            fprintf(stderr, "[fmgpu trace] chunk %u: h2d done %.3f ms, kernels %.3f .. %.3f ms, d2h done %.3f ms\n", k, a, b, c, d);
+            cudaEventDestroy(t_in[k]);
+            cudaEventDestroy(t_k0[k]);
+            cudaEventDestroy(t_k1[k]);
+            cudaEventDestroy(t_out[k]);
+        }
+        cudaEventDestroy(t0);
+    }
     return 0;
+}
+}  // namespace
+
+int fmgpu_count_batch(fmgpu_index* ix, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts_out,
+                      int32_t* status_out) {
+    return count_host(ix, chars, 2, pat_off, n_pat, counts_out, status_out);
+}
+
+int fmgpu_count_batch_utf8(fmgpu_index* ix, const uint8_t* bytes, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts_out,
+                           int32_t* status_out) {
+    return count_host(ix, bytes, 1, pat_off, n_pat, counts_out, status_out);
+}
+
+int fmgpu_count_batch_utf8_device(fmgpu_index* ix, const uint8_t* d_bytes, const uint64_t* d_pat_off, uint64_t total_bytes, uint32_t n_pat,
+                                  int32_t* d_counts_out, int32_t* d_status_out, void* cuda_stream) {
+    if (!ix || !d_pat_off || !d_counts_out || (!d_bytes && total_bytes)) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", ix->device);
+    CU(ix->in_a.reserve((size_t)total_bytes * 2 + 64));
+    CU(ix->u8conv.reserve((size_t)n_pat * 8 + 64));
+    Utf8Src u8{d_bytes, (uint16_t*)ix->in_a.p, (int32_t*)ix->u8conv.p, (int32_t*)ix->u8conv.p + n_pat};
+    return count_on_stream(ix, nullptr, d_pat_off, total_bytes, n_pat, d_counts_out, d_status_out, nullptr, (cudaStream_t)cuda_stream, true, 0, &u8);
 }
 
 int fmgpu_set_stats(fmgpu_index* ix, int enable) {

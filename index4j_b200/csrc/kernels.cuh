@@ -22,6 +22,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #define COUNT_THREADS 512
 #endif
 constexpr int CTA_THREADS = COUNT_THREADS;
+constexpr int PIPE_CTA_THREADS = COUNT_THREADS >= 128 ? COUNT_THREADS - 64 : COUNT_THREADS;  // chunked host call (fmgpu.cu)
 constexpr uint32_t SMEM_C_MAX = 4096;   // entries of C kept in shared memory
 constexpr uint32_t SMEM_SB_MAX = 2048;  // superblock descriptors kept in shared memory
 
@@ -81,25 +82,39 @@ __global__ void __launch_bounds__(256) k_prepass(const uint16_t* __restrict__ ch
     for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x)
         if (h[i]) atomicAdd(&bins[i], h[i]);
 }
-// exclusive scan of the bins, longest patterns first (they are the long poles of the launch)
-__global__ void __launch_bounds__(LEN_BINS) k_len_scan(uint32_t* __restrict__ bins) {
-    __shared__ uint32_t s[LEN_BINS];
+// exclusive scan of the bins, longest patterns first (they are the long poles of the launch).  256 threads x 4 bins: small
+// enough to share an SM with resident k_count CTAs of an earlier chunk (the chunked host call overlaps launches).
+constexpr uint32_t SCAN_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_THREADS) k_len_scan(uint32_t* __restrict__ bins) {
+    static_assert(LEN_BINS == 4 * SCAN_THREADS, "k_len_scan handles four bins per thread");
+    __shared__ uint32_t s[SCAN_THREADS];
     const uint32_t t = threadIdx.x;
-    s[t] = bins[LEN_BINS - 1 - t];
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {  // reversed order: element e = bins[LEN_BINS - 1 - e]
+        v[k] = bins[LEN_BINS - 1 - (4 * t + k)];
+        sum += v[k];
+    }
+    s[t] = sum;
     __syncthreads();
-    for (uint32_t o = 1; o < LEN_BINS; o <<= 1) {
-        const uint32_t v = t >= o ? s[t - o] : 0u;
+    for (uint32_t o = 1; o < SCAN_THREADS; o <<= 1) {
+        const uint32_t x = t >= o ? s[t - o] : 0u;
         __syncthreads();
-        s[t] += v;
+        s[t] += x;
         __syncthreads();
     }
-    bins[LEN_BINS - 1 - t] = t ? s[t - 1] : 0u;
+    uint32_t run = t ? s[t - 1] : 0u;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        bins[LEN_BINS - 1 - (4 * t + k)] = run;
+        run += v[k];
+    }
 }
 // Scatter pattern ids into length order.  A block ranks its tile inside shared memory (the value returned by the
 // shared-memory atomic is the pattern's rank among the block's patterns of that length) and takes ONE global
 // atomic per (block, length) for the base, instead of one per pattern on ~60 hot addresses.
 constexpr uint32_t SCATTER_PER_THREAD = 8;
-__global__ void __launch_bounds__(256) k_len_scatter(const PatDesc* __restrict__ pats, uint32_t n_pat, uint32_t* __restrict__ bins,
+__global__ void __launch_bounds__(256, 8) k_len_scatter(const PatDesc* __restrict__ pats, uint32_t n_pat, uint32_t* __restrict__ bins,
                                                      uint32_t* __restrict__ order) {
     __shared__ uint32_t h[LEN_BINS];
     const uint32_t tile = 256u * SCATTER_PER_THREAD;
@@ -177,6 +192,9 @@ inline size_t count_smem_bytes(const DevIndex& ix) {
 #ifndef COUNT_MIN_CTAS
 #define COUNT_MIN_CTAS 2
 #endif
+#ifndef COUNT_BLOCK_ASSIGN
+#define COUNT_BLOCK_ASSIGN 1
+#endif
 // STATS: count rank queries / levels / records (fmgpu_set_stats; bench.py's roofline accounting and the tests) — off in production
 template <bool STATS>
 __global__ void __launch_bounds__(CTA_THREADS, COUNT_MIN_CTAS)
@@ -189,10 +207,22 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
     CountCounters cnt;
     cnt.ranks = cnt.levels = cnt.loads = cnt.recs = cnt.spec_wasted = 0;
 
+    // Work distribution: the first batch of every warp is static — CTA b takes the contiguous batches [b*W, (b+1)*W) of the
+    // length-ordered batch, so the warps of a CTA run patterns of (nearly) the same length and the CTA retires as a whole
+    // when they are done (short-pattern CTAs early), which lets the CTAs of the NEXT launch (the chunked host call runs
+    // several launches on different streams) backfill the SM instead of waiting for one long-pattern warp per CTA.  Further
+    // batches come from the global queue.
+    const unsigned warps_per_cta = blockDim.x >> 5;
+    bool first = COUNT_BLOCK_ASSIGN != 0;
     for (;;) {
         unsigned batch = 0;
-        if (lane == 0) batch = atomicAdd(queue, 1u);
-        batch = __shfl_sync(FULL, batch, 0);
+        if (first) {
+            batch = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
+            first = false;
+        } else {
+            if (lane == 0) batch = atomicAdd(queue, 1u);
+            batch = __shfl_sync(FULL, batch, 0) + (COUNT_BLOCK_ASSIGN ? gridDim.x * warps_per_cta : 0u);
+        }
         if ((uint64_t)batch * 32u >= n_pat) break;
         const uint32_t slot = batch * 32u + lane;
         const bool have = slot < n_pat;

@@ -31,6 +31,7 @@ _MESSAGES = {
     7: "Boundary does not exist",
     8: "Extraction does not fit in the supplied destination. Currently extracted: {n}",
     9: "ArrayIndexOutOfBoundsException",
+    10: "Found a character that exceeds (32767): it was {n}",
 }
 
 
@@ -85,6 +86,9 @@ def native():
         L.fmgpu_count_batch.argtypes = [vp, vp, vp, u32, vp, vp]
         L.fmgpu_count_batch_device.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp]
         L.fmgpu_locate_batch.argtypes = [vp, vp, vp, u32, i32, vp, vp, vp, u64, vp]
+        L.fmgpu_count_batch_utf8.argtypes = [vp, vp, vp, u32, vp, vp]
+        L.fmgpu_count_batch_utf8_device.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp]
+        L.fmgpu_locate_batch_utf8.argtypes = [vp, vp, vp, u32, i32, vp, vp, vp, u64, vp]
         L.fmgpu_locate_batch_device.argtypes = [vp, vp, vp, u64, u32, i32, vp, vp, vp, u64, vp, C.POINTER(u64), vp]
         L.fmgpu_extract_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
         L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
@@ -222,21 +226,53 @@ class FmIndex:
         self._check(self._lib.fmgpu_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data))
         return (counts, status) if return_status else counts
 
+    def count_batch_utf8(self, data, pat_off, return_status: bool = False):
+        """UTF-8 byte patterns (``convertBytePatternToCharPattern`` + ``count``); ``pat_off`` are byte offsets.  Where the status
+        is 10 the count slot holds the offending code point."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self._lib.fmgpu_count_batch_utf8(self._h, data.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data))
+        return (counts, status) if return_status else counts
+
+    def count_batch_utf8_into(self, data: np.ndarray, pat_off: np.ndarray, counts: np.ndarray, status: np.ndarray | None = None):
+        """``count_batch_utf8`` writing into caller-owned (e.g. pinned) buffers — the raw C-ABI call."""
+        self._check(self._lib.fmgpu_count_batch_utf8(self._h, data.ctypes.data, pat_off.ctypes.data, pat_off.size - 1, counts.ctypes.data,
+                                                     status.ctypes.data if status is not None else None))
+
+    def count_batch_utf8_device(self, d_bytes, d_pat_off, d_counts, d_status=None, stream: int | None = None):
+        """Device-resident UTF-8 patterns (torch uint8 / int64 tensors on this index's GPU)."""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_bytes.device).cuda_stream
+        self._check(self._lib.fmgpu_count_batch_utf8_device(self._h, d_bytes.data_ptr(), d_pat_off.data_ptr(), d_bytes.numel(),
+                                                            d_pat_off.numel() - 1, d_counts.data_ptr(),
+                                                            d_status.data_ptr() if d_status is not None else None, stream))
+
     def locate_batch(self, chars, pat_off, max_hits: int = -1):
         """-> (n_hits int32[n], hit_off uint64[n+1], positions int32[total], status int32[n])"""
-        chars = _u16(chars)
+        return self._locate_batch(self._lib.fmgpu_locate_batch, _u16(chars), pat_off, max_hits)
+
+    def locate_batch_utf8(self, data, pat_off, max_hits: int = -1):
+        """``locate_batch`` for UTF-8 byte patterns (``pat_off`` are byte offsets)."""
+        data = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if isinstance(data, (bytes, bytearray)) else data, dtype=np.uint8)
+        return self._locate_batch(self._lib.fmgpu_locate_batch_utf8, data, pat_off, max_hits)
+
+    def _locate_batch(self, fn, chars, pat_off, max_hits):
         pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
         n = pat_off.size - 1
         n_hits = np.zeros(n, dtype=np.int32)
         hit_off = np.zeros(n + 1, dtype=np.uint64)
         status = np.zeros(n, dtype=np.int32)
-        self._check(self._lib.fmgpu_locate_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data,
-                                                 hit_off.ctypes.data, None, 0, status.ctypes.data))
+        self._check(fn(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data, hit_off.ctypes.data, None, 0,
+                       status.ctypes.data))
         total = int(hit_off[-1])
         positions = np.zeros(max(total, 1), dtype=np.int32)
         if total:
-            self._check(self._lib.fmgpu_locate_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data,
-                                                     hit_off.ctypes.data, positions.ctypes.data, total, status.ctypes.data))
+            self._check(fn(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data, hit_off.ctypes.data,
+                           positions.ctypes.data, total, status.ctypes.data))
         return n_hits, hit_off, positions[:total], status
 
     def extract_batch(self, start, stop, arena_off=None):
@@ -276,6 +312,13 @@ class FmIndex:
         counts, status = self.count_batch(p[offset: offset + length], np.array([0, max(length, 0)], dtype=np.uint64), True)
         if status[0]:
             raise_status(status[0])
+        return int(counts[0])
+
+    def count_utf8(self, pattern: bytes) -> int:
+        """``count`` of a UTF-8 byte pattern: ``convertBytePatternToCharPattern`` (FmIndex.java:239-298) then ``count``."""
+        counts, status = self.count_batch_utf8(pattern, np.array([0, len(pattern)], dtype=np.uint64), True)
+        if status[0]:
+            raise_status(status[0], counts[0])
         return int(counts[0])
 
     def locate(self, pattern, offset: int = 0, length: int | None = None, locations=None, max_matches: int = -1):

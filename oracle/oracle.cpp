@@ -51,6 +51,7 @@ enum {
     ST_NO_BOUNDARY = 7,      // IllegalArgumentException("Boundary does not exist")              FM:659,792,849
     ST_DOES_NOT_FIT = 8,     // RuntimeException("Extraction does not fit ... Currently extracted: N") FM:733,817,894
     ST_INDEX_OOB = 9,        // ArrayIndexOutOfBoundsException (e.g. quirk Q4, WF:1022-1026)
+    ST_CHAR_EXCEEDS = 10,    // RuntimeException("Found a character that exceeds (32767): it was N")  FM:262-267
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -802,6 +803,45 @@ struct FmIndex {
     }
 };
 
+// FmIndex.convertBytePatternToCharPattern (fm/FmIndex.java:239-298), restated branch by branch.  `pattern` is a Java byte[]
+// of `array_len` bytes: reading past its end throws ArrayIndexOutOfBounds (a multi-byte sequence cut off by the end of the
+// array).  Returns the number of chars written to `destination`.
+int64_t convert_byte_pattern_to_char_pattern(const int8_t* pattern, int64_t array_len, int64_t offset, int64_t length, uint16_t* destination) {
+    auto at = [&](int64_t i) -> int32_t {
+        if (i < 0 || i >= array_len) throw std::out_of_range("pattern");
+        return (int32_t)pattern[i];  // Java promotes the (signed) byte to int
+    };
+    int64_t pos = offset;
+    int64_t i = 0;
+    while (pos < length + offset) {  // :245
+        const int32_t firstByte = at(pos);
+        uint16_t nextChar;
+        if (firstByte < 0) {  // :247
+            if (((firstByte & 0xF0) >> 3) == 30) {  // :249 four-byte sequence
+                const int32_t secondByte = at(pos + 1), thirdByte = at(pos + 2), fourthByte = at(pos + 3);
+                pos += 4;
+                const int32_t beforeConversion =
+                    (((firstByte & 0x07) << 18) | ((secondByte & 0x3F) << 12) | ((thirdByte & 0x3F) << 6) | (fourthByte & 0x3F)) & 0x1FFFFF;  // :255-260
+                if (beforeConversion > 32767) throw JavaThrow{ST_CHAR_EXCEEDS, beforeConversion};  // :261-267
+                nextChar = (uint16_t)beforeConversion;
+            } else if (((firstByte & 0xE0) >> 4) == 14) {  // :270 three-byte sequence
+                const int32_t secondByte = at(pos + 1), thirdByte = at(pos + 2);
+                pos += 3;
+                nextChar = (uint16_t)((((firstByte & 0x0F) << 12) | ((secondByte & 0x3F) << 6) | (thirdByte & 0x3F)) & 0xFFFF);  // :274-279
+            } else {  // :280 two-byte sequence (every other negative first byte, continuation bytes included)
+                const int32_t secondByte = at(pos + 1);
+                pos += 2;
+                nextChar = (uint16_t)((((firstByte & 0x1F) << 6) | (secondByte & 0x3F)) & 0x7FF);  // :284-287
+            }
+        } else {  // :289 single byte
+            ++pos;
+            nextChar = (uint16_t)firstByte;
+        }
+        destination[i++] = nextChar;  // :294
+    }
+    return i;
+}
+
 template <typename F>
 int guarded(F&& f) {
     try {
@@ -928,6 +968,60 @@ void orc_fm_count_batch(void* h, const uint16_t* chars, const uint64_t* pat_off,
         counts[i] = c;
         if (status) status[i] = st;
     });
+}
+// convertBytePatternToCharPattern + count per pattern; every pattern is its own byte[] (bytes[pat_off[i], pat_off[i+1])).
+// status 10: the converter's "Found a character that exceeds (32767): it was N", N in counts[i].
+void orc_fm_count_batch_utf8(void* h, const uint8_t* bytes, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
+                             int32_t threads) {
+    FmIndex* f = (FmIndex*)h;
+    parallel_for((int64_t)n_pat, threads, [&](int64_t i) {
+        const int64_t len = (int64_t)(pat_off[i + 1] - pat_off[i]);
+        std::vector<uint16_t> dst((size_t)len + 1);
+        int32_t c = 0;
+        int st = 0;
+        try {
+            const int64_t n = convert_byte_pattern_to_char_pattern((const int8_t*)bytes + pat_off[i], len, 0, len, dst.data());
+            st = orc_fm_count(f, dst.data(), 0, (int32_t)n, &c);
+        } catch (const JavaThrow& t) {
+            st = t.status;
+            c = t.n;
+        } catch (const std::out_of_range&) {
+            st = ST_INDEX_OOB;
+        }
+        counts[i] = c;
+        if (status) status[i] = st;
+    });
+}
+void orc_fm_locate_batch_utf8(void* h, const uint8_t* bytes, const uint64_t* pat_off, uint32_t n_pat, int32_t max_matches, int32_t* n_hits,
+                              int32_t* positions, int64_t stride, int32_t* status, int32_t threads) {
+    FmIndex* f = (FmIndex*)h;
+    parallel_for((int64_t)n_pat, threads, [&](int64_t i) {
+        const int64_t len = (int64_t)(pat_off[i + 1] - pat_off[i]);
+        std::vector<uint16_t> dst((size_t)len + 1);
+        int32_t k = 0;
+        int st = 0;
+        try {
+            const int64_t n = convert_byte_pattern_to_char_pattern((const int8_t*)bytes + pat_off[i], len, 0, len, dst.data());
+            st = orc_fm_locate(f, dst.data(), 0, (int32_t)n, positions + i * stride, stride, max_matches, &k);
+        } catch (const JavaThrow& t) {
+            st = t.status;
+        } catch (const std::out_of_range&) {
+            st = ST_INDEX_OOB;
+        }
+        n_hits[i] = k;
+        if (status) status[i] = st;
+    });
+}
+// the converter alone: returns the char count, or -100 - status (value of the offending code point in *value)
+int64_t orc_convert_utf8(const uint8_t* bytes, int64_t array_len, int64_t offset, int64_t length, uint16_t* dst, int32_t* value) {
+    try {
+        return convert_byte_pattern_to_char_pattern((const int8_t*)bytes, array_len, offset, length, dst);
+    } catch (const JavaThrow& t) {
+        if (value) *value = t.n;
+        return -100 - t.status;
+    } catch (const std::out_of_range&) {
+        return -100 - ST_INDEX_OOB;
+    }
 }
 // positions of pattern i are written at positions + i*stride (stride >= max hits expected).
 void orc_fm_locate_batch(void* h, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t max_matches, int32_t* n_hits,

@@ -25,6 +25,7 @@ STATUS_MESSAGES = {
     7: "Boundary does not exist",
     8: "Extraction does not fit in the supplied destination. Currently extracted: {n}",
     9: "ArrayIndexOutOfBoundsException",
+    10: "Found a character that exceeds (32767): it was {n}",
 }
 
 _lib = None
@@ -52,6 +53,10 @@ def lib():
         L.orc_fm_extract_until_boundary.argtypes = [vp, i32, vp, i64, i32, C.c_uint16, i32, C.POINTER(i32)]
         L.orc_fm_count_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, i32]
         L.orc_fm_locate_batch.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, i64, vp, i32]
+        L.orc_fm_count_batch_utf8.argtypes = [vp, vp, vp, C.c_uint32, vp, vp, i32]
+        L.orc_fm_locate_batch_utf8.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, i64, vp, i32]
+        L.orc_convert_utf8.argtypes = [vp, i64, i64, i64, vp, C.POINTER(i32)]
+        L.orc_convert_utf8.restype = i64
         L.orc_fm_extract_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, i64, vp, vp, i32]
         L.orc_fm_extract_until_boundary_batch.argtypes = [vp, vp, C.c_uint32, C.c_uint16, i32, i32, vp, vp, vp, i32]
         L.orc_fm_stats.argtypes = [vp, vp, i32]
@@ -164,6 +169,27 @@ class OracleFmIndex:
         lib().orc_fm_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data, threads)
         return counts, status
 
+    def count_batch_utf8(self, data, pat_off, threads=1):
+        """convertBytePatternToCharPattern + count per pattern (every pattern its own byte[])."""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        lib().orc_fm_count_batch_utf8(self._h, data.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data, threads)
+        return counts, status
+
+    def locate_batch_utf8(self, data, pat_off, max_matches, stride, threads=1):
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        n_hits = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        pos = np.zeros((n, stride), dtype=np.int32)
+        lib().orc_fm_locate_batch_utf8(self._h, data.ctypes.data, pat_off.ctypes.data, n, max_matches, n_hits.ctypes.data,
+                                       pos.ctypes.data, stride, status.ctypes.data, threads)
+        return n_hits, pos, status
+
     def locate_batch(self, chars, pat_off, max_matches, stride, threads=1):
         chars = _u16(chars)
         pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
@@ -220,6 +246,18 @@ class OracleFmIndex:
 
     def sampled_access(self, pos):
         return lib().orc_fm_sampled_access(self._h, pos)
+
+
+def convert_byte_pattern_to_char_pattern(pattern, offset=0, length=None) -> np.ndarray:
+    """FmIndex.convertBytePatternToCharPattern (fm/FmIndex.java:239-298); raises JavaException like the reference."""
+    data = np.ascontiguousarray(np.frombuffer(bytes(pattern), dtype=np.uint8))
+    length = data.size - offset if length is None else length
+    dst = np.zeros(max(1, length), dtype=np.uint16)
+    val = C.c_int32(0)
+    n = lib().orc_convert_utf8(data.ctypes.data, data.size, offset, length, dst.ctypes.data, C.byref(val))
+    if n < 0:
+        raise JavaException(int(-100 - n), val.value)
+    return dst[:n].copy()
 
 
 def rrr_inverse_table() -> np.ndarray:

@@ -117,3 +117,19 @@ def make_patterns(text: np.ndarray, n_pat: int, min_len: int, max_len: int, seed
     off = np.zeros(n_pat + 1, dtype=np.uint64)
     off[1:] = np.cumsum([p.size for p in pats])
     return np.ascontiguousarray(np.concatenate(pats), dtype=np.uint16), off
+
+
+@pytest.fixture(scope="module")
+def gpu_indexes():
+    """GPU-resident indexes of the test cases (loaded through the C ABI), one set per test module."""
+    from index4j_b200 import FmIndex
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            cache[name] = FmIndex.read(get_case(name).blob)
+        return cache[name]
+
+    yield get
+    for v in cache.values():
+        v.close()

@@ -11,6 +11,7 @@
 #include "../../index4j_b200/csrc/jstream.hpp"
 #include "../../index4j_b200/csrc/count_lane.h"
 #include "../../index4j_b200/csrc/lf_lane.h"
+#include "../../index4j_b200/csrc/utf8_lane.h"
 
 using namespace fmgpu;
 
@@ -297,6 +298,12 @@ void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
     sampled_access_rank(h.ix, R, *sg_addr(h.ix, pos), pos, &b, &r);
     *bit = (int32_t)b;
     *rank = (int32_t)r;
+}
+
+// the device-side UTF-8 decoder (utf8_lane.h) on one pattern: returns the char count or -status (*value = code point)
+int64_t fc_utf8_convert(const uint8_t* bytes, uint64_t len, uint16_t* out, int32_t* value) {
+    uint32_t last = 0;
+    return utf8_convert(bytes, 0, len, out, value, &last);
 }
 
 // all 32768 (class, offset) pairs through the device unranking, in table order

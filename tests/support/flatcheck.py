@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "flatcheck.cpp")] + [
-        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "lf_lane.h", "ldrec.h", "layout.h")
+        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "lf_lane.h", "ldrec.h", "layout.h", "count_lane.h", "utf8_lane.h")
     ]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
@@ -42,6 +42,8 @@ def lib():
         L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp]
         L.fc_sampled.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
         L.fc_unrank_table.argtypes = [vp]
+        L.fc_utf8_convert.argtypes = [vp, C.c_uint64, vp, C.POINTER(i32)]
+        L.fc_utf8_convert.restype = C.c_int64
         _lib = L
     return _lib
 
@@ -121,3 +123,14 @@ def unrank_table():
     t = np.zeros(32768, dtype=np.uint16)
     lib().fc_unrank_table(t.ctypes.data)
     return t
+
+
+def utf8_convert(data: bytes):
+    """The device-side decoder of utf8_lane.h run on the host: -> (chars uint16[n], 0, 0) or (None, status, value)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.zeros(max(1, buf.size), dtype=np.uint16)
+    val = C.c_int32(0)
+    n = lib().fc_utf8_convert(buf.ctypes.data if buf.size else None, buf.size, out.ctypes.data, C.byref(val))
+    if n < 0:
+        return None, int(-n), int(val.value)
+    return out[:n].copy(), 0, 0

@@ -12,21 +12,6 @@ from conftest import CASE_NAMES, get_case, make_patterns
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def gpu_indexes():
-    from index4j_b200 import FmIndex
-    cache = {}
-
-    def get(name):
-        if name not in cache:
-            cache[name] = FmIndex.read(get_case(name).blob)
-        return cache[name]
-
-    yield get
-    for v in cache.values():
-        v.close()
-
-
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_count_matches_oracle(gpu_indexes, name):
     case = get_case(name)
