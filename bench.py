@@ -38,6 +38,25 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly one JSON line: everything else that writes to fd 1 (e.g. NCCL's version banner) is sent to
+    stderr, and emit() writes to the original stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def cache_path(name: str) -> str:
     for d in (CACHE, ALT_CACHE):
         p = os.path.join(d, name)
@@ -214,7 +233,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args):
@@ -246,6 +265,7 @@ def main():
     ap.add_argument("--dst-len", type=int, default=512)
     ap.add_argument("--build-only", action="store_true", help="build + cache the index and the pattern batches, then exit")
     args = ap.parse_args()
+    claim_stdout()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
 
@@ -463,7 +483,7 @@ def main():
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                    "sample": "first %d of the %d patterns, best of %d passes, %.1fs per pass (C++ restatement of the reference's Java loops; no JVM in this image)"
                                              % (cpu_counts.size, n_pat, args.cpu_repeats, dt)}
-        print(json.dumps(out), flush=True)
+        emit(out)
     ix.close()
     if world > 1:
         dist.destroy_process_group()

@@ -133,6 +133,15 @@ int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d
                                               int32_t dst_len, int32_t mode, uint16_t* d_arena, int32_t* d_len_out,
                                               int32_t* d_status_out, void* cuda_stream);
 
+/* The index's wavelet structure (FmIndex.waveletFixedBlockBoosting) queried directly — the reference's public
+ * WaveletFixedBlockBoosting.rank(long position, short symbol) WF:1010-1285 and inverseSelect(long position) WF:1305-1537
+ * over alphabet CODES (FmIndex maps chars to codes by first appearance, FM:396-435).  out[i] of inverse_select is the
+ * packed long Java returns: (rank << 32) | symbol, the bare symbol for position 0.  Status FMGPU_ST_INDEX_OOB where the
+ * reference indexes out of its arrays (negative arguments, rank(size, .) on a superblock boundary, inverseSelect outside
+ * [0, size)). */
+int fmgpu_wavelet_rank_batch(fmgpu_index* idx, const int64_t* pos, const int32_t* sym, uint32_t n, int64_t* out, int32_t* status_out);
+int fmgpu_wavelet_inverse_select_batch(fmgpu_index* idx, const int64_t* pos, uint32_t n, int64_t* out, int32_t* status_out);
+
 /* Work counters of the most recent batch call on this index (device-side counted, read back here):
  * [0] rank queries that touched memory  [1] wavelet levels walked by rank queries
  * [2] LF steps (inverseSelect walks)     [3] wavelet levels walked by LF steps

@@ -324,7 +324,12 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         Rec32& D = F.blocks[(size_t)P.first_block + b];
         memset(&D, 0, sizeof D);
         if (T.h == 0) {
-            D.w[1] = 1u | (((uint32_t)T.sym[0] & 0xffu) << 8);  // inverseSelect keeps the low byte only (:1329-1332)
+            const uint32_t c8 = (uint32_t)T.sym[0] & 0xffu;
+            D.w[1] = 1u | (c8 << 8);  // inverseSelect keeps the low byte only (:1329-1332)
+            // inverseSelect's rank inside a single-symbol block (:1338-1352): boundary ranks of the TRUNCATED symbol at the
+            // superblock / hyperblock level + the block boundary rank of the header entry + position in block
+            if (c8 < (uint32_t)sigma)
+                D.w[5] = (uint32_t)((uint64_t)W.hyper_rank[c8] + (uint64_t)(int64_t)W.sb_rank[sb * (size_t)sigma + c8] + T.brank[0]);
             continue;
         }
         block_node_base[b] = node;

@@ -18,6 +18,7 @@
 #include "kernels_lf.cuh"
 #include "kernels_locate.cuh"
 #include "kernels_utf8.cuh"
+#include "kernels_wavelet.cuh"
 #include "layout.h"
 
 using namespace fmgpu;
@@ -235,6 +236,7 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
 }  // namespace
 
 #include "api_lf.inc"
+#include "api_wavelet.inc"
 
 extern "C" {
 

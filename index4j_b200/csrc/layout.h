@@ -44,7 +44,7 @@ constexpr uint32_t CELL_INLINE_PAIRS = 5;
 // --- block descriptor (LF / inverseSelect entry, :1305-1537):
 //   w0 first level record of the root, w1 info (bit0 = run block, bits 8-23 = run symbol c' as inverseSelect decodes it),
 //   run blocks: w2 / w3 = value / kind of the (block, c') cell, i.e. rank(j, c') for j inside the block;
-//   w4 = node record of the root.
+//   w4 = node record of the root; run blocks: w5 = the boundary ranks inverseSelect adds the in-block position to (:1338-1352).
 // --- node record of an even-depth node (32 B): entries [t][u] = {c, a} at w[4t + 2u], t = bit at this depth, u = bit at
 // the next.  Child t is a leaf: entry [t][0] = {LEAF1_FLAG | symbol, boundary rank of the symbol}.  Else grandchild [t][u]:
 // leaf => {LEAF_FLAG | symbol, boundary rank}; internal => {its node record, its first level record}.

@@ -94,6 +94,8 @@ def native():
         L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp, vp]
+        L.fmgpu_wavelet_rank_batch.argtypes = [vp, vp, vp, u32, vp, vp]
+        L.fmgpu_wavelet_inverse_select_batch.argtypes = [vp, vp, u32, vp, vp]
         L.fmgpu_last_stats.argtypes = [vp, vp]
         L.fmgpu_last_stats_ex.argtypes = [vp, vp, C.c_uint32]
         L.fmgpu_set_timing.argtypes = [vp, i32]
@@ -274,6 +276,24 @@ class FmIndex:
             self._check(fn(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, n_hits.ctypes.data, hit_off.ctypes.data,
                            positions.ctypes.data, total, status.ctypes.data))
         return n_hits, hit_off, positions[:total], status
+
+    # --- the wavelet structure itself (WaveletFixedBlockBoosting.rank / inverseSelect over alphabet codes) ---------
+    def wavelet_rank_batch(self, pos, sym):
+        """``WaveletFixedBlockBoosting.rank(position, symbol)`` per query -> (ranks int64[n], status int32[n])"""
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        sym = np.ascontiguousarray(sym, dtype=np.int32)
+        out = np.zeros(pos.size, dtype=np.int64)
+        st = np.zeros(pos.size, dtype=np.int32)
+        self._check(self._lib.fmgpu_wavelet_rank_batch(self._h, pos.ctypes.data, sym.ctypes.data, pos.size, out.ctypes.data, st.ctypes.data))
+        return out, st
+
+    def wavelet_inverse_select_batch(self, pos):
+        """``WaveletFixedBlockBoosting.inverseSelect(position)`` per query -> (packed int64[n] = rank << 32 | symbol, status)"""
+        pos = np.ascontiguousarray(pos, dtype=np.int64)
+        out = np.zeros(pos.size, dtype=np.int64)
+        st = np.zeros(pos.size, dtype=np.int32)
+        self._check(self._lib.fmgpu_wavelet_inverse_select_batch(self._h, pos.ctypes.data, pos.size, out.ctypes.data, st.ctypes.data))
+        return out, st
 
     def extract_batch(self, start, stop, arena_off=None):
         """-> (arena uint16[..], arena_off, len int32[n], status int32[n]); slot i = arena[arena_off[i]:arena_off[i+1]]"""

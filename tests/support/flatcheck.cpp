@@ -300,6 +300,32 @@ void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
     *rank = (int32_t)r;
 }
 
+// inverseSelect(pos) through the block descriptor / level + node records, as k_wavelet_inverse_select walks them
+int fc_inverse_select(void* hv, int64_t p64, int64_t* out) {
+    FC& h = *(FC*)hv;
+    *out = 0;
+    if (p64 < 0 || p64 >= (int64_t)h.ix.length) return 9;
+    const uint32_t p = (uint32_t)p64;
+    const SbDesc sd = h.T.sb[p >> SB_LOG];
+    const uint32_t blk = sd.first_block + ((p & SB_MASK) >> sd.block_log);
+    uint32_t r = p & ((1u << sd.block_log) - 1u);
+    const Rec32& D = h.ix.blocks[blk];
+    uint32_t sym = 0, rk = 0;
+    if (D.w[1] & 1u) {
+        sym = (D.w[1] >> 8) & 0xffffu;
+        rk = D.w[5] + r;
+    } else {
+        uint32_t sec = D.w[0], nrec = D.w[4], levels = 0;
+        for (;;) {
+            const Rec32& X = h.ix.sectors[sec + r / SECTOR_BITS];
+            const Rec32& N = h.ix.nodes[nrec];
+            if (dlevel_descend(X, N, r % SECTOR_BITS, &r, &nrec, &sec, &sym, &rk, &levels)) break;
+        }
+    }
+    *out = p == 0u ? (int64_t)sym : (((int64_t)rk << 32) | (int64_t)sym);
+    return 0;
+}
+
 // the device-side UTF-8 decoder (utf8_lane.h) on one pattern: returns the char count or -status (*value = code point)
 int64_t fc_utf8_convert(const uint8_t* bytes, uint64_t len, uint16_t* out, int32_t* value) {
     uint32_t last = 0;

@@ -35,6 +35,7 @@ def lib():
         L.fc_sizes.argtypes = [vp, vp]
         L.fc_rank.argtypes = [vp, u32, u32, C.POINTER(C.c_int64)]
         L.fc_count_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
+        L.fc_inverse_select.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
         L.fc_check_roots.argtypes = [vp]
         L.fc_check_roots.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
@@ -82,6 +83,11 @@ class FlatIndexHost:
         lib().fc_count_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data,
                              ranges.ctypes.data, self.counters.ctypes.data)
         return counts, status, ranges.reshape(n, 2)
+
+    def inverse_select(self, pos: int):
+        out = C.c_int64(0)
+        st = lib().fc_inverse_select(self._h, int(pos), C.byref(out))
+        return st, int(out.value)
 
     def check_roots(self) -> int:
         return int(lib().fc_check_roots(self._h))

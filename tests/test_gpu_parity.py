@@ -214,3 +214,31 @@ def test_malformed_streams_rejected():
     bad[9] = 3
     with pytest.raises(IOError, match="Incompatible serial versions! Expected version 0 but was 3."):
         FmIndex.read(bytes(bad))
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_wavelet_rank_and_inverse_select_match_oracle(gpu_indexes, name):
+    """The wavelet structure queried directly (fmgpu_wavelet_rank_batch / fmgpu_wavelet_inverse_select_batch)."""
+    case, g = get_case(name), gpu_indexes(name)
+    rng = np.random.default_rng(17)
+    L = case.oracle.getInputLength()
+    sigma = case.oracle.getAlphabetLength() + 2
+    pos = np.concatenate([rng.integers(0, L + 1, 20000), [0, 1, L - 1, L, L + 5, -1, -7],
+                          (rng.integers(1, max(2, L >> 9), 3000) << 9) + rng.integers(-1, 2, 3000)]).astype(np.int64)
+    sym = rng.integers(0, sigma, pos.size).astype(np.int32)
+    sym[:50] = -1
+    got, st = g.wavelet_rank_batch(pos, sym)
+    for i in range(pos.size):
+        try:
+            want, wst = case.oracle.wfbb_rank(int(pos[i]), int(sym[i])), 0
+        except pyoracle.JavaException as e:
+            want, wst = 0, e.status
+        assert st[i] == wst and (wst or got[i] == want), (int(pos[i]), int(sym[i]), want, int(got[i]), wst, int(st[i]))
+    ipos = np.concatenate([rng.integers(0, L, 20000), [0, 1, L - 1, -1, L, L + 9]]).astype(np.int64)
+    got, st = g.wavelet_inverse_select_batch(ipos)
+    for i in range(ipos.size):
+        p = int(ipos[i])
+        if p < 0 or p >= L:
+            assert st[i] == 9
+        else:
+            assert st[i] == 0 and int(got[i]) == case.oracle.wfbb_inverse_select(p), p

@@ -48,6 +48,20 @@ def test_rank_cells_match_oracle(flats, name):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
+def test_inverse_select_records_match_oracle(flats, name):
+    """WaveletFixedBlockBoosting.inverseSelect through the block descriptors / level + node records (incl. the low-byte symbol of
+    single-symbol blocks, quirk Q1) against the oracle's restatement of :1305-1537."""
+    case, f = get_case(name), flats(name)
+    rng = np.random.default_rng(5)
+    L = case.oracle.getInputLength()
+    pos = np.concatenate([rng.integers(0, L, 20000), [0, 1, L - 1], (rng.integers(1, max(2, L >> 9), 2000) << 9) + rng.integers(-1, 2, 2000)])
+    for p in np.clip(pos, 0, L - 1):
+        st, got = f.inverse_select(int(p))
+        assert st == 0 and got == case.oracle.wfbb_inverse_select(int(p)), int(p)
+    assert f.inverse_select(-1)[0] == 9 and f.inverse_select(L)[0] == 9
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
 def test_root_record_directory(flats, name):
     """The speculative root fetch of count_step computes a block's root record from shared-memory tables alone: it must be the
     first record of every NORMAL cell of the block (and the block descriptor's root)."""
