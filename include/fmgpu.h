@@ -45,6 +45,7 @@ extern "C" {
 #define FMGPU_ST_DST_ZERO 6       /* IllegalArgumentException("Supplied destination for extraction has size zero") FM:623 */
 #define FMGPU_ST_NO_BOUNDARY 7    /* IllegalArgumentException("Boundary does not exist")           FM:659,792,849 */
 #define FMGPU_ST_DOES_NOT_FIT 8   /* RuntimeException("Extraction does not fit in the supplied destination. Currently extracted: N") FM:733,817,894; N in len_out */
+#define FMGPU_ST_RRR_RANGE 11     /* IllegalArgumentException("Out of range access. Requested P when range is [0, L)") RRR:316-323 */
 #define FMGPU_ST_CHAR_EXCEEDS 10  /* RuntimeException("Found a character that exceeds (32767): it was N") FM:261-267 (UTF-8 entry points; N in counts_out) */
 #define FMGPU_ST_INDEX_OOB 9      /* ArrayIndexOutOfBoundsException (empty pattern FM:456; rank(size,.) on a superblock boundary, wavelet/WaveletFixedBlockBoosting.java:1022-1026) */
 
@@ -139,6 +140,18 @@ int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d
  * packed long Java returns: (rank << 32) | symbol, the bare symbol for position 0.  Status FMGPU_ST_INDEX_OOB where the
  * reference indexes out of its arrays (negative arguments, rank(size, .) on a superblock boundary, inverseSelect outside
  * [0, size)). */
+/* fmgpu_wavelet_load_serialized: a handle from a bare WaveletFixedBlockBoosting stream (WaveletFixedBlockBoosting.write WF:1544 /
+ * read WF:286) — valid for the two fmgpu_wavelet_* calls and the getters only (symbols are the structure's own short values).
+ * fmgpu_rrr_load_serialized: a handle from a bare RrrVector stream (RrrVector.write / read, bitsequence/RrrVector.java:430-469)
+ * — valid for fmgpu_rrr_rank_access_batch only.  Every other call on such handles returns FMGPU_ERR_UNSUPPORTED.  Free both
+ * with fmgpu_index_free. */
+int fmgpu_wavelet_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out);
+int fmgpu_rrr_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out);
+/* RrrVector.rankOnes(int) RRR:358-396 and access(int) RRR:314-349 per position (on an RRR handle, or the sampledSuffixes
+ * vector of an FmIndex handle).  rankOnes: position < 0 -> 0, position >= length -> total ones; access outside [0, length)
+ * throws in the reference: status_out FMGPU_ST_RRR_RANGE, access_out 0.  rankZeroes(p) = p - rankOnes(p) (RRR:405). */
+int fmgpu_rrr_rank_access_batch(fmgpu_index* idx, const int32_t* pos, uint32_t n, int32_t* rank_ones_out, int32_t* access_out,
+                                int32_t* status_out);
 int fmgpu_wavelet_rank_batch(fmgpu_index* idx, const int64_t* pos, const int32_t* sym, uint32_t n, int64_t* out, int32_t* status_out);
 int fmgpu_wavelet_inverse_select_batch(fmgpu_index* idx, const int64_t* pos, uint32_t n, int64_t* out, int32_t* status_out);
 

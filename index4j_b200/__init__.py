@@ -9,5 +9,7 @@ method set of the reference's ``com.dynatrace.fm.FmIndex``
 
 from .builder import FmIndexBuilder, build_index, gen_log_text, gen_patterns  # noqa: F401
 from .fm_index import FmIndex, FmIndexError  # noqa: F401
+from .structures import RrrVector, WaveletFixedBlockBoosting  # noqa: F401
 
-__all__ = ["FmIndex", "FmIndexError", "FmIndexBuilder", "build_index", "gen_log_text", "gen_patterns"]
+__all__ = ["FmIndex", "FmIndexError", "FmIndexBuilder", "build_index", "gen_log_text", "gen_patterns", "RrrVector",
+           "WaveletFixedBlockBoosting"]

@@ -592,7 +592,9 @@ inline void unpack_samples(const PackedInts& v, std::vector<Rec32>& out) {
 // budget for the dense (block x symbol) cell table; beyond it the index is rejected for now
 constexpr uint64_t MAX_CELL_BYTES = 48ULL << 30;
 
-inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
+// wavelet_only: the stream held a bare WaveletFixedBlockBoosting (fm.wf filled, everything else empty): only the wavelet
+// records are produced (rank / inverseSelect entry points)
+inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_only = false) {
     const WfbbStream& W = fm.wf;
     fmgpu::DevIndex& M = F.meta;
     M.length = (uint32_t)fm.length;
@@ -699,10 +701,34 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F) {
     // pass 2: fill
     parallel_sbs(nsb, threads, [&](size_t sb) { flatten_superblock(W, sb, plan[sb], F); });
 
+    if (wavelet_only) {
+        F.sgroups.assign(1, Rec32{});
+        F.soffsets.assign(16, 0);
+        F.sa.assign(1, Rec32{});
+        F.isa.assign(1, Rec32{});
+        return;
+    }
     flatten_sampled(fm.sampled, F);
     unpack_samples(fm.suffixes, F.sa);
     if (fm.enable_extract) unpack_samples(fm.positions, F.isa);
     else F.isa.assign(1, Rec32{});
+}
+
+// a bare RrrVector stream: only the group records / offset stream of the rank / access kernels
+inline void flatten_rrr(const RrrStream& r, FlatIndex& F) {
+    fmgpu::DevIndex& M = F.meta;
+    M = fmgpu::DevIndex{};
+    M.length = (uint32_t)r.length;
+    M.sample_rate = 1;
+    M.s_total_ones = (uint32_t)r.total_ones;
+    F.C.assign(2, 0);
+    F.char2code.assign(65536, 0);
+    F.code2char.assign(1, 0);
+    F.sb.assign(1, fmgpu::SbDesc{0, 16});
+    F.sbroot.assign(1, fmgpu::U32x2{0, 1});
+    F.blkmap.assign(1, fmgpu::U32x2{0, 0});
+    for (auto* v : {&F.cells, &F.sectors, &F.ovf, &F.blocks, &F.nodes, &F.sa, &F.isa}) v->assign(1, Rec32{});
+    flatten_sampled(r, F);
 }
 
 }  // namespace fmgpu_host

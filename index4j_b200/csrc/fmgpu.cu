@@ -79,8 +79,11 @@ enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x 9 at word 2.. */
 
 }  // namespace
 
+enum { KIND_FM = 0, KIND_WAVELET = 1, KIND_RRR = 2 };
+
 struct fmgpu_index {
     int device = 0;
+    int kind = KIND_FM;  // what the handle was loaded from: an FmIndex stream, a bare WaveletFixedBlockBoosting, a bare RrrVector
     DevIndex dev{};
     std::vector<void*> allocs;
     uint64_t layout_bytes[8] = {0};
@@ -162,6 +165,7 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
                     const Utf8Src* u8 = nullptr, cudaStream_t pre = nullptr, cudaEvent_t pre_ev = nullptr, int threads = CTA_THREADS) {
     // `pre` (optional): stream for the pre-pass kernels, joined into `st` through pre_ev before the search kernel
     (void)total_chars;
+    if (ix->kind != KIND_FM) return fail(FMGPU_ERR_UNSUPPORTED, "the handle holds no FmIndex (loaded from a bare wavelet / RRR stream)");
     if (u8) d_chars = u8->d_chars;
     Scratch& s_pats = ctx ? ix->cctx[ctx - 1].pats : ix->pats;
     Scratch& s_ctrl = ctx ? ix->cctx[ctx - 1].ctrl : ix->ctrl;
@@ -243,7 +247,11 @@ extern "C" {
 const char* fmgpu_last_error(void) { return g_err.c_str(); }
 const char* fmgpu_version(void) { return "fmgpu 0.1 (sm_100a)"; }
 
-int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out) {
+}  // extern "C"
+
+namespace {
+// Parses a serialized FmIndex / WaveletFixedBlockBoosting / RrrVector (Java stream layout), re-lays it out and uploads it.
+int load_common(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out, int kind) {
     if (!buf || !out) return fail(FMGPU_ERR_ARG, "null argument");
     *out = nullptr;
     int dev = opts ? opts->device : -1;
@@ -259,9 +267,21 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
     fmgpu_host::FlatIndex F;
     try {
         fmgpu_host::JavaIn in(buf, len);
-        fmgpu_host::FmStream fm;
-        fm.read(in);
-        fmgpu_host::flatten(fm, threads, F);
+        if (kind == KIND_FM) {
+            fmgpu_host::FmStream fm;
+            fm.read(in);
+            fmgpu_host::flatten(fm, threads, F);
+        } else if (kind == KIND_WAVELET) {  // WaveletFixedBlockBoosting.read (wavelet/WaveletFixedBlockBoosting.java:286-322)
+            fmgpu_host::FmStream fm;
+            fm.wf.read(in);
+            fm.length = (int32_t)fm.wf.size;
+            fm.sample_rate = 1;
+            fmgpu_host::flatten(fm, threads, F, true);
+        } else {  // RrrVector.read (bitsequence/RrrVector.java:448-469)
+            fmgpu_host::RrrStream r;
+            r.read(in);
+            fmgpu_host::flatten_rrr(r, F);
+        }
     } catch (const fmgpu_host::FormatError& e) {
         return fail(FMGPU_ERR_FORMAT, "%s", e.what());
     } catch (const std::bad_alloc&) {
@@ -274,6 +294,7 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
     if (!g.ok) return fail(FMGPU_ERR_CUDA, "cannot select device %d", dev);
     fmgpu_index* ix = new fmgpu_index();
     ix->device = dev;
+    ix->kind = kind;
     ix->dev = F.meta;
     ix->alphabet_length = F.alphabet_length;
     int rc = 0;
@@ -347,6 +368,19 @@ int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts
     }
     *out = ix;
     return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out) {
+    return load_common(buf, len, opts, out, KIND_FM);
+}
+int fmgpu_wavelet_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out) {
+    return load_common(buf, len, opts, out, KIND_WAVELET);
+}
+int fmgpu_rrr_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out) {
+    return load_common(buf, len, opts, out, KIND_RRR);
 }
 
 void fmgpu_index_free(fmgpu_index* ix) {

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.cuh"
+#include "kernels_locate.cuh"
 
 namespace fmgpu {
 
@@ -71,6 +72,44 @@ __global__ void __launch_bounds__(256) k_wavelet_inverse_select(const DevIndex i
         }
         out[i] = p == 0u ? (int64_t)sym : (((int64_t)rk << 32) | (int64_t)sym);
         status[i] = 0;
+    }
+}
+
+// RrrVector.rankOnes / access per position over the 32-block group records (the (class, offset) -> block table in shared
+// memory, like k_locate)
+__global__ void __launch_bounds__(256) k_rrr_rank_access(const DevIndex ix, const int32_t* __restrict__ pos, uint32_t n,
+                                                         int32_t* __restrict__ rank_out, int32_t* __restrict__ access_out,
+                                                         int32_t* __restrict__ status) {
+    extern __shared__ uint32_t smem[];
+    uint16_t* inv = reinterpret_cast<uint16_t*>(smem);
+    uint16_t* cbase = inv + 32768;
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(ix.rrr_inv);
+        for (uint32_t i = threadIdx.x; i < 16384u; i += blockDim.x) smem[i] = __ldg(src + i);
+        if (threadIdx.x < 16) cbase[threadIdx.x] = __ldg(ix.rrr_cbase + threadIdx.x);
+    }
+    __syncthreads();
+    RrrTab R;
+    R.inv = inv;
+    R.cbase = cbase;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t p = pos[i];
+        int32_t rk = 0, bit = 0, st = 0;
+        if (p < 0) {  // :360-362 / :316-323
+            st = 11;
+        } else if ((uint32_t)p >= ix.length) {
+            rk = (int32_t)ix.s_total_ones;
+            st = 11;
+        } else {
+            uint32_t b = 0, r = 0;
+            const Rec32 G = ld256(sg_addr(ix, (uint32_t)p));
+            sampled_access_rank(ix, R, G, (uint32_t)p, &b, &r);
+            rk = (int32_t)r;
+            bit = (int32_t)b;
+        }
+        rank_out[i] = rk;
+        access_out[i] = bit;
+        status[i] = st;
     }
 }
 

@@ -32,6 +32,7 @@ _MESSAGES = {
     8: "Extraction does not fit in the supplied destination. Currently extracted: {n}",
     9: "ArrayIndexOutOfBoundsException",
     10: "Found a character that exceeds (32767): it was {n}",
+    11: "Out of range access",
 }
 
 
@@ -54,7 +55,7 @@ class FmIndexOutOfBounds(FmIndexError, IndexError):
 
 def raise_status(status: int, n: int = 0):
     msg = _MESSAGES.get(int(status), "status %d" % status).format(n=int(n))
-    if status in (6, 7):
+    if status in (6, 7, 11):
         raise FmIndexIllegalArgument(msg, int(status), int(n))
     if status == 9:
         raise FmIndexOutOfBounds(msg, int(status), int(n))
@@ -94,6 +95,9 @@ def native():
         L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp, vp]
+        L.fmgpu_wavelet_load_serialized.argtypes = [vp, u64, vp, vp]
+        L.fmgpu_rrr_load_serialized.argtypes = [vp, u64, vp, vp]
+        L.fmgpu_rrr_rank_access_batch.argtypes = [vp, vp, u32, vp, vp, vp]
         L.fmgpu_wavelet_rank_batch.argtypes = [vp, vp, vp, u32, vp, vp]
         L.fmgpu_wavelet_inverse_select_batch.argtypes = [vp, vp, u32, vp, vp]
         L.fmgpu_last_stats.argtypes = [vp, vp]

@@ -9,6 +9,8 @@ import pytest
 
 from conftest import CASE_NAMES, get_case, make_patterns
 
+import pyoracle
+
 pytestmark = pytest.mark.gpu
 
 
