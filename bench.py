@@ -77,23 +77,22 @@ def get_index_blob(n: int, sr: int, text_holder: dict, use_gpu_sa: bool = True) 
     if os.path.exists(p):
         with open(p, "rb") as fh:
             return fh.read()
-    from index4j_b200.builder import build_index, map_text
+    from index4j_b200.builder import build_index
     t0 = time.time()
     text = text_holder.get("text")
     if text is None:
         text = text_holder["text"] = get_text(n)
-    sa = None
+    blob = None
     if use_gpu_sa:
         import torch
         if torch.cuda.is_available():
-            from index4j_b200.gpu_sa import suffix_array
-            codes, sigma = map_text(text)
-            sa = suffix_array(codes, sigma, device="cuda", verbose=True)
-            del codes
+            # suffix array, BWT and sampled structures on the GPU (index4j_b200/gpu_sa.py, csrc/kernels_build.cuh); the host encodes
+            # the wavelet structure / RRR vector and serializes
+            from index4j_b200.gpu_sa import build_index_gpu
+            blob = build_index_gpu(text, sr, True, framed=False, verbose=True)
             torch.cuda.empty_cache()
-    log("suffix array ready after %.1fs" % (time.time() - t0))
-    blob = build_index(text, sr, True, framed=False, verbose=True, suffix_array=sa)
-    del sa
+    if blob is None:
+        blob = build_index(text, sr, True, framed=False, verbose=True)
     tmp = p + ".tmp%d" % os.getpid()
     with open(tmp, "wb") as fh:
         fh.write(blob)

@@ -155,6 +155,16 @@ int fmgpu_rrr_rank_access_batch(fmgpu_index* idx, const int32_t* pos, uint32_t n
 int fmgpu_wavelet_rank_batch(fmgpu_index* idx, const int64_t* pos, const int32_t* sym, uint32_t n, int64_t* out, int32_t* status_out);
 int fmgpu_wavelet_inverse_select_batch(fmgpu_index* idx, const int64_t* pos, uint32_t n, int64_t* out, int32_t* status_out);
 
+/* Index PRODUCTION, device stage (not a query-path call): from the suffix array of (alphabet codes + sentinel),
+ * both already in device memory, to the pieces the FmIndex constructor derives from it (FM:343-394): the BWT
+ * (d_bwt_out[length]), the sampled-row marks (one bit per row, LSB first, d_mask_words_out[(length+31)/32]), the SA samples in
+ * row order (d_suffixes_out, *n_sampled_out of them) and the inverse-SA samples with the wrap entry (d_positions_out[length /
+ * sample_rate + 2], may be NULL).  Synchronizes the stream.  The host-side producer (index4j_b200/csrc/host) encodes and
+ * serializes them. */
+int fmgpu_build_bwt_samples_device(const uint16_t* d_codes, const int32_t* d_sa, int64_t length, int32_t sample_rate, uint16_t* d_bwt_out,
+                                   uint32_t* d_mask_words_out, int32_t* d_suffixes_out, int64_t suffixes_cap, int32_t* d_positions_out,
+                                   int64_t* n_sampled_out, void* cuda_stream);
+
 /* Work counters of the most recent batch call on this index (device-side counted, read back here):
  * [0] rank queries that touched memory  [1] wavelet levels walked by rank queries
  * [2] LF steps (inverseSelect walks)     [3] wavelet levels walked by LF steps

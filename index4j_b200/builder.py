@@ -29,6 +29,8 @@ def _host():
                                      C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         lib.fmhost_build_with_sa.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                              C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        lib.fmhost_build_with_parts.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32,
+                                                C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
         lib.fmhost_free.argtypes = [C.c_void_p]
         lib.fmhost_map_text.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         lib.fmhost_map_text.restype = C.c_int32
@@ -105,6 +107,36 @@ def build_index(text, sample_rate: int = 32, enable_extraction: bool = True, fra
         msg = lib.fmhost_last_error().decode()
         if "more than" in msg:
             raise ValueError(msg)  # IllegalArgumentException, FmIndex.java:423-426
+        raise RuntimeError(msg)
+    try:
+        return C.string_at(out, n.value)
+    finally:
+        lib.fmhost_free(out)
+
+
+def build_index_from_parts(text, bwt, mask_words, suffixes, positions, sample_rate: int = 32, enable_extraction: bool = True,
+                           framed: bool = True, threads: int = 0, verbose: bool = False) -> bytes:
+    """Serialized ``FmIndex`` from the pieces the device stage produced (``fmgpu_build_bwt_samples_device``): the BWT over
+    alphabet codes, the sampled-row marks (uint32 words, LSB first), the SA samples in row order and the inverse-SA samples."""
+    lib = _host()
+    t = as_chars(text)
+    bwt = np.ascontiguousarray(bwt, dtype=np.uint16)
+    mask_words = np.ascontiguousarray(mask_words, dtype=np.uint32)
+    suffixes = np.ascontiguousarray(suffixes, dtype=np.int32)
+    assert bwt.size == t.size + 1 and mask_words.size >= (t.size + 1 + 31) // 32
+    pos_ptr = None
+    if enable_extraction:
+        positions = np.ascontiguousarray(positions, dtype=np.int32)
+        assert positions.size == (t.size + 1) // sample_rate + 2
+        pos_ptr = positions.ctypes.data
+    out = C.c_void_p()
+    n = C.c_uint64()
+    rc = lib.fmhost_build_with_parts(t.ctypes.data, t.size, bwt.ctypes.data, mask_words.ctypes.data, suffixes.ctypes.data, suffixes.size,
+                                     pos_ptr, sample_rate, int(enable_extraction), int(framed), threads, int(verbose), C.byref(out), C.byref(n))
+    if rc != 0:
+        msg = lib.fmhost_last_error().decode()
+        if "more than" in msg:
+            raise ValueError(msg)
         raise RuntimeError(msg)
     try:
         return C.string_at(out, n.value)

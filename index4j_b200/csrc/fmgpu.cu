@@ -19,6 +19,7 @@
 #include "kernels_locate.cuh"
 #include "kernels_utf8.cuh"
 #include "kernels_wavelet.cuh"
+#include "kernels_build.cuh"
 #include "layout.h"
 
 using namespace fmgpu;
@@ -241,6 +242,7 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
 
 #include "api_lf.inc"
 #include "api_wavelet.inc"
+#include "api_build.inc"
 
 extern "C" {
 

@@ -163,9 +163,20 @@ double now_s() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-// Build from text; if sa_in != nullptr it must be the suffix array of (mapped text + sentinel).
+// Pieces of the constructor computed elsewhere (on the GPU, fmgpu_build_bwt_samples_device): the BWT over alphabet codes, the
+// sampled-row marks (one bit per row, LSB first), the SA samples in row order and the inverse-SA samples incl. the wrap entry.
+struct BuildParts {
+    const uint16_t* bwt = nullptr;
+    const uint32_t* mask_words = nullptr;
+    const int32_t* suffixes = nullptr;
+    int64_t n_suffixes = 0;
+    const int32_t* positions = nullptr;  // length / sampleRate + 2 entries (enable_extract)
+};
+
+// Build from text; if sa_in != nullptr it must be the suffix array of (mapped text + sentinel); with `parts` neither a suffix
+// array nor the text passes over it are needed.
 int build_index(const uint16_t* text, int64_t n, int sample_rate, int enable_extract, int framed,
-                int threads, const int32_t* sa_in, int verbose, std::vector<uint8_t>& out_bytes) {
+                int threads, const int32_t* sa_in, int verbose, std::vector<uint8_t>& out_bytes, const BuildParts* parts = nullptr) {
     if (n < 1) {
         g_err = "text must have at least one char";
         return -1;
@@ -216,16 +227,24 @@ int build_index(const uint16_t* text, int64_t n, int sample_rate, int enable_ext
         g_err = "Input has more than 32767 different symbols";
         return -1;
     }
-    std::vector<uint16_t> mapped((size_t)length);
-    for (int64_t i = 0; i < n; ++i) mapped[(size_t)i] = (uint16_t)code_of[text[i]];
-    mapped[(size_t)n] = 0;
+    std::vector<uint16_t> mapped;
+    if (!parts) {
+        mapped.resize((size_t)length);
+        for (int64_t i = 0; i < n; ++i) mapped[(size_t)i] = (uint16_t)code_of[text[i]];
+        mapped[(size_t)n] = 0;
+    }
 
     // --- cumulative counts (:307-327)
     const int32_t n_lookup = (int32_t)lookup.size();
     std::vector<int32_t> C((size_t)n_lookup + 1, 0);
     {
         std::vector<int64_t> cnt((size_t)n_lookup, 0);
-        for (int64_t i = 0; i < length; ++i) cnt[mapped[(size_t)i]]++;
+        if (parts) {
+            for (int64_t i = 0; i < n; ++i) cnt[(size_t)code_of[text[i]]]++;
+            cnt[0]++;  // the sentinel
+        } else {
+            for (int64_t i = 0; i < length; ++i) cnt[mapped[(size_t)i]]++;
+        }
         int64_t acc = 0;
         for (int32_t c = 0; c < n_lookup; ++c) {
             C[(size_t)c] = (int32_t)acc;
@@ -237,7 +256,7 @@ int build_index(const uint16_t* text, int64_t n, int sample_rate, int enable_ext
     // --- suffix array
     std::vector<int32_t> sa_store;
     const int32_t* SA = sa_in;
-    if (!SA) {
+    if (!SA && !parts) {
         sa_store.resize((size_t)length);
         suffix_array<uint16_t>(mapped.data(), sa_store.data(), (int32_t)length, n_codes);
         SA = sa_store.data();
@@ -251,7 +270,21 @@ int build_index(const uint16_t* text, int64_t n, int sample_rate, int enable_ext
     if (enable_extract) positions.init(length / sample_rate + 2, bw);
     BitString sampled;
     sampled.resize((uint64_t)length);
-    {
+    if (parts) {
+        if (parts->n_suffixes != (length - 1) / sample_rate + 1 || parts->n_suffixes > suffixes.length) {
+            g_err = "sampled-row count does not match the text length";
+            return -1;
+        }
+        for (int64_t k = 0; k < parts->n_suffixes; ++k) suffixes.set(k, (uint64_t)(uint32_t)parts->suffixes[k]);
+        if (enable_extract) {
+            if (!parts->positions) {
+                g_err = "inverse-SA samples missing";
+                return -1;
+            }
+            for (int64_t k = 0; k < positions.length; ++k) positions.set(k, (uint64_t)(uint32_t)parts->positions[k]);
+        }
+        sampled.from_words32(parts->mask_words, (uint64_t)length);
+    } else {
         int64_t k = 0;
         for (int64_t i = 0; i < length; ++i) {
             int32_t p = SA[i];
@@ -269,9 +302,13 @@ int build_index(const uint16_t* text, int64_t n, int sample_rate, int enable_ext
 
     // --- BWT (:374-394)
     std::vector<uint16_t> bwt((size_t)length);
-    for (int64_t i = 0; i < length; ++i) {
-        int32_t p = SA[i];
-        bwt[(size_t)i] = p == 0 ? mapped[(size_t)(length - 1)] : mapped[(size_t)(p - 1)];
+    if (parts) {
+        memcpy(bwt.data(), parts->bwt, (size_t)length * 2);
+    } else {
+        for (int64_t i = 0; i < length; ++i) {
+            int32_t p = SA[i];
+            bwt[(size_t)i] = p == 0 ? mapped[(size_t)(length - 1)] : mapped[(size_t)(p - 1)];
+        }
     }
     sa_store = std::vector<int32_t>();
     mapped = std::vector<uint16_t>();
@@ -361,6 +398,31 @@ int fmhost_build_with_sa(const uint16_t* text, int64_t n, const int32_t* sa, int
     std::vector<uint8_t> bytes;
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
     int rc = build_index(text, n, sample_rate, enable_extract, framed, threads, sa, verbose, bytes);
+    if (rc) return rc;
+    *out = (uint8_t*)malloc(bytes.size());
+    if (!*out) {
+        g_err = "out of memory";
+        return -2;
+    }
+    memcpy(*out, bytes.data(), bytes.size());
+    *out_len = bytes.size();
+    return 0;
+}
+
+// Same, from the pieces the device stage produced (fmgpu_build_bwt_samples_device, include/fmgpu.h): no suffix array crosses
+// to the host.  `text` is still needed for the alphabet map and the cumulative counts.
+int fmhost_build_with_parts(const uint16_t* text, int64_t n, const uint16_t* bwt, const uint32_t* mask_words, const int32_t* suffixes,
+                            int64_t n_suffixes, const int32_t* positions, int32_t sample_rate, int32_t enable_extract, int32_t framed,
+                            int32_t threads, int32_t verbose, uint8_t** out, uint64_t* out_len) {
+    std::vector<uint8_t> bytes;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    BuildParts parts;
+    parts.bwt = bwt;
+    parts.mask_words = mask_words;
+    parts.suffixes = suffixes;
+    parts.n_suffixes = n_suffixes;
+    parts.positions = positions;
+    int rc = build_index(text, n, sample_rate, enable_extract, framed, threads, nullptr, verbose, bytes, &parts);
     if (rc) return rc;
     *out = (uint8_t*)malloc(bytes.size());
     if (!*out) {

@@ -27,6 +27,13 @@ struct BitString {
         w.assign((n + 63) / 64 + 1, 0);  // +1 slack word so straddling reads never fault
     }
     inline void set1(uint64_t i) { w[i >> 6] |= 1ULL << (i & 63); }
+    // n bits from 32-bit words (bit k of the string = bit k % 32 of word k / 32); bits past n are dropped
+    void from_words32(const uint32_t* words, uint64_t n) {
+        resize(n);
+        const uint64_t nw32 = (n + 31) / 32;
+        for (uint64_t k = 0; k < nw32; ++k) w[k >> 1] |= (uint64_t)words[k] << (32 * (k & 1));
+        if (n & 63) w[n >> 6] &= (1ULL << (n & 63)) - 1;
+    }
     inline bool get(uint64_t i) const { return (w[i >> 6] >> (i & 63)) & 1; }
     // read `len` (<= 57) bits starting at bit i
     inline uint64_t get_bits(uint64_t i, int len) const {
