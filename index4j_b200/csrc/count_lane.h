@@ -17,7 +17,7 @@
 
 #include "lane_logic.h"
 
-// 1 = speculative root fetch (experiment knob, tools/variants_v5.sh).  Measured on B200 (profiles/experiments): the fused
+// 1 = speculative root fetch (experiment knob, tools/gpu_v5_cycle.sh).  Measured on B200 (profiles/experiments): the fused
 // two-track walk alone runs the configs[1] batch at 895 M patterns/s, with the speculative fetch on top 790-826 M/s although
 // only 1.65 M of the ~45 M speculative loads per launch are wasted: k_count is bound by issued instructions at 14/32 lane
 // utilisation, not by the cell -> record latency chain, and the directory lookups add instructions.  Default off.
@@ -34,26 +34,11 @@
 
 namespace fmgpu {
 
-struct CountTables {  // SmemTables + the root-record directory (shared memory when it fits)
-    const uint32_t* C;
-    const SbDesc* sb;
-    const U32x2* sbroot;
-    const U32x2* blkmap;
-};
+using CountTables = SmemTables;  // C, superblock descriptors, root-record directory
 
 struct CountCounters {
     uint32_t ranks, levels, loads, recs, spec_wasted;
 };
-
-// root level record of (superblock sbi, block blk), or false when the block has no tree (single-symbol block, or the
-// extra row of position == size)
-FMGPU_HD bool root_record(const CountTables& T, uint32_t sbi, uint32_t blk, uint32_t* rec) {
-    const U32x2 m = T.blkmap[blk >> 5];
-    const uint32_t bit = blk & 31u;
-    const U32x2 sr = T.sbroot[sbi];
-    *rec = sr.x + (m.y + popc32(m.x & ((1u << bit) - 1u))) * sr.y;
-    return ((m.x >> bit) & 1u) != 0u;
-}
 
 struct Track {
     uint32_t base, code, len, r;  // boundary rank; Huffman code left-aligned (bit 31 = next decision); levels left; position

@@ -26,34 +26,42 @@ constexpr int PIPE_CTA_THREADS = COUNT_THREADS >= 128 ? COUNT_THREADS - 64 : COU
 constexpr uint32_t SMEM_C_MAX = 4096;   // entries of C kept in shared memory
 constexpr uint32_t SMEM_SB_MAX = 2048;  // superblock descriptors kept in shared memory
 
-// Index tables small enough for shared memory (C array, superblock descriptors).
-__device__ __forceinline__ SmemTables stage_tables(const DevIndex& ix, uint32_t* smem) {
+// Index tables small enough for shared memory: C array, superblock descriptors and — with ROOTS — the root-record directory
+// (layout.h) that the speculative root fetches need.
+constexpr uint32_t SMEM_BLKMAP_MAX = 8192;  // blkmap entries (32 blocks each) kept in shared memory
+template <bool ROOTS>
+__device__ __forceinline__ SmemTables stage_tables_t(const DevIndex& ix, uint32_t* smem) {
     SmemTables t;
     uint32_t used = 0;
-    if (ix.n_c <= SMEM_C_MAX) {
-        for (uint32_t i = threadIdx.x; i < ix.n_c; i += blockDim.x) smem[i] = ix.C[i];
-        t.C = smem;
-        used = ix.n_c;
-    } else {
-        t.C = ix.C;
-    }
-    if (ix.n_sb <= SMEM_SB_MAX) {
+    auto stage = [&](const uint32_t* src, uint32_t words, bool fits) -> const uint32_t* {
+        if (!fits) return src;
         uint32_t* d = smem + used;
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(ix.sb);
-        for (uint32_t i = threadIdx.x; i < 2 * ix.n_sb; i += blockDim.x) d[i] = s[i];
-        t.sb = reinterpret_cast<const SbDesc*>(d);
-    } else {
-        t.sb = ix.sb;
+        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) d[i] = src[i];
+        used += (words + 1u) & ~1u;  // keep 8-byte alignment for the 64-bit entries
+        return d;
+    };
+    t.C = stage(ix.C, ix.n_c, ix.n_c <= SMEM_C_MAX);
+    t.sb = reinterpret_cast<const SbDesc*>(stage(reinterpret_cast<const uint32_t*>(ix.sb), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
+    t.sbroot = ix.sbroot;
+    t.blkmap = ix.blkmap;
+    if (ROOTS) {
+        t.sbroot = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.sbroot), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
+        t.blkmap = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.blkmap), 2 * ix.n_blkmap, ix.n_blkmap <= SMEM_BLKMAP_MAX));
     }
     __syncthreads();
     return t;
 }
-inline size_t tables_smem_bytes(const DevIndex& ix) {
+template <bool ROOTS>
+inline size_t tables_smem_bytes_t(const DevIndex& ix) {
     size_t n = 0;
-    if (ix.n_c <= SMEM_C_MAX) n += ix.n_c;
-    if (ix.n_sb <= SMEM_SB_MAX) n += 2 * (size_t)ix.n_sb;
+    if (ix.n_c <= SMEM_C_MAX) n += (ix.n_c + 1u) & ~1u;
+    if (ix.n_sb <= SMEM_SB_MAX) n += (ROOTS ? 4 : 2) * (size_t)ix.n_sb;
+    if (ROOTS && ix.n_blkmap <= SMEM_BLKMAP_MAX) n += 2 * (size_t)ix.n_blkmap;
     return n * 4 + 16;
 }
+constexpr size_t TABLES_SMEM_MAX_BYTES = (SMEM_C_MAX + 4 * (size_t)SMEM_SB_MAX + 2 * (size_t)SMEM_BLKMAP_MAX) * 4 + 16;
+__device__ __forceinline__ SmemTables stage_tables(const DevIndex& ix, uint32_t* smem) { return stage_tables_t<false>(ix, smem); }
+inline size_t tables_smem_bytes(const DevIndex& ix) { return tables_smem_bytes_t<false>(ix); }
 
 // ---------------------------------------------------------------------------------------------
 // Pre-pass: one descriptor per pattern (offset, length, alphabet code of the last char =
@@ -155,39 +163,9 @@ __global__ void __launch_bounds__(256, 8) k_len_scatter(const PatDesc* __restric
 // than the lane state machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...); the price is that a step
 // lasts as long as its deepest walk.
 // ---------------------------------------------------------------------------------------------
-constexpr uint32_t SMEM_BLKMAP_MAX = 8192;  // blkmap entries (32 blocks each) kept in shared memory
-
-// C, superblock descriptors and the root-record directory, in shared memory when they fit
-__device__ __forceinline__ CountTables stage_count_tables(const DevIndex& ix, uint32_t* smem) {
-    CountTables t;
-    uint32_t used = 0;
-    auto stage = [&](const uint32_t* src, uint32_t words, bool fits) -> const uint32_t* {
-        if (!fits) return src;
-        uint32_t* d = smem + used;
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) d[i] = src[i];
-        used += (words + 1u) & ~1u;  // keep 8-byte alignment for the 64-bit entries
-        return d;
-    };
-    t.C = stage(ix.C, ix.n_c, ix.n_c <= SMEM_C_MAX);
-    t.sb = reinterpret_cast<const SbDesc*>(stage(reinterpret_cast<const uint32_t*>(ix.sb), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
-#if COUNT_SPEC_ROOT
-    t.sbroot = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.sbroot), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
-    t.blkmap = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.blkmap), 2 * ix.n_blkmap, ix.n_blkmap <= SMEM_BLKMAP_MAX));
-#else
-    t.sbroot = ix.sbroot;
-    t.blkmap = ix.blkmap;
-#endif
-    __syncthreads();
-    return t;
-}
-constexpr size_t COUNT_SMEM_MAX_BYTES = (SMEM_C_MAX + 4 * (size_t)SMEM_SB_MAX + 2 * (size_t)SMEM_BLKMAP_MAX) * 4 + 16;
-inline size_t count_smem_bytes(const DevIndex& ix) {
-    size_t n = 0;
-    if (ix.n_c <= SMEM_C_MAX) n += (ix.n_c + 1u) & ~1u;
-    if (ix.n_sb <= SMEM_SB_MAX) n += (COUNT_SPEC_ROOT ? 4 : 2) * (size_t)ix.n_sb;
-    if (COUNT_SPEC_ROOT && ix.n_blkmap <= SMEM_BLKMAP_MAX) n += 2 * (size_t)ix.n_blkmap;
-    return n * 4 + 16;
-}
+__device__ __forceinline__ CountTables stage_count_tables(const DevIndex& ix, uint32_t* smem) { return stage_tables_t<COUNT_SPEC_ROOT != 0>(ix, smem); }
+constexpr size_t COUNT_SMEM_MAX_BYTES = TABLES_SMEM_MAX_BYTES;
+inline size_t count_smem_bytes(const DevIndex& ix) { return tables_smem_bytes_t<COUNT_SPEC_ROOT != 0>(ix); }
 
 #ifndef COUNT_MIN_CTAS
 #define COUNT_MIN_CTAS 2

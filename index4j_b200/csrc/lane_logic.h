@@ -51,10 +51,22 @@ FMGPU_HD uint32_t low_mask_clamped(int width) {
 #endif
 }
 
-struct SmemTables {  // C array and superblock descriptors (shared memory when they fit)
+struct SmemTables {  // C array, superblock descriptors and the root-record directory (shared memory when they fit)
     const uint32_t* C;
     const SbDesc* sb;
+    const U32x2* sbroot;
+    const U32x2* blkmap;
 };
+
+// root level record of (superblock sbi, block blk) from the root-record directory (layout.h), or false when the block has
+// no tree (single-symbol block, or the extra row of position == size)
+FMGPU_HD bool root_record(const SmemTables& T, uint32_t sbi, uint32_t blk, uint32_t* rec) {
+    const U32x2 m = T.blkmap[blk >> 5];
+    const uint32_t bit = blk & 31u;
+    const U32x2 sr = T.sbroot[sbi];
+    *rec = sr.x + (m.y + popc32(m.x & ((1u << bit) - 1u))) * sr.y;
+    return ((m.x >> bit) & 1u) != 0u;
+}
 
 // ------------------------------------------------------------------------------------------
 // level records (layout.h): two tree levels from one 64-byte record

@@ -82,6 +82,8 @@ int fc_load(const uint8_t* buf, uint64_t len, int threads, void** out) {
         h->ix.blkmap = h->F.blkmap.data();
         h->T.C = h->ix.C;
         h->T.sb = h->ix.sb;
+        h->T.sbroot = h->ix.sbroot;
+        h->T.blkmap = h->ix.blkmap;
         h->CT.C = h->ix.C;
         h->CT.sb = h->ix.sb;
         h->CT.sbroot = h->ix.sbroot;
