@@ -138,11 +138,16 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
 // k_extract<MODE> — LF walks of FmIndex.extract (fm/FmIndex.java:564-608) and extractUntilBoundary{,Left,Right}
 // (:640-922), warp-lockstep: one lane = one extraction, every trip each live lane takes one LF step (preceded by
 // the ISA-sample fetch when a walk starts) and hands the char to ExLane::on_char (lf_lane.h).
+// 576 threads x 2 CTAs = 36 warps/SM at 56 registers (measured: extractUntilBoundary 5.09 ms per 1 M records vs 5.35 ms at
+// 256 x 4 / 63 registers, 5.33 ms at 640 x 2 / 48 registers with spills)
 #ifndef EXTRACT_THREADS
-#define EXTRACT_THREADS 256
+#define EXTRACT_THREADS 576
+#endif
+#ifndef EXTRACT_MIN_CTAS
+#define EXTRACT_MIN_CTAS 2
 #endif
 template <int MODE, bool STATS>
-__global__ void __launch_bounds__(EXTRACT_THREADS)
+__global__ void __launch_bounds__(EXTRACT_THREADS, EXTRACT_MIN_CTAS)
 k_extract(const DevIndex ix, WalkParams P, uint32_t chunk, unsigned int* queue, unsigned long long* stats) {
     extern __shared__ uint32_t smem[];
     const SmemTables T = stage_tables(ix, smem);  // ends with __syncthreads()
