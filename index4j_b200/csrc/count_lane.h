@@ -159,8 +159,11 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
             if (STATS) cnt.loads += (go_b ? 1u : 0u) + (go_a ? 1u : 0u);
         }
     }
-    *sp = on_a ? A.base + A.r : 0u;
-    *ep = B.base + B.r;
+    // a rank never exceeds the number of positions; the clamp only matters for a corrupt (but loadable) index, whose
+    // boundary ranks could otherwise send the next step outside the directories
+    const uint32_t va = A.base + A.r, vb = B.base + B.r;
+    *sp = on_a ? (va < ix.length ? va : ix.length) : 0u;
+    *ep = vb < ix.length ? vb : ix.length;
     return err;
 }
 

@@ -140,7 +140,8 @@ struct VarReader {
     }
 };
 
-inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_block_size, BlockTree& T) {
+// `sigma`: the wavelet alphabet size — header symbols must lie below it (the kernels index C[] and the rank directories with them)
+inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_block_size, BlockTree& T, int32_t sigma) {
     const BlockHdr& H = S.blocks[b];
     const int h = H.tree_height;
     const int sig = (int)H.sigma_m1 + 1;
@@ -163,6 +164,8 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
         T.brank[(size_t)i] = R.u24(ptr32 + 5 * (int64_t)i + 2);
     }
     if (!R.ok) throw FormatError("variable block header truncated");
+    for (int i = 0; i < sig; ++i)
+        if ((int32_t)T.sym[(size_t)i] >= sigma) throw FormatError("block header symbol outside the alphabet");
     if (h == 0) return;  // run block: no tree
     if (sig < 2) throw FormatError("tree block with a single symbol");
     T.leaves.resize((size_t)sig);
@@ -320,7 +323,7 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
     std::vector<uint64_t> block_node_base(nblk, 0), block_ovf_base(nblk, 0);
     for (size_t b = 0; b < nblk; ++b) {
         BlockTree& T = trees[b];
-        build_block_tree(S, b, sb_block_size(W, sb, b), T);
+        build_block_tree(S, b, sb_block_size(W, sb, b), T, W.sigma);
         Rec32& D = F.blocks[(size_t)P.first_block + b];
         memset(&D, 0, sizeof D);
         if (T.h == 0) {
@@ -577,16 +580,23 @@ inline void flatten_sampled(const RrrStream& r, FlatIndex& F) {
         ones += go;
         if (bitpos > 0xffffffffULL) throw FormatError("sampled-row offset stream exceeds 2^32 bits");
     }
+    if (bitpos > (uint64_t)(r.offsets.size() - 1) * 64) throw FormatError("RrrVector offset stream shorter than its classes need");
+    if (ones != (uint64_t)(uint32_t)r.total_ones) throw FormatError("RrrVector totalOnes differs from the sum of its block classes");
     // offset stream verbatim (LSB-first 64-bit words == little-endian 32-bit word pairs), padded
     const size_t nw64 = r.offsets.size();
     F.soffsets.assign(nw64 * 2 + 16, 0);
     memcpy(F.soffsets.data(), r.offsets.data(), nw64 * 8);
 }
 
-inline void unpack_samples(const PackedInts& v, std::vector<Rec32>& out) {
+// `limit`: every sample must lie below it (the LF kernels use inverse-SA samples as rows, SA samples are results)
+inline void unpack_samples(const PackedInts& v, std::vector<Rec32>& out, uint64_t limit, const char* what) {
     const size_t n = (size_t)v.length;
     out.assign(n / 8 + 1, Rec32{});
-    for (size_t i = 0; i < n; ++i) out[i / 8].w[i % 8] = (uint32_t)v.get((int64_t)i);
+    for (size_t i = 0; i < n; ++i) {
+        const uint64_t x = (uint64_t)v.get((int64_t)i);
+        if (x >= limit) throw FormatError(std::string(what) + " sample outside the index");
+        out[i / 8].w[i % 8] = (uint32_t)x;
+    }
 }
 
 // budget for the dense (block x symbol) cell table; beyond it the index is rejected for now
@@ -618,6 +628,14 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
     for (size_t i = 0; i < fm.lookup.size(); ++i) F.code2char[i] = (uint16_t)fm.lookup[i];
     for (const auto& kv : fm.map)
         if (kv.second < 0 || (size_t)kv.second + 1 >= fm.C.size()) throw FormatError("alphabet code outside cumulativeCounts");
+    if (!wavelet_only) {
+        // cumulativeCounts (fm/FmIndex.java:307-327): SA ranges of the symbol codes — non-decreasing, inside [0, length], one
+        // entry beyond the last wavelet symbol (the kernels form C[sym] and C[sym + 1] for every symbol the wavelet can return)
+        if (fm.C.size() < (size_t)W.sigma + 1) throw FormatError("cumulativeCounts shorter than the wavelet alphabet");
+        for (size_t i = 0; i < fm.C.size(); ++i)
+            if (fm.C[i] < 0 || (int64_t)fm.C[i] > (int64_t)fm.length || (i && fm.C[i] < fm.C[i - 1]))
+                throw FormatError("cumulativeCounts not a non-decreasing sequence inside the index");
+    }
 
     // pass 1: sizes
     const size_t nsb = W.sbs.size();
@@ -635,7 +653,7 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
         P.has_tree.assign(P.rows, 0);
         BlockTree T;
         for (size_t b = 0; b < S.blocks.size(); ++b) {
-            build_block_tree(S, b, sb_block_size(W, sb, b), T);
+            build_block_tree(S, b, sb_block_size(W, sb, b), T, W.sigma);
             if (T.h != 0) {
                 P.has_tree[b] = 1;
                 ++P.n_tree_blocks;
@@ -709,8 +727,9 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
         return;
     }
     flatten_sampled(fm.sampled, F);
-    unpack_samples(fm.suffixes, F.sa);
-    if (fm.enable_extract) unpack_samples(fm.positions, F.isa);
+    if ((uint64_t)(uint32_t)fm.sampled.total_ones > (uint64_t)fm.suffixes.length) throw FormatError("more sampled rows than suffix-array samples");
+    unpack_samples(fm.suffixes, F.sa, (uint64_t)fm.length, "suffix-array");
+    if (fm.enable_extract) unpack_samples(fm.positions, F.isa, (uint64_t)fm.length, "inverse suffix-array");
     else F.isa.assign(1, Rec32{});
 }
 

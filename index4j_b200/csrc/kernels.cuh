@@ -260,6 +260,7 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
                 } else {
                     sp = T.C[c] + val_s;  // :469-470
                     ep = T.C[c] + val_e;
+                    ep = ep < ix.length ? ep : ix.length;  // no-op on a consistent index (see count_step)
                 }
             }
         }

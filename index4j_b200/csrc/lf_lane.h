@@ -65,7 +65,7 @@ FMGPU_HD void sampled_access_rank(const DevIndex& ix, const RrrTab& R, const Rec
     const uint32_t hi = FMGPU_LDG32(ix.soffsets + wi + 1u);  // the stream is padded
     const unsigned long long both = ((unsigned long long)hi << 32) | lo;
     const uint32_t off = (uint32_t)(both >> sh) & ((1u << nb) - 1u);
-    const uint32_t block = R.inv[(uint32_t)R.cbase[cls] + off];
+    const uint32_t block = R.inv[((uint32_t)R.cbase[cls] + off) & 32767u];  // the mask only matters for a corrupt offset
     *bit = (block >> use) & 1u;
     *rank = ones + popc32(block & ((1u << use) - 1u));
 }
@@ -121,7 +121,9 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
             return j;
         }
     }
-    return T.C[sym] + rank_j;
+    // 1 <= LF(j) <= length - 1 on a consistent index; the clamps keep a corrupt (but loadable) one inside the tables
+    const uint32_t jn = T.C[sym] + rank_j;
+    return jn == 0u ? 1u : (jn < ix.length ? jn : ix.length);
 }
 
 // ------------------------------------------------------------------------------------------------

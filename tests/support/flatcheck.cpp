@@ -164,6 +164,7 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
                     }
                     sp = h.ix.C[c] + a;
                     ep = h.ix.C[c] + b;
+                    ep = ep < h.ix.length ? ep : h.ix.length;
                 }
                 if (!zero && !st) result = ep > sp ? (int32_t)(ep - sp) : 0;
             }
