@@ -458,6 +458,16 @@ def main():
                     out["roofline"]["traffic"] = json.load(fh).get("dram_bytes_per_launch")
             except Exception:
                 pass
+        # north-star "fraction of the gather roofline": what the part sustains for dependent, uniformly random 32-byte sector
+        # reads (tools/gather_peak.cu -> profiles/r01_gather_peak.jsonl: 38-70 G sectors/s depending on the footprint) next to
+        # what k_count moves: record loads it issues, and DRAM sectors (ncu traffic of the committed capture / live kernel time)
+        t_s = kern_ms / 1e3
+        out["roofline"]["gather"] = {
+            "record_loads_per_s": stats["search_records_loaded"] / t_s,
+            "dram_sectors_per_s": (out["roofline"]["traffic"] / 32.0 / t_s) if out["roofline"]["traffic"] else None,
+            "uniform_random_sector_peak_per_s": [38e9, 70e9],
+            "note": "k_count runs above the uniform-random rate because cells hit L2 and neighbouring positions share DRAM rows",
+        }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, dt, cpu_counts, oracle_ix = cpu_count_throughput(blob, chars, off, args.cpu_sample, threads, args.cpu_repeats)

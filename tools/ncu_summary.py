@@ -41,6 +41,17 @@ def main():
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
         tot = rd * scale[units[hdr.index("dram__bytes_read.sum")]] + wr * scale[units[hdr.index("dram__bytes_write.sum")]]
         print("  dram_bytes_per_launch %.0f" % tot)
+        # derived: achieved HBM GB/s, 32-byte sectors per global-load request, DRAM sectors per second
+        tu = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "nsecond": 1e-9, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0}
+        ti = hdr.index("gpu__time_duration.sum")
+        secs = float(r[ti]) * tu.get(units[ti], 1e-9)
+        print("  derived: achieved_hbm_gb_per_s %.1f   dram_sectors_per_s %.1f G" % (tot / secs / 1e9, tot / 32.0 / secs / 1e9))
+        try:
+            req = float(r[hdr.index("l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum")])
+            sec = float(r[hdr.index("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum")])
+            print("  derived: sectors_per_global_load_request %.2f (32 lanes x 1 record = 32 when all lanes load distinct records)" % (sec / req))
+        except (ValueError, ZeroDivisionError):
+            pass
 
 
 if __name__ == "__main__":
