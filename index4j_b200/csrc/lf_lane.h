@@ -1,9 +1,10 @@
-// Straight-line per-lane code of one LF step and of the sampled-row test (locate v2, lockstep kernels).
+// Per-lane code of one LF step, of the sampled-row test and of the extract / extractUntilBoundary* work item (lockstep kernels
+// k_locate / k_extract).
 //
-// Unlike the lane state machine of walk_lane.h (one record per trip, every phase's code executed every
-// trip), these are plain sequential functions: a warp runs them for its 32 work items together and the
-// hardware reconverges the lanes after each data-dependent loop.  Host/device code: the kernels fetch
-// records with 256-bit loads, the host layout test (tests/support/flatcheck.cpp) with plain reads.
+// Plain sequential functions: a warp runs them for its 32 work items together and the hardware reconverges the lanes after
+// each data-dependent loop (the round-1 phase machine, which executed every phase's code every trip, needed ~6x more issued
+// instructions per LF step).  Host/device code: the kernels fetch records with 256-bit loads, the host layout test
+// (tests/support/flatcheck.cpp) with plain reads.
 //
 // Reference semantics (paths under indices/src/main/java/com/dynatrace/):
 //   sampled_access_rank  bitsequence/RrrVector.java:314-349 (access) and :358-396 (rankOnes)
@@ -128,9 +129,8 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
 
 // ------------------------------------------------------------------------------------------------
 // extract / extractUntilBoundary* work item of the lockstep kernel k_extract: the control flow around the LF
-// steps (fm/FmIndex.java:564-608, :640-759, :772-831, :844-922).  Same arithmetic as the phase machine of
-// walk_lane.h, expressed as "what happens after an LF step produced a char" so that every trip of the warp
-// loop is: [ISA sample if a walk starts] -> one LF step -> on_char().
+// steps (fm/FmIndex.java:564-608, :640-759, :772-831, :844-922), expressed as "what happens after an LF step produced a
+// char" so that every trip of the warp loop is: [ISA sample if a walk starts] -> one LF step -> on_char().
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 struct ExLane {
