@@ -439,7 +439,8 @@ def main():
                          "spec_root_loads_wasted_per_launch": stats.get("spec_root_wasted", 0),
                          "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3)},
-            "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob)},
+            "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob),
+                      "start_table_q": ix.start_table_q()},
         }
         if lf:
             out["locate"] = {"metric": "located hits/sec (max %d hits per pattern)" % args.max_hits, "value": all_hits / (loc_ms / 1e3),

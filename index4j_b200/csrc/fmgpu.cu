@@ -112,6 +112,7 @@ struct fmgpu_index {
     uint64_t last_launches = 0;
     bool stats_valid = false;
     bool count_stats = false;  // fmgpu_set_stats: backward-search kernel with work counters
+    bool use_kmer = true;      // fmgpu_set_start_table: patterns start from the q-gram start table when the index has one
     uint32_t stats_ctx_mask = 1;  // compute contexts whose counters belong to the most recent call
     // optional per-call timing of the dominant kernel (bench.py's roofline): ring of event pairs
     static constexpr int TIMING_SLOTS = 64;
@@ -200,11 +201,13 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
     unsigned int* ctrl = (unsigned int*)s_ctrl.p;
     // descriptors + length histogram, then a counting sort by length so that a warp's 32 patterns run in lockstep
     const int pre_grid = prepass_grid(n_pat, ix->sm_count);
+    const uint32_t kq = ix->use_kmer ? ix->dev.kmer_q : 0u;  // 0: every pattern starts from its last char
     if (u8)
         k_prepass_utf8<<<pre_grid, 256, 0, pre>>>(u8->d_bytes, d_pat_off, n_pat, ix->dev.char2code, u8->d_chars, (PatDesc*)s_pats.p,
-                                                 (uint32_t*)s_bins.p, u8->d_conv_status, u8->d_conv_value);
+                                                 (uint32_t*)s_bins.p, u8->d_conv_status, u8->d_conv_value, kq, ix->dev.kmer_stride, ix->dev.sigma);
     else
-        k_prepass<<<pre_grid, 256, 0, pre>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)s_pats.p, (uint32_t*)s_bins.p);
+        k_prepass<<<pre_grid, 256, 0, pre>>>(d_chars, d_pat_off, n_pat, ix->dev.char2code, (PatDesc*)s_pats.p, (uint32_t*)s_bins.p, kq,
+                                             ix->dev.kmer_stride, ix->dev.sigma);
     k_len_scan<<<1, SCAN_THREADS, 0, pre>>>((uint32_t*)s_bins.p);
     const int sc_grid = prepass_grid(((uint64_t)n_pat + SCATTER_PER_THREAD - 1) / SCATTER_PER_THREAD, ix->sm_count);
     k_len_scatter<<<sc_grid, 256, 0, pre>>>((const PatDesc*)s_pats.p, n_pat, (uint32_t*)s_bins.p, (uint32_t*)s_order.p);
@@ -235,6 +238,74 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
         ix->last_launches += 1;
     }
     CU(cudaGetLastError());
+    return 0;
+}
+
+// q-gram start table (layout.h): the search kernel itself computes, for every q-gram of alphabet codes, the SA range after its
+// q chars; q = the largest value with sigma^q entries <= 2^21 (q >= 2).  Built once per load (~1 ms of GPU time).
+int build_start_table(fmgpu_index* ix, const std::vector<uint16_t>& code2char, const std::vector<uint16_t>& char2code) {
+    if (const char* e = getenv("FMGPU_START_TABLE"))
+        if (atoi(e) == 0) return 0;
+    const uint64_t S = ix->dev.sigma;
+    if (S < 2 || S > 1448) return 0;
+    uint32_t q = 2;
+    while (q < 8 && [&] { uint64_t n = 1; for (uint32_t k = 0; k <= q; ++k) n *= S; return n; }() <= (1ull << 21)) ++q;
+    uint64_t n_entries = 1;
+    for (uint32_t k = 0; k < q; ++k) n_entries *= S;
+    // every q-gram of codes 1 .. S-1 that chars can spell; pattern text order = first-consumed char last
+    std::vector<uint32_t> idx_of;
+    std::vector<uint16_t> chars;
+    std::vector<uint32_t> codes(q);
+    for (uint64_t idx = 0; idx < n_entries; ++idx) {
+        uint64_t v = idx;
+        bool ok = true;
+        for (uint32_t k = 0; k < q; ++k) {  // codes[0] = last consumed ... codes[q-1] = the q-gram's last char
+            codes[k] = (uint32_t)(v % S);
+            v /= S;
+            if (codes[k] == 0 || codes[k] >= code2char.size() || char2code[code2char[codes[k]]] != codes[k]) ok = false;
+        }
+        if (!ok) continue;
+        idx_of.push_back((uint32_t)idx);
+        for (uint32_t k = 0; k < q; ++k) chars.push_back(code2char[codes[k]]);
+    }
+    const uint32_t n = (uint32_t)idx_of.size();
+    std::vector<U32x2> table((size_t)n_entries, U32x2{0xffffffffu, 0u});
+    if (n) {
+        std::vector<uint64_t> off((size_t)n + 1);
+        for (uint32_t i = 0; i <= n; ++i) off[i] = (uint64_t)i * q;
+        uint16_t* d_chars = nullptr;
+        uint64_t* d_off = nullptr;
+        int32_t *d_counts = nullptr, *d_status = nullptr;
+        uint32_t* d_ranges = nullptr;
+        cudaStream_t st = ix->stream;
+        CU(cudaMalloc((void**)&d_chars, chars.size() * 2));
+        CU(cudaMalloc((void**)&d_off, off.size() * 8));
+        CU(cudaMalloc((void**)&d_counts, (size_t)n * 4));
+        CU(cudaMalloc((void**)&d_status, (size_t)n * 4));
+        CU(cudaMalloc((void**)&d_ranges, (size_t)n * 8));
+        CU(cudaMemcpyAsync(d_chars, chars.data(), chars.size() * 2, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_off, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+        const bool was = ix->use_kmer;
+        ix->use_kmer = false;
+        int rc = count_on_stream(ix, d_chars, d_off, chars.size(), n, d_counts, d_status, d_ranges, st);
+        ix->use_kmer = was;
+        std::vector<int32_t> status(n);
+        std::vector<uint32_t> ranges((size_t)n * 2);
+        if (!rc) {
+            CU(cudaMemcpyAsync(status.data(), d_status, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(ranges.data(), d_ranges, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+        }
+        for (void* p : {(void*)d_chars, (void*)d_off, (void*)d_counts, (void*)d_status, (void*)d_ranges}) cudaFree(p);
+        if (rc) return rc;
+        for (uint32_t i = 0; i < n; ++i)
+            if (status[i] == 0) table[idx_of[i]] = U32x2{ranges[2 * (size_t)i], ranges[2 * (size_t)i + 1]};
+    }
+    int rc = upload(ix, table, &ix->dev.kmer, nullptr);
+    if (rc) return rc;
+    ix->dev.kmer_q = q;
+    ix->dev.kmer_stride = (uint32_t)S;
+    ix->stats_valid = false;
     return 0;
 }
 
@@ -364,6 +435,7 @@ int load_common(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_in
         const char* g = getenv("FMGPU_L2_FETCH");
         if (g && atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     }
+    if (!rc && kind == KIND_FM) rc = build_start_table(ix, F.code2char, F.char2code);
     if (rc) {
         fmgpu_index_free(ix);
         return rc;
@@ -563,6 +635,14 @@ int fmgpu_count_batch_utf8_device(fmgpu_index* ix, const uint8_t* d_bytes, const
     Utf8Src u8{d_bytes, (uint16_t*)ix->in_a.p, (int32_t*)ix->u8conv.p, (int32_t*)ix->u8conv.p + n_pat};
     return count_on_stream(ix, nullptr, d_pat_off, total_bytes, n_pat, d_counts_out, d_status_out, nullptr, (cudaStream_t)cuda_stream, true, 0, &u8);
 }
+
+int fmgpu_set_start_table(fmgpu_index* ix, int enable) {
+    if (!ix) return fail(FMGPU_ERR_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->use_kmer = enable != 0;
+    return 0;
+}
+int32_t fmgpu_start_table_q(const fmgpu_index* ix) { return ix ? (int32_t)ix->dev.kmer_q : -1; }
 
 int fmgpu_set_stats(fmgpu_index* ix, int enable) {
     if (!ix) return fail(FMGPU_ERR_ARG, "null argument");

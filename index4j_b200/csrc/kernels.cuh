@@ -71,9 +71,24 @@ inline size_t tables_smem_bytes(const DevIndex& ix) { return tables_smem_bytes_t
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t LEN_BINS = 1024;
 
+// PatDesc.last of a pattern whose chars end at chars[b - 1]: the code of its last char, or — when the index has a q-gram
+// start table, the pattern has at least q chars and its last q chars are all in the wavelet alphabet — the table index
+__device__ __forceinline__ uint32_t pattern_start(const uint16_t* chars, uint64_t b, uint32_t len,
+                                                  const uint16_t* __restrict__ char2code, uint32_t kmer_q, uint32_t kmer_stride, uint32_t sigma) {
+    const uint32_t last = (uint32_t)__ldg(char2code + chars[b - 1]);
+    if (kmer_q < 2u || len < kmer_q || last == 0u || last >= sigma) return last;
+    uint32_t idx = last;
+    for (uint32_t k = 1; k < kmer_q; ++k) {
+        const uint32_t c = (uint32_t)__ldg(char2code + chars[b - 1 - k]);
+        if (c == 0u || c >= sigma) return last;
+        idx = idx * kmer_stride + c;
+    }
+    return PAT_KMER | idx;
+}
+
 __global__ void __launch_bounds__(256) k_prepass(const uint16_t* __restrict__ chars, const uint64_t* __restrict__ pat_off, uint32_t n_pat,
                                                  const uint16_t* __restrict__ char2code, PatDesc* __restrict__ pats,
-                                                 uint32_t* __restrict__ bins) {
+                                                 uint32_t* __restrict__ bins, uint32_t kmer_q, uint32_t kmer_stride, uint32_t sigma) {
     __shared__ uint32_t h[LEN_BINS];
     for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x) h[i] = 0;
     __syncthreads();
@@ -82,7 +97,7 @@ __global__ void __launch_bounds__(256) k_prepass(const uint16_t* __restrict__ ch
         PatDesc d;
         d.off = a;
         d.len = b > a ? (uint32_t)(b - a) : 0u;
-        d.last = d.len ? (uint32_t)__ldg(char2code + chars[b - 1]) : 0u;
+        d.last = d.len ? pattern_start(chars, b, d.len, char2code, kmer_q, kmer_stride, sigma) : 0u;
         pats[i] = d;
         atomicAdd(&h[d.len < LEN_BINS - 1 ? d.len : LEN_BINS - 1], 1u);
     }
@@ -214,18 +229,31 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
         uint32_t c = pd.last, sp = 0, ep = 0, err = 0;
         int32_t i = (int32_t)pd.len - 1;
         bool alive = have;
+        const uint16_t* pch = chars + pd.off;
+        bool from_table = false;
+        if (have && (c & PAT_KMER)) {
+            // q-gram start table: the range after the pattern's last q chars, i.e. the state after q - 1 steps (layout.h)
+            const U32x2 r = ix.kmer[c & ~PAT_KMER];
+            if (r.x != 0xffffffffu) {
+                sp = r.x;
+                ep = r.y;
+                i -= (int32_t)ix.kmer_q - 1;
+                from_table = true;
+            } else {
+                c = (uint32_t)__ldg(ix.char2code + __ldg(pch + i));  // that q-gram throws on its way: step by step
+            }
+        }
         if (have && pd.len == 0) {  // pattern[-1]: ArrayIndexOutOfBounds (FmIndex.java:456-457)
             err = 1;
             alive = false;
-        } else if (have && c == 0) {  // :458
+        } else if (have && !from_table && c == 0) {  // :458
             alive = false;
-        } else if (have) {
+        } else if (have && !from_table) {
             sp = T.C[c];
             ep = T.C[c + 1];
         }
         // the pattern's chars are mapped to alphabet codes on the fly, fetched two steps ahead (raw char) and one
         // step ahead (its code) so that neither load is on the step's critical path
-        const uint16_t* pch = chars + pd.off;
         uint32_t cnext = (alive && i >= 1) ? (uint32_t)__ldg(ix.char2code + __ldg(pch + (i - 1))) : 0u;
         uint32_t raw2 = (alive && i >= 2) ? (uint32_t)__ldg(pch + (i - 2)) : 0u;
 

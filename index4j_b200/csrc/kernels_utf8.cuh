@@ -14,9 +14,9 @@ namespace fmgpu {
 // so the patterns' char ranges cannot overlap), descriptor {offset, length in chars, code of the last char}, length histogram.
 // A pattern whose conversion throws gets length 0 here; k_utf8_merge writes its status after the search.
 __global__ void __launch_bounds__(256) k_prepass_utf8(const uint8_t* __restrict__ bytes, const uint64_t* __restrict__ pat_off, uint32_t n_pat,
-                                                      const uint16_t* __restrict__ char2code, uint16_t* __restrict__ chars,
+                                                      const uint16_t* __restrict__ char2code, uint16_t* chars,
                                                       PatDesc* __restrict__ pats, uint32_t* __restrict__ bins, int32_t* __restrict__ conv_status,
-                                                      int32_t* __restrict__ conv_value) {
+                                                      int32_t* __restrict__ conv_value, uint32_t kmer_q, uint32_t kmer_stride, uint32_t sigma) {
     __shared__ uint32_t h[LEN_BINS];
     for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x) h[i] = 0;
     __syncthreads();
@@ -28,7 +28,8 @@ __global__ void __launch_bounds__(256) k_prepass_utf8(const uint8_t* __restrict_
         PatDesc d;
         d.off = a;
         d.len = n > 0 ? (uint32_t)n : 0u;
-        d.last = d.len ? (uint32_t)__ldg(char2code + (last & 0xffffu)) : 0u;
+        (void)last;
+        d.last = d.len ? pattern_start(chars, a + d.len, d.len, char2code, kmer_q, kmer_stride, sigma) : 0u;  // reads this thread's own chars
         pats[i] = d;
         conv_status[i] = n < 0 ? (int32_t)(-n) : 0;
         conv_value[i] = value;

@@ -76,8 +76,9 @@ struct U32x2 {
 struct PatDesc {  // one per pattern, written by the pre-pass
     uint64_t off;     // offset of the pattern's first char in the concatenated code array
     uint32_t len;
-    uint32_t last;    // code of the last char (the first one backward search consumes)
+    uint32_t last;    // code of the last char (the first one backward search consumes), or PAT_KMER | q-gram table index
 };
+constexpr uint32_t PAT_KMER = 0x80000000u;
 
 struct DevIndex {
     // FmIndex scalars
@@ -93,6 +94,13 @@ struct DevIndex {
     uint32_t n_sa;
     uint32_t s_total_ones;
     uint32_t n_blkmap;     // entries of blkmap
+    // q-gram start table of the backward search (0 = none): for every q-gram of alphabet codes the SA range after its q chars,
+    // i.e. the state of FmIndex.count after q - 1 steps, computed at load by the search kernel itself.  Entry of the q-gram
+    // whose LAST char has code a, the one before b, ... : index ((a * stride + b) * stride + ...); {0xffffffff, .} = not usable
+    // (a step of that q-gram throws in the reference), the pattern then starts from its last char as usual.
+    uint32_t kmer_q;
+    uint32_t kmer_stride;
+    const U32x2* kmer;
     const uint32_t* C;
     const U32x2* sbroot;        // [n_sb + 1] root-record directory (see above)
     const U32x2* blkmap;        // [n_blkmap]

@@ -104,6 +104,8 @@ def native():
         L.fmgpu_last_stats_ex.argtypes = [vp, vp, C.c_uint32]
         L.fmgpu_set_timing.argtypes = [vp, i32]
         L.fmgpu_set_stats.argtypes = [vp, i32]
+        L.fmgpu_set_start_table.argtypes = [vp, i32]
+        L.fmgpu_start_table_q.argtypes = [vp]
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         _lib = L
     return _lib
@@ -201,6 +203,13 @@ class FmIndex:
     def set_stats(self, enable: bool = True):
         """Work counters of the kernels (``last_stats``) on/off; off by default (production kernels carry none)."""
         self._check(self._lib.fmgpu_set_stats(self._h, int(enable)))
+
+    def set_start_table(self, enable: bool = True):
+        """Use (default) / bypass the q-gram start table of the backward search; results are identical either way."""
+        self._check(self._lib.fmgpu_set_start_table(self._h, int(enable)))
+
+    def start_table_q(self) -> int:
+        return int(self._lib.fmgpu_start_table_q(self._h))
 
     def set_timing(self, enable: bool = True):
         self._check(self._lib.fmgpu_set_timing(self._h, int(enable)))

@@ -26,11 +26,15 @@ def test_count_matches_oracle(gpu_indexes, name):
     assert np.array_equal(got_st, want_st)
     assert np.array_equal(got, want)
     assert int((want > 0).sum()) > 1000
+    # the same without the q-gram start table (every pattern from its last char), with the instrumented kernel: identical
+    # results, and then the kernel walks exactly the ranks the reference's loop performs
     g.set_stats(True)
+    g.set_start_table(False)
     try:
         got, got_st = g.count_batch(chars, off, return_status=True)
     finally:
         g.set_stats(False)
+        g.set_start_table(True)
     assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
     # work counters agree with the oracle's instrumentation
     case.oracle.stats(reset=True)
@@ -39,6 +43,39 @@ def test_count_matches_oracle(gpu_indexes, name):
     mine = g.last_stats()
     assert mine["launches"] == 4
     assert mine["rank_levels"] == st["rank_levels"]
+
+
+def test_start_table_is_transparent(gpu_indexes):
+    """Patterns of every length around q, known / unknown chars at every position of the last q chars: the q-gram start table gives
+    the counts, statuses and located positions of the step-by-step search."""
+    for name in ("log1m_sr32", "tiny600k_sr4"):
+        case, g = get_case(name), gpu_indexes(name)
+        q = g.start_table_q()
+        assert q >= 2
+        rng = np.random.default_rng(9)
+        t = case.text
+        pats = []
+        for ln in range(1, q + 4):
+            for _ in range(300):
+                a = int(rng.integers(0, t.size - ln))
+                p = t[a: a + ln].copy()
+                if rng.random() < 0.3:
+                    p[int(rng.integers(0, ln))] = rng.choice([0xFFFE, 0, int(t[int(rng.integers(0, t.size))])])
+                pats.append(p)
+        off = np.zeros(len(pats) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([p.size for p in pats])
+        chars = np.concatenate(pats).astype(np.uint16)
+        want, want_st = case.oracle.count_batch(chars, off, threads=4)
+        got, got_st = g.count_batch(chars, off, return_status=True)
+        assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
+        n1, o1, p1, s1 = g.locate_batch(chars, off, 20)
+        g.set_start_table(False)
+        try:
+            got0 = g.count_batch(chars, off)
+            n0, o0, p0, s0 = g.locate_batch(chars, off, 20)
+        finally:
+            g.set_start_table(True)
+        assert np.array_equal(got0, want) and np.array_equal(n0, n1) and np.array_equal(p0, p1) and np.array_equal(s0, s1)
 
 
 def test_count_edge_cases(gpu_indexes):
