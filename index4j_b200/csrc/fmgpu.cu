@@ -241,15 +241,19 @@ int count_on_stream(fmgpu_index* ix, const uint16_t* d_chars, const uint64_t* d_
     return 0;
 }
 
+constexpr int START_TABLE_LOG2 = 25;  // up to 32 M entries = 256 MB (q = 4 for a 70-symbol log alphabet: 24 M entries)
+
 // q-gram start table (layout.h): the search kernel itself computes, for every q-gram of alphabet codes, the SA range after its
 // q chars; q = the largest value with sigma^q entries <= 2^21 (q >= 2).  Built once per load (~1 ms of GPU time).
 int build_start_table(fmgpu_index* ix, const std::vector<uint16_t>& code2char, const std::vector<uint16_t>& char2code) {
     if (const char* e = getenv("FMGPU_START_TABLE"))
         if (atoi(e) == 0) return 0;
     const uint64_t S = ix->dev.sigma;
-    if (S < 2 || S > 1448) return 0;
+    int log2_max = START_TABLE_LOG2;  // FMGPU_START_TABLE_LOG2: largest table, in log2 entries of 8 bytes
+    if (const char* e = getenv("FMGPU_START_TABLE_LOG2")) log2_max = atoi(e) >= 2 && atoi(e) <= 27 ? atoi(e) : log2_max;
+    if (S < 2 || S * S > (1ull << log2_max)) return 0;
     uint32_t q = 2;
-    while (q < 8 && [&] { uint64_t n = 1; for (uint32_t k = 0; k <= q; ++k) n *= S; return n; }() <= (1ull << 21)) ++q;
+    while (q < 8 && [&] { uint64_t n = 1; for (uint32_t k = 0; k <= q; ++k) n *= S; return n; }() <= (1ull << log2_max)) ++q;
     uint64_t n_entries = 1;
     for (uint32_t k = 0; k < q; ++k) n_entries *= S;
     // every q-gram of codes 1 .. S-1 that chars can spell; pattern text order = first-consumed char last
@@ -297,6 +301,8 @@ int build_start_table(fmgpu_index* ix, const std::vector<uint16_t>& code2char, c
             CU(cudaStreamSynchronize(st));
         }
         for (void* p : {(void*)d_chars, (void*)d_off, (void*)d_counts, (void*)d_status, (void*)d_ranges}) cudaFree(p);
+        if (n > (1u << 22))  // a large table was built with scratch buffers no query batch is likely to need: give them back
+            for (Scratch* sc : {&ix->pats, &ix->order}) sc->release();
         if (rc) return rc;
         for (uint32_t i = 0; i < n; ++i)
             if (status[i] == 0) table[idx_of[i]] = U32x2{ranges[2 * (size_t)i], ranges[2 * (size_t)i + 1]};
