@@ -142,18 +142,20 @@ class ShardedFmIndex:
         n_hits = keep_n.sum(0)
         hit_off = torch.zeros(n + 1, dtype=torch.int64, device=dev)
         hit_off[1:] = torch.cumsum(n_hits, 0)
-        out = torch.empty(int(hit_off[-1].item()), dtype=torch.int64, device=dev)
-        ar = torch.arange(n, device=dev)
-        for r in range(self.world):
-            tot = int(totals[r].item())
-            if tot == 0:
-                continue
-            pid = torch.repeat_interleave(ar, all_n[r])
-            roff = torch.cumsum(all_n[r], 0) - all_n[r]
-            t = torch.arange(tot, device=dev) - roff[pid]
-            sel = t < keep_n[r][pid]
-            dst = hit_off[:-1][pid] + kept_before[r][pid] + t
-            out[dst[sel]] = recv[r, :tot][sel]
+        # one pass over all (rank, pattern) segments: segment (r, p) holds all_n[r][p] hits in recv[r] from roff[r][p]; its first
+        # keep_n[r][p] go to out[hit_off[p] + kept_before[r][p] ...]  (no per-rank loop, one host sync for the output size)
+        total = int(hit_off[-1].item())
+        out = torch.empty(total, dtype=torch.int64, device=dev)
+        if total:
+            stride = max(pad, 1)
+            roff = torch.cumsum(all_n, 1) - all_n
+            src0 = (roff + torch.arange(self.world, device=dev).unsqueeze(1) * stride).reshape(-1)
+            dst0 = (hit_off[:-1].unsqueeze(0) + kept_before).reshape(-1)
+            seg_len = keep_n.reshape(-1)
+            seg = torch.repeat_interleave(torch.arange(seg_len.numel(), device=dev), seg_len, output_size=total)
+            seg_first = torch.cumsum(seg_len, 0) - seg_len
+            t = torch.arange(total, device=dev) - seg_first[seg]
+            out[dst0[seg] + t] = recv.reshape(-1)[src0[seg] + t]
         return n_hits, hit_off, out
 
 
