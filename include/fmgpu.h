@@ -89,7 +89,7 @@ int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const ui
                              uint32_t n_pat, int32_t* d_counts_out, int32_t* d_status_out, void* cuda_stream);
 
 /* q-gram start table of the backward search: at load the search kernel computes, for every q-gram of alphabet codes (q = the
- * largest value with sigma^q <= 2^25 entries of 8 bytes, q >= 2; none for alphabets above 5792 symbols), the SA range after its q chars —
+ * largest value with sigma^q <= min(2^25, 4 x text length) entries of 8 bytes, q >= 2; none for alphabets above 5792 symbols), the SA range after its q chars —
  * the state of FmIndex.count (FM:455-474) after q - 1 steps of its loop — and count / locate start every pattern of >= q
  * known chars from that entry instead of from C[] of its last char.  Results are identical (the entries ARE the loop's states;
  * q-grams on whose way the reference throws are not entered).  fmgpu_set_start_table(idx, 0) makes every pattern start from its

@@ -251,6 +251,11 @@ int build_start_table(fmgpu_index* ix, const std::vector<uint16_t>& code2char, c
     const uint64_t S = ix->dev.sigma;
     int log2_max = START_TABLE_LOG2;  // FMGPU_START_TABLE_LOG2: largest table, in log2 entries of 8 bytes
     if (const char* e = getenv("FMGPU_START_TABLE_LOG2")) log2_max = atoi(e) >= 2 && atoi(e) <= 27 ? atoi(e) : log2_max;
+    {  // no more than ~4 entries per text position: a small index does not get a table larger than itself
+        int lb = 2;
+        while ((1ull << lb) < (uint64_t)ix->dev.length * 4 && lb < 27) ++lb;
+        if (lb < log2_max) log2_max = lb;
+    }
     if (S < 2 || S * S > (1ull << log2_max)) return 0;
     uint32_t q = 2;
     while (q < 8 && [&] { uint64_t n = 1; for (uint32_t k = 0; k <= q; ++k) n *= S; return n; }() <= (1ull << log2_max)) ++q;
