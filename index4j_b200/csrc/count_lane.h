@@ -40,6 +40,31 @@ struct CountCounters {
     uint32_t ranks, levels, loads, recs, spec_wasted;
 };
 
+// --- q-gram start table (layout.h) ---------------------------------------------------------------------------------
+// PatDesc.last of a pattern whose chars end at chars[b - 1]: the code of its last char, or — when the index has a q-gram
+// start table, the pattern has at least q chars and its last q chars are all in the wavelet alphabet — the table index
+FMGPU_HD uint32_t pattern_start(const uint16_t* chars, uint64_t b, uint32_t len, const uint16_t* char2code, uint32_t kmer_q,
+                                uint32_t kmer_stride, uint32_t sigma) {
+    const uint32_t last = (uint32_t)FMGPU_LDG16(char2code + chars[b - 1]);
+    if (kmer_q < 2u || len < kmer_q || last == 0u || last >= sigma) return last;
+    uint32_t idx = last;
+    for (uint32_t k = 1; k < kmer_q; ++k) {
+        const uint32_t c = (uint32_t)FMGPU_LDG16(char2code + chars[b - 1 - k]);
+        if (c == 0u || c >= sigma) return last;
+        idx = idx * kmer_stride + c;
+    }
+    return PAT_KMER | idx;
+}
+// the start state of a pattern whose descriptor carries a table index: true and {*sp, *ep} = the SA range after its last q chars
+// (FmIndex.count after q - 1 steps, fm/FmIndex.java:455-474), or false when the entry is not usable
+FMGPU_HD bool start_table_lookup(const DevIndex& ix, uint32_t last, uint32_t* sp, uint32_t* ep) {
+    const U32x2 r = ix.kmer[last & ~PAT_KMER];
+    if (r.x == 0xffffffffu) return false;
+    *sp = r.x;
+    *ep = r.y;
+    return true;
+}
+
 struct Track {
     uint32_t base, code, len, r;  // boundary rank; Huffman code left-aligned (bit 31 = next decision); levels left; position
 };

@@ -71,21 +71,6 @@ inline size_t tables_smem_bytes(const DevIndex& ix) { return tables_smem_bytes_t
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t LEN_BINS = 1024;
 
-// PatDesc.last of a pattern whose chars end at chars[b - 1]: the code of its last char, or — when the index has a q-gram
-// start table, the pattern has at least q chars and its last q chars are all in the wavelet alphabet — the table index
-__device__ __forceinline__ uint32_t pattern_start(const uint16_t* chars, uint64_t b, uint32_t len,
-                                                  const uint16_t* __restrict__ char2code, uint32_t kmer_q, uint32_t kmer_stride, uint32_t sigma) {
-    const uint32_t last = (uint32_t)__ldg(char2code + chars[b - 1]);
-    if (kmer_q < 2u || len < kmer_q || last == 0u || last >= sigma) return last;
-    uint32_t idx = last;
-    for (uint32_t k = 1; k < kmer_q; ++k) {
-        const uint32_t c = (uint32_t)__ldg(char2code + chars[b - 1 - k]);
-        if (c == 0u || c >= sigma) return last;
-        idx = idx * kmer_stride + c;
-    }
-    return PAT_KMER | idx;
-}
-
 __global__ void __launch_bounds__(256) k_prepass(const uint16_t* __restrict__ chars, const uint64_t* __restrict__ pat_off, uint32_t n_pat,
                                                  const uint16_t* __restrict__ char2code, PatDesc* __restrict__ pats,
                                                  uint32_t* __restrict__ bins, uint32_t kmer_q, uint32_t kmer_stride, uint32_t sigma) {
@@ -233,10 +218,7 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
         bool from_table = false;
         if (have && (c & PAT_KMER)) {
             // q-gram start table: the range after the pattern's last q chars, i.e. the state after q - 1 steps (layout.h)
-            const U32x2 r = ix.kmer[c & ~PAT_KMER];
-            if (r.x != 0xffffffffu) {
-                sp = r.x;
-                ep = r.y;
+            if (start_table_lookup(ix, c, &sp, &ep)) {
                 i -= (int32_t)ix.kmer_q - 1;
                 from_table = true;
             } else {

@@ -33,7 +33,9 @@ __device__ __forceinline__ Rec32 ld256_stream(const Rec32* p) {
 #if defined(__CUDA_ARCH__)
 #define FMGPU_LD256(p) ::fmgpu::ld256(p)
 #define FMGPU_LDG32(p) __ldg(p)
+#define FMGPU_LDG16(p) __ldg(p)
 #else
 #define FMGPU_LD256(p) (*(p))
 #define FMGPU_LDG32(p) (*(p))
+#define FMGPU_LDG16(p) (*(p))
 #endif

@@ -23,6 +23,7 @@ struct FC {
     SmemTables T;
     CountTables CT;
     uint16_t binom[15 * 16];
+    std::vector<U32x2> kmer;  // q-gram start table built by fc_build_start_table (host twin of build_start_table, fmgpu.cu)
 };
 const Rec32 ZERO{};
 
@@ -126,54 +127,74 @@ int fc_rank(void* h, uint32_t pos, uint32_t sym, int64_t* out) {
     return st;
 }
 
-// FmIndex.count over the flat layout: the kernel's per-lane step (count_step, count_lane.h) driven sequentially
-void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
-                    uint32_t* ranges, uint64_t* counters) {
-    FC& h = *(FC*)hv;
+// FmIndex.count of one pattern over the flat layout: the kernel's per-lane code (pattern_start / start_table_lookup / count_step,
+// count_lane.h) driven sequentially.  use_table: start from the q-gram start table when the handle has one (like k_count).
+static void count_one(FC& h, const uint16_t* pat, int64_t len, bool use_table, CountCounters& cnt, int32_t* result_out, int32_t* st_out,
+                      uint32_t* sp_out, uint32_t* ep_out) {
+    int32_t result = 0, st = 0;
+    uint32_t sp = 0, ep = 0;
+    if (len == 0) {
+        st = 9;
+    } else {
+        int64_t i = len - 1;
+        uint32_t c = pattern_start(pat, (uint64_t)len, (uint32_t)len, h.ix.char2code, use_table ? h.ix.kmer_q : 0u, h.ix.kmer_stride, h.ix.sigma);
+        bool from_table = false;
+        if (c & PAT_KMER) {
+            if (start_table_lookup(h.ix, c, &sp, &ep)) {
+                i -= (int64_t)h.ix.kmer_q - 1;
+                from_table = true;
+            } else {
+                c = h.ix.char2code[pat[i]];
+            }
+        }
+        if (from_table || c != 0) {
+            if (!from_table) {
+                sp = h.ix.C[c];
+                ep = h.ix.C[c + 1];
+            }
+            bool zero = false;
+            while (sp < ep && i >= 1) {
+                c = h.ix.char2code[pat[--i]];
+                if (c == 0 || c >= h.ix.sigma) {
+                    zero = true;
+                    sp = ep = 0;
+                    break;
+                }
+                if (h.ix.q4 && ep >= h.ix.length) {
+                    st = 9;
+                    break;
+                }
+                uint32_t a = sp, b = ep;
+                if (count_step<true>(h.ix, h.CT, c, &a, &b, true, cnt)) {
+                    st = 9;
+                    break;
+                }
+                sp = h.ix.C[c] + a;
+                ep = h.ix.C[c] + b;
+                ep = ep < h.ix.length ? ep : h.ix.length;
+            }
+            if (!zero && !st) result = ep > sp ? (int32_t)(ep - sp) : 0;
+        }
+    }
+    *result_out = st ? 0 : result;
+    *st_out = st;
+    *sp_out = sp;
+    *ep_out = (!st && result > 0) ? ep : sp;
+}
+
+static void count_batch_impl(FC& h, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
+                             uint32_t* ranges, uint64_t* counters, bool use_table) {
     CountCounters cnt{0, 0, 0, 0, 0};
     uint64_t n_rank = 0, n_level = 0, n_rec = 0, n_load = 0, n_waste = 0;
     for (uint32_t p = 0; p < n_pat; ++p) {
-        const uint16_t* pat = chars + pat_off[p];
-        const int64_t len = (int64_t)(pat_off[p + 1] - pat_off[p]);
         int32_t result = 0, st = 0;
         uint32_t sp = 0, ep = 0;
-        if (len == 0) {
-            st = 9;
-        } else {
-            int64_t i = len - 1;
-            uint32_t c = h.ix.char2code[pat[i]];
-            if (c != 0) {
-                sp = h.ix.C[c];
-                ep = h.ix.C[c + 1];
-                bool zero = false;
-                while (sp < ep && i >= 1) {
-                    c = h.ix.char2code[pat[--i]];
-                    if (c == 0 || c >= h.ix.sigma) {
-                        zero = true;
-                        sp = ep = 0;
-                        break;
-                    }
-                    if (h.ix.q4 && ep >= h.ix.length) {
-                        st = 9;
-                        break;
-                    }
-                    uint32_t a = sp, b = ep;
-                    if (count_step<true>(h.ix, h.CT, c, &a, &b, true, cnt)) {
-                        st = 9;
-                        break;
-                    }
-                    sp = h.ix.C[c] + a;
-                    ep = h.ix.C[c] + b;
-                    ep = ep < h.ix.length ? ep : h.ix.length;
-                }
-                if (!zero && !st) result = ep > sp ? (int32_t)(ep - sp) : 0;
-            }
-        }
-        counts[p] = st ? 0 : result;
+        count_one(h, chars + pat_off[p], (int64_t)(pat_off[p + 1] - pat_off[p]), use_table, cnt, &result, &st, &sp, &ep);
+        counts[p] = result;
         if (status) status[p] = st;
         if (ranges) {
             ranges[2 * p] = sp;
-            ranges[2 * p + 1] = (!st && result > 0) ? ep : sp;
+            ranges[2 * p + 1] = ep;
         }
         n_rank += cnt.ranks;
         n_level += cnt.levels;
@@ -189,6 +210,51 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
         counters[6] += n_load;
         counters[7] += n_rec;
     }
+}
+
+void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
+                    uint32_t* ranges, uint64_t* counters) {
+    count_batch_impl(*(FC*)hv, chars, pat_off, n_pat, counts, status, ranges, counters, false);
+}
+// the same starting every pattern from the q-gram start table (fc_build_start_table first)
+void fc_count_batch_table(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
+                          uint32_t* ranges, uint64_t* counters) {
+    count_batch_impl(*(FC*)hv, chars, pat_off, n_pat, counts, status, ranges, counters, true);
+}
+
+// Host twin of build_start_table (fmgpu.cu): for every q-gram of codes the chars can spell, the (sp, ep) the step-by-step search
+// reports for it as a pattern; q-grams that end in an error are left unusable.  Returns the number of usable entries.
+uint64_t fc_build_start_table(void* hv, uint32_t q) {
+    FC& h = *(FC*)hv;
+    const uint64_t S = h.ix.sigma;
+    uint64_t n_entries = 1;
+    for (uint32_t k = 0; k < q; ++k) n_entries *= S;
+    h.kmer.assign((size_t)n_entries, U32x2{0xffffffffu, 0u});
+    h.ix.kmer_q = 0;
+    std::vector<uint16_t> pat(q);
+    CountCounters cnt{0, 0, 0, 0, 0};
+    uint64_t usable = 0;
+    for (uint64_t idx = 0; idx < n_entries; ++idx) {
+        uint64_t v = idx;
+        bool ok = true;
+        for (uint32_t k = 0; k < q; ++k) {
+            const uint32_t code = (uint32_t)(v % S);
+            v /= S;
+            if (code == 0 || code >= h.F.code2char.size() || h.ix.char2code[h.F.code2char[code]] != code) ok = false;
+            else pat[k] = h.F.code2char[code];
+        }
+        if (!ok) continue;
+        int32_t result = 0, st = 0;
+        uint32_t sp = 0, ep = 0;
+        count_one(h, pat.data(), (int64_t)q, false, cnt, &result, &st, &sp, &ep);
+        if (st) continue;
+        h.kmer[(size_t)idx] = U32x2{sp, ep};
+        ++usable;
+    }
+    h.ix.kmer = h.kmer.data();
+    h.ix.kmer_q = q;
+    h.ix.kmer_stride = (uint32_t)S;
+    return usable;
 }
 
 // every NORMAL cell's first record must be the root record the directory computes (speculative root fetch); returns the

@@ -38,6 +38,9 @@ def lib():
         L.fc_inverse_select.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
         L.fc_check_roots.argtypes = [vp]
         L.fc_check_roots.restype = C.c_uint64
+        L.fc_count_batch_table.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
+        L.fc_build_start_table.argtypes = [vp, u32]
+        L.fc_build_start_table.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
         L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
         L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp]
@@ -91,6 +94,21 @@ class FlatIndexHost:
 
     def check_roots(self) -> int:
         return int(lib().fc_check_roots(self._h))
+
+    def build_start_table(self, q: int) -> int:
+        return int(lib().fc_build_start_table(self._h, q))
+
+    def count_batch_table(self, chars, pat_off):
+        """count_batch starting from the q-gram start table (build_start_table first)"""
+        chars = np.ascontiguousarray(chars, dtype=np.uint16)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        counts = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        ranges = np.zeros(2 * n, dtype=np.uint32)
+        lib().fc_count_batch_table(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data,
+                                   ranges.ctypes.data, self.counters.ctypes.data)
+        return counts, status, ranges.reshape(n, 2)
 
     def locate_rows(self, rows):
         rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()

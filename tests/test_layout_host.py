@@ -94,6 +94,37 @@ def test_count_and_locate_lanes(flats, name):
     assert np.array_equal(got_pos, np.array(exp, dtype=np.int64))
 
 
+@pytest.mark.parametrize("name,q", [("log300k_sr64", 2), ("log300k_sr64", 3), ("tiny600k_sr4", 5), ("log200k_sr1", 2)])
+def test_start_table_lanes(name, q):
+    """The q-gram start table (pattern_start / start_table_lookup of count_lane.h, table built by the step-by-step search itself):
+    counts, statuses and SA ranges equal the oracle's / the table-less search's for patterns of every length around q with known
+    and unknown chars in their last q positions."""
+    case = get_case(name)
+    f = flatcheck.FlatIndexHost(case.blob)
+    assert f.build_start_table(q) > 0
+    rng = np.random.default_rng(13)
+    t = case.text
+    pats = []
+    for ln in range(1, q + 4):
+        for _ in range(250):
+            a = int(rng.integers(0, t.size - ln))
+            p = t[a: a + ln].copy()
+            if rng.random() < 0.3:
+                p[int(rng.integers(0, ln))] = rng.choice([0xFFFE, 0, int(t[int(rng.integers(0, t.size))])])
+            pats.append(p)
+    chars0, off0 = make_patterns(t, 1500, 1, 40, seed=14)
+    off = np.zeros(len(pats) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([p.size for p in pats])
+    chars = np.concatenate(pats + [chars0]).astype(np.uint16)
+    off = np.concatenate([off, off[-1] + off0[1:]]).astype(np.uint64)
+    want, want_st = case.oracle.count_batch(chars, off, threads=4)
+    got, got_st, ranges = f.count_batch_table(chars, off)
+    assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
+    plain, plain_st, plain_ranges = f.count_batch(chars, off)
+    hit = want > 0
+    assert np.array_equal(ranges[hit], plain_ranges[hit])  # locate starts from these rows
+
+
 @pytest.mark.parametrize("name", CASE_NAMES)
 def test_extract_lanes(flats, name):
     case, f = get_case(name), flats(name)
