@@ -85,6 +85,21 @@ struct JavaSink {
     void i64(int64_t v) {
         for (int s = 56; s >= 0; s -= 8) u8((uint8_t)((uint64_t)v >> s));
     }
+    // n big-endian longs; the unframed stream takes them in one resize + byte-swapped stores (the word arrays of the packed
+    // vectors are most of a serialized index)
+    void i64_array(const uint64_t* w, size_t n) {
+        if (framed) {
+            for (size_t i = 0; i < n; ++i) i64((int64_t)w[i]);
+            return;
+        }
+        const size_t at = out.size();
+        out.resize(at + 8 * n);
+        uint8_t* p = out.data() + at;
+        for (size_t i = 0; i < n; ++i) {
+            const uint64_t be = __builtin_bswap64(w[i]);
+            memcpy(p + 8 * i, &be, 8);
+        }
+    }
     void finish() {
         if (framed) drain();
     }
@@ -94,7 +109,7 @@ void write_intvec(JavaSink& s, const IntVec& v) {  // IntVector.java:196-203
     s.u8(0);
     s.i32(v.length);
     s.i32(v.width);
-    for (uint64_t w : v.data) s.i64((int64_t)w);
+    s.i64_array(v.data.data(), v.data.size());
 }
 void write_rrr(JavaSink& s, const RrrEnc& r) {  // RrrVector.java:430-440
     s.u8(0);
@@ -105,7 +120,7 @@ void write_rrr(JavaSink& s, const RrrEnc& r) {  // RrrVector.java:430-440
     write_intvec(s, r.classes);
     s.u8(0);  // VariableWidthIntVector.java:175-181
     s.i32((int32_t)r.offsets.size());
-    for (uint64_t w : r.offsets) s.i64((int64_t)w);
+    s.i64_array(r.offsets.data(), r.offsets.size());
     write_intvec(s, r.sampled_offset_pos);
     write_intvec(s, r.prefix_sums);
 }

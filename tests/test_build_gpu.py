@@ -34,6 +34,27 @@ def test_host_producer_from_parts_is_byte_identical(name, sr, extract):
     assert a == b
 
 
+def _unframe(blob: bytes) -> bytes:
+    """Payload of an ObjectOutputStream of block-data records (0x77 len8 / 0x7A len32), Serialization.java:67-78."""
+    assert blob[:4] == b"\xac\xed\x00\x05"
+    out, i = bytearray(), 4
+    while i < len(blob):
+        if blob[i] == 0x77:
+            n, i = blob[i + 1], i + 2
+        else:
+            assert blob[i] == 0x7A
+            n, i = int.from_bytes(blob[i + 1: i + 5], "big"), i + 5
+        out += blob[i: i + n]
+        i += n
+    return bytes(out)
+
+
+def test_unframed_stream_is_the_payload_of_the_framed_one():
+    """The raw writer (bulk big-endian stores) and the block-data writer (byte by byte) must serialize the same bytes."""
+    text = get_case("log300k_sr64").text[:120_000]
+    assert _unframe(build_index(text, 16, True, framed=True)) == build_index(text, 16, True, framed=False)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,sr,extract", [("log1m_sr32", 32, True), ("log200k_sr1", 1, True), ("multi400k_sr8", 8, True),
                                              ("tiny600k_sr4", 4, False), ("log300k_sr64", 64, True)])
