@@ -47,6 +47,9 @@ extern "C" {
 #define FMGPU_ST_DOES_NOT_FIT 8   /* RuntimeException("Extraction does not fit in the supplied destination. Currently extracted: N") FM:733,817,894; N in len_out */
 #define FMGPU_ST_RRR_RANGE 11     /* IllegalArgumentException("Out of range access. Requested P when range is [0, L)") RRR:316-323 */
 #define FMGPU_ST_CHAR_EXCEEDS 10  /* RuntimeException("Found a character that exceeds (32767): it was N") FM:261-267 (UTF-8 entry points; N in counts_out) */
+#define FMGPU_ST_NO_TERMINATION 12 /* the reference never returns: an LF walk of locate (FM:531-537) has run for more than
+                                    * getInputLength() steps, i.e. in a cycle — only possible on an index with more than 256
+                                    * symbols where inverseSelect truncated a single-symbol block's symbol (WF:1329-1332) */
 #define FMGPU_ST_INDEX_OOB 9      /* ArrayIndexOutOfBoundsException (empty pattern FM:456; rank(size,.) on a superblock boundary, wavelet/WaveletFixedBlockBoosting.java:1022-1026) */
 
 #define FMGPU_MODE_BOTH 0  /* FmIndex.extractUntilBoundary       FM:640 */
@@ -116,7 +119,10 @@ int fmgpu_locate_batch_utf8(fmgpu_index* idx, const uint8_t* bytes, const uint64
  * max_hits <= 0 means unlimited (FM:544).  Hits of pattern i are written to
  * positions_out[hit_off_out[i] .. hit_off_out[i+1]) in SA-row order (the order Java fills its
  * array).  Two-phase sizing: with positions_out == NULL only n_hits_out / hit_off_out are produced.
- * If positions_cap < total hits the call returns FMGPU_ERR_CAPACITY (hit_off_out is still valid). */
+ * If positions_cap < total hits the call returns FMGPU_ERR_CAPACITY (hit_off_out is still valid).
+ * Where an LF walk of a hit indexes outside the reference's arrays (rank(size, .) on a superblock boundary, WF:1022-1026)
+ * the reference throws out of locate(): status_out[pattern] = FMGPU_ST_INDEX_OOB (FMGPU_ST_NO_TERMINATION for a walk in a
+ * cycle) and that hit's slot holds -1; n_hits_out keeps the number of slots. */
 int fmgpu_locate_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t max_hits,
                        int32_t* n_hits_out, uint64_t* hit_off_out, int32_t* positions_out, uint64_t positions_cap,
                        int32_t* status_out);

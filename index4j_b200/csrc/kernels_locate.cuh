@@ -33,7 +33,7 @@ inline size_t locate_smem_bytes(const DevIndex& ix) { return LOCATE_TAB_WORDS * 
 template <bool STATS>
 __global__ void __launch_bounds__(LOCATE_THREADS, LOCATE_MIN_CTAS)
 k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, uint32_t chunk, unsigned int* queue,
-         unsigned long long* stats) {
+         unsigned long long* stats, const uint64_t* __restrict__ hit_off, uint32_t n_pat, int32_t* __restrict__ status) {
     extern __shared__ uint32_t smem[];
     uint16_t* inv = reinterpret_cast<uint16_t*>(smem);
     uint16_t* cbase = inv + 32768;
@@ -101,9 +101,22 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
             if (!bit) {
                 uint32_t sym = 0, err = 0;
                 const uint32_t jn = lf_step(ix, T, D, j, bmask, &sym, &err, cnt);  // :532-536
+                // The reference throws out of locate() when an LF step indexes outside its arrays (status 9), and never returns
+                // when a walk runs into a cycle — possible only where inverseSelect truncates a run-block symbol (quirk Q1): a
+                // walk of more than `length` steps has visited a row twice (status 12).  The hit's pattern gets the status.
+                if (!err && dist >= ix.length) err = 2;
                 if (err) {
                     rows_pos[w] = 0xffffffffu;
                     active = false;
+                    if (status) {
+                        uint32_t lo = 0, hi = n_pat;  // last pattern with hit_off[p] <= w
+                        while (hi - lo > 1u) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (hit_off[mid] <= (uint64_t)w) lo = mid;
+                            else hi = mid;
+                        }
+                        atomicMax(status + lo, err == 2 ? 12 : 9);
+                    }
                 } else {
                     j = jn;
                     ++dist;

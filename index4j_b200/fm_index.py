@@ -33,6 +33,7 @@ _MESSAGES = {
     9: "ArrayIndexOutOfBoundsException",
     10: "Found a character that exceeds (32767): it was {n}",
     11: "Out of range access",
+    12: "locate does not terminate in the reference (LF walk in a cycle behind a truncated run-block symbol)",
 }
 
 

@@ -52,6 +52,8 @@ enum {
     ST_DOES_NOT_FIT = 8,     // RuntimeException("Extraction does not fit ... Currently extracted: N") FM:733,817,894
     ST_INDEX_OOB = 9,        // ArrayIndexOutOfBoundsException (e.g. quirk Q4, WF:1022-1026)
     ST_CHAR_EXCEEDS = 10,    // RuntimeException("Found a character that exceeds (32767): it was N")  FM:262-267
+    ST_NO_TERMINATION = 12,  // the reference never returns: an LF walk of locate (FM:531-537) longer than `length` steps has
+                             // visited a row twice, i.e. runs in a cycle (possible only behind quirk Q1, WF:1329-1332)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -265,9 +267,29 @@ inline int64_t u24le(const std::vector<int8_t>& v, int64_t p) {
            ((int32_t)v.at((size_t)p) & 0x0000ff);
 }
 
-struct Stats {  // instrumentation for roofline accounting (not part of the reference)
-    std::atomic<uint64_t> ranks{0}, rank_levels{0}, lf_steps{0}, lf_levels{0};
+// Work counters (instrumentation for the roofline accounting and the tests that cross-check the GPU's own counters; not part
+// of the reference).  They must not slow the timed CPU arm down: every thread counts into its own thread-local tally, which
+// is added to the process-wide totals once, when the thread ends (the batch calls join their workers) or when orc_fm_stats
+// reads them — no shared cache line is touched inside rank / inverseSelect.  -DORACLE_NO_STATS (the build bench.py times as the
+// CPU baseline) compiles the counters out altogether.
+#ifndef ORACLE_NO_STATS
+std::atomic<uint64_t> g_totals[4];  // ranks, rank_levels, lf_steps, lf_levels
+struct Tally {
+    uint64_t v[4] = {0, 0, 0, 0};
+    void flush() {
+        for (int i = 0; i < 4; ++i)
+            if (v[i]) {
+                g_totals[i].fetch_add(v[i], std::memory_order_relaxed);
+                v[i] = 0;
+            }
+    }
+    ~Tally() { flush(); }
 };
+thread_local Tally t_tally;
+#define ORC_COUNT(slot, n) (t_tally.v[slot] += (uint64_t)(n))
+#else
+#define ORC_COUNT(slot, n) ((void)0)
+#endif
 
 struct Wfbb {
     int64_t size = 0;
@@ -276,7 +298,6 @@ struct Wfbb {
     std::vector<int32_t> sb_rank;
     std::vector<int16_t> global_mapping;
     std::vector<SuperBlockHeaderItem> sbs;
-    mutable Stats stats;
 
     void read(Reader& r) {  // WF:286-322
         r.version();
@@ -353,7 +374,7 @@ struct Wfbb {
         if (position == 0) return 0;
         if (position > size) position = size;
         if (symbol >= sigma) return 0;
-        stats.ranks.fetch_add(1, std::memory_order_relaxed);
+        ORC_COUNT(0, 1);
         if (symbol < 0) throw JavaThrow{ST_INDEX_OOB, symbol};
         int64_t hb = position >> 32;
         int64_t sb = position >> 20;
@@ -406,7 +427,7 @@ struct Wfbb {
         int64_t node_rank = block_index;
         int64_t block_sigma = (int64_t)H.sigma + 1;
         int64_t second = var_off + (tree_height - 1) * 4 + block_sigma * 5;
-        stats.rank_levels.fetch_add((uint64_t)code_length, std::memory_order_relaxed);
+        ORC_COUNT(1, code_length);
         for (int64_t depth = 0; depth < code_length; ++depth) {
             int64_t rank1 = S.rank_support.rank_ones((int32_t)(bv_offset + left_sib_bv + node_rank));
             int64_t left_ones = 0;
@@ -466,7 +487,7 @@ struct Wfbb {
         int64_t tmp8 = ptr8;
         if (tree_height > 0) tmp8 += (tree_height - 1) * 4;
         const int64_t ptr32 = tmp8;
-        stats.lf_steps.fetch_add(1, std::memory_order_relaxed);
+        ORC_COUNT(2, 1);
         if (tree_height == 0) {
             int8_t b0 = S.var.at((size_t)ptr32);
             int8_t b1 = S.var.at((size_t)ptr32 + 1);
@@ -529,7 +550,7 @@ struct Wfbb {
                 break;
             }
         }
-        stats.lf_levels.fetch_add((uint64_t)code_length, std::memory_order_relaxed);
+        ORC_COUNT(3, code_length);
         int64_t block_c = symbol_from_header(S.var, copy_ptr8, code, code_length);
         int32_t c = (int32_t)u16le(S.var, ptr32 + 5 * block_c);
         if (position == 0) return c;
@@ -618,6 +639,7 @@ struct FmIndex {
                     int32_t rk = (int32_t)wf.rank(j, c);
                     j = C.at((size_t)c) + rk;
                     ++distance;
+                    if (distance > length) throw JavaThrow{ST_NO_TERMINATION, distance};
                 }
                 if (k >= cap) throw JavaThrow{ST_INDEX_OOB, k};
                 locations[k] = (int32_t)(suffixes.get(sampled.rank_ones(j) - 1, bw_suffixes) + (uint64_t)distance);
@@ -1059,17 +1081,24 @@ void orc_fm_extract_until_boundary_batch(void* h, const int32_t* from, uint32_t 
 // Work counters since the last reset: rank queries, tree levels walked by rank, LF steps
 // (inverseSelect calls) and their levels.  Used by tests to cross-check the GPU's own counters.
 void orc_fm_stats(void* h, uint64_t* out4, int32_t reset) {
-    Stats& s = ((FmIndex*)h)->wf.stats;
-    out4[0] = s.ranks.load();
-    out4[1] = s.rank_levels.load();
-    out4[2] = s.lf_steps.load();
-    out4[3] = s.lf_levels.load();
-    if (reset) {
-        s.ranks = 0;
-        s.rank_levels = 0;
-        s.lf_steps = 0;
-        s.lf_levels = 0;
+    (void)h;  // process-wide totals (one index is queried at a time by the tests that read them)
+#ifndef ORACLE_NO_STATS
+    t_tally.flush();
+    for (int i = 0; i < 4; ++i) {
+        out4[i] = g_totals[i].load();
+        if (reset) g_totals[i] = 0;
     }
+#else
+    (void)reset;
+    for (int i = 0; i < 4; ++i) out4[i] = 0;
+#endif
+}
+int32_t orc_has_stats(void) {
+#ifndef ORACLE_NO_STATS
+    return 1;
+#else
+    return 0;
+#endif
 }
 
 // Direct access to the two lower layers of the loaded index (for layer tests).

@@ -26,17 +26,36 @@ STATUS_MESSAGES = {
     8: "Extraction does not fit in the supplied destination. Currently extracted: {n}",
     9: "ArrayIndexOutOfBoundsException",
     10: "Found a character that exceeds (32767): it was {n}",
+    12: "locate does not terminate in the reference (LF walk in a cycle behind a truncated run-block symbol)",
 }
 
+NATIVE_LIB = os.path.join(HERE, "liboracle_native.so")
+
 _lib = None
+_lib_path = LIB
+
+
+def use_native() -> str:
+    """bench.py's CPU arm: build the oracle ON this box with -march=native and without the work counters (`make native`) and
+    make lib() load that build.  Must be called before the first use of the oracle in the process; falls back to the portable
+    build if the compile fails.  Returns a description of the build that will be timed."""
+    global _lib_path
+    if _lib is not None:
+        return "portable build (-march=x86-64-v3, thread-local work counters)" if _lib_path == LIB else "native"
+    try:
+        subprocess.check_call(["make", "-s", "-B", "-C", HERE, "native"])
+        _lib_path = NATIVE_LIB
+        return "g++ -O3 -march=native, work counters compiled out"
+    except Exception:  # noqa: BLE001
+        return "portable build (-march=x86-64-v3, thread-local work counters)"
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB):
+        if _lib_path == LIB and not os.path.exists(LIB):
             subprocess.check_call(["make", "-s", "-C", HERE])
-        L = C.CDLL(LIB)
+        L = C.CDLL(_lib_path)
         L.orc_last_error.restype = C.c_char_p
         vp, i32, i64, u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64
         L.orc_fm_load.argtypes = [vp, u64, C.POINTER(vp)]

@@ -54,6 +54,32 @@ def tiny_alphabet_text(n: int, sigma: int = 6, seed: int = 3) -> np.ndarray:
     return np.ascontiguousarray(np.concatenate(out)[:n], dtype=np.uint16)
 
 
+def nul_text(n: int, k: int = 1000, seed: int = 12) -> np.ndarray:
+    """Log text with k chars overwritten by \\0 — the reference's FmIndexTest.java:53-65,202-217: the text's own \\0 gets
+    alphabet code 1 or later, the appended sentinel keeps code 0 (fm/FmIndex.java:398-415)."""
+    from index4j_b200.builder import gen_log_text
+    t = gen_log_text(n, seed=seed).copy()
+    rng = np.random.default_rng(seed)
+    t[rng.integers(0, n, k)] = 0
+    return t
+
+
+def big_code_runs_text(seed: int = 4) -> np.ndarray:
+    """More than 256 distinct chars first, then long periodic stretches of chars that appear late (alphabet codes >= 256): the
+    BWT then holds single-symbol blocks whose symbol code is >= 256, where inverseSelect keeps only the low byte (quirk Q1,
+    wavelet/WaveletFixedBlockBoosting.java:1329-1332)."""
+    rng = np.random.default_rng(seed)
+    head = np.arange(0x4E00, 0x4E00 + 300, dtype=np.uint16)  # codes 1..300 in order of first appearance
+    late = np.arange(0x5000, 0x5000 + 6, dtype=np.uint16)    # codes 301..306
+    parts = [head]
+    for _ in range(4):  # 100,000 (a b) pairs: BWT runs of 100,000 equal symbols, longer than the largest block (2^16)
+        a, b = rng.choice(late, 2, replace=False)
+        parts.append(np.tile(np.array([a, b], dtype=np.uint16), 100_000))
+        parts.append(rng.choice(head, 200).astype(np.uint16))
+        parts.append(np.array([0x0A], dtype=np.uint16))
+    return np.ascontiguousarray(np.concatenate(parts), dtype=np.uint16)
+
+
 class Case:
     def __init__(self, name, text, sample_rate, extraction=True):
         from index4j_b200.builder import build_index
@@ -89,6 +115,14 @@ def get_case(name: str) -> Case:
             c = Case(name, multiscript_text(400_000), 8)
         elif name == "tiny600k_sr4":
             c = Case(name, tiny_alphabet_text(600_000), 4)
+        elif name == "q4_2m_sr32":  # n + 1 = 2 * 2^20: rank(size, .) indexes past the superblock arrays (quirk Q4, :1022-1026)
+            c = Case(name, gen_log_text((2 << 20) - 1, seed=21), 32)
+        elif name == "nul1m_sr32":
+            c = Case(name, nul_text(1 << 20), 32)
+        elif name == "q1_runs_sr4":
+            c = Case(name, big_code_runs_text(), 4)
+        elif name == "cfg1_16m_sr32":  # BASELINE.json configs[0]: 16 MiB of log text, sampleRate 32, extraction on
+            c = Case(name, gen_log_text(16 << 20), 32)
         elif name == "noextract":
             c = Case(name, gen_log_text(100_000, seed=8), 32, extraction=False)
         else:
@@ -98,6 +132,8 @@ def get_case(name: str) -> Case:
 
 
 CASE_NAMES = ["log1m_sr32", "log3m_sr16", "log300k_sr64", "log200k_sr1", "multi400k_sr8", "tiny600k_sr4"]
+# the reference's quirk regions, one index each (Q4, text containing \\0, Q1)
+QUIRK_CASE_NAMES = ["q4_2m_sr32", "nul1m_sr32", "q1_runs_sr4"]
 
 
 def make_patterns(text: np.ndarray, n_pat: int, min_len: int, max_len: int, seed: int, absent_frac: float = 0.15):

@@ -341,8 +341,8 @@ void fc_locate_rows(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* counters
             }
             uint32_t sym = 0, err = 0;
             const uint32_t jn = lf_step(h.ix, h.T, h.ix.blocks[blk], j, bmask, &sym, &err, cnt);
-            if (err) {
-                rows_pos[w] = 0xffffffffu;
+            if (err || dist >= h.ix.length) {  // as k_locate: the reference throws / never returns (walk in a cycle)
+                rows_pos[w] = err ? 0xffffffffu : 0xfffffffeu;
                 break;
             }
             j = jn;

@@ -99,7 +99,7 @@ def test_count_edge_cases(gpu_indexes):
 
 
 @pytest.mark.parametrize("name", CASE_NAMES)
-@pytest.mark.parametrize("max_hits", [-1, 1, 100])
+@pytest.mark.parametrize("max_hits", [-1, 0, 1, 100])
 def test_locate_matches_oracle(gpu_indexes, name, max_hits):
     case = get_case(name)
     g = gpu_indexes(name)
@@ -110,6 +110,8 @@ def test_locate_matches_oracle(gpu_indexes, name, max_hits):
     n_hits, hit_off, pos, st = g.locate_batch(chars, off, max_hits)
     assert np.array_equal(st, want_st)
     assert np.array_equal(n_hits, want_n)
+    if max_hits == 0:  # maxMatches <= 0 = unlimited (fm/FmIndex.java:544)
+        assert np.array_equal(n_hits[st == 0], counts[st == 0])
     assert int(hit_off[-1]) == int(want_n.sum()) == pos.size
     for i in range(want_n.size):
         a = pos[int(hit_off[i]): int(hit_off[i + 1])]

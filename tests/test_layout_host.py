@@ -5,7 +5,9 @@ lane at a time with plain memory reads, and the results must be bit-exact with t
 import numpy as np
 import pytest
 
-from conftest import CASE_NAMES, get_case, make_patterns
+from conftest import CASE_NAMES, QUIRK_CASE_NAMES, get_case, make_patterns
+
+ALL_CASES = CASE_NAMES + QUIRK_CASE_NAMES
 
 import flatcheck
 import pyoracle
@@ -27,7 +29,7 @@ def test_unranking_reproduces_reference_table():
     assert np.array_equal(flatcheck.unrank_table(), pyoracle.rrr_inverse_table())
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_rank_cells_match_oracle(flats, name):
     case, f = get_case(name), flats(name)
     rng = np.random.default_rng(1)
@@ -47,7 +49,7 @@ def test_rank_cells_match_oracle(flats, name):
         assert got_st == st and (st or got == want), (int(p), s, want, got, st, got_st)
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_inverse_select_records_match_oracle(flats, name):
     """WaveletFixedBlockBoosting.inverseSelect through the block descriptors / level + node records (incl. the low-byte symbol of
     single-symbol blocks, quirk Q1) against the oracle's restatement of :1305-1537."""
@@ -61,14 +63,14 @@ def test_inverse_select_records_match_oracle(flats, name):
     assert f.inverse_select(-1)[0] == 9 and f.inverse_select(L)[0] == 9
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_root_record_directory(flats, name):
     """The speculative root fetch of count_step computes a block's root record from shared-memory tables alone: it must be the
     first record of every NORMAL cell of the block (and the block descriptor's root)."""
     assert flats(name).check_roots() == 0
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_sampled_rows_match_oracle(flats, name):
     case, f = get_case(name), flats(name)
     rng = np.random.default_rng(2)
@@ -78,7 +80,7 @@ def test_sampled_rows_match_oracle(flats, name):
         assert b == case.oracle.sampled_access(int(p)) and r == case.oracle.sampled_rank(int(p)), int(p)
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_count_and_locate_lanes(flats, name):
     case, f = get_case(name), flats(name)
     chars, off = make_patterns(case.text, 2500, 1, 40, seed=3)
@@ -144,7 +146,7 @@ def test_extract_lanes(flats, name):
         assert np.array_equal(arena[int(aoff[i]): int(aoff[i + 1])], case.text[start[i]: stop[i]]), i
 
 
-@pytest.mark.parametrize("name", CASE_NAMES)
+@pytest.mark.parametrize("name", ALL_CASES)
 @pytest.mark.parametrize("mode", [0, 1, 2])
 def test_extract_until_boundary_lanes(flats, name, mode):
     case, f = get_case(name), flats(name)
