@@ -182,11 +182,18 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_count_throughput(blob: bytes, chars, off, n_sample: int, threads: int, repeats: int = 1):
-    """The reference's CPU path (C++ restatement of the Java loops = oracle port) on a bounded sample."""
+def load_oracle(blob: bytes):
+    """The CPU arm's engine: the C++ restatement of the reference's Java loops, compiled ON this box with -march=native and
+    without its work counters (oracle/Makefile `native`)."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
-    o = pyoracle.OracleFmIndex(blob)
+    build = pyoracle.use_native()
+    return pyoracle.OracleFmIndex(blob), build
+
+
+def cpu_count_throughput(o, chars, off, n_sample: int, threads: int, repeats: int = 1):
+    """FmIndex.count of the first n_sample patterns on `threads` host threads (one shared immutable index, contiguous slices of
+    the batch per thread — one @ThreadSafe FmIndex shared by a Java thread pool).  -> (patterns/s, seconds, counts)"""
     n_sample = min(n_sample, off.size - 1)
     sub_off = off[: n_sample + 1]
     sub_chars = chars[: int(sub_off[-1])]
@@ -197,22 +204,51 @@ def cpu_count_throughput(blob: bytes, chars, off, n_sample: int, threads: int, r
         counts, _ = o.count_batch(sub_chars, sub_off, threads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return n_sample / best, best, counts, o
+    return n_sample / best, best, counts
+
+
+def cpu_thread_scaling(o, chars, off, n_sample: int, max_threads: int) -> dict:
+    """patterns/s of the CPU arm at 1 / 8 / 16 / all host threads on a small sample (how the baseline scales on this box)."""
+    out = {}
+    for th in sorted({1, 8, 16, max_threads}):
+        if th > max_threads:
+            continue
+        n = min(n_sample if th > 1 else max(n_sample // 8, 1000), off.size - 1)
+        v, _, _ = cpu_count_throughput(o, chars, off, n, th)
+        out[str(th)] = v
+    return out
+
+
+def cpu_lf_arms(o, chars, off, args, threads: int, frm) -> dict:
+    """CPU arms of the locate and extractUntilBoundary legs on bounded samples (same engine, all host threads)."""
+    k = min(args.cpu_locate_sample, off.size - 1)
+    t0 = time.perf_counter()
+    w_n, w_pos, _ = o.locate_batch(chars[: int(off[k])], off[: k + 1], args.max_hits, max(args.max_hits, 1), threads=threads)
+    dt_loc = time.perf_counter() - t0
+    m = min(args.cpu_eub_sample, frm.size)
+    t0 = time.perf_counter()
+    w_arena, w_ln, w_st = o.extract_until_boundary_batch(frm[:m], 10, args.dst_len, 0, threads=threads)
+    dt_eub = time.perf_counter() - t0
+    return {"locate": {"value": float(w_n.sum()) / dt_loc, "unit": "hits/s", "cores": threads, "kind": "port",
+                       "sample": "locate(max %d) of the first %d patterns: %d hits in %.2fs" % (args.max_hits, k, int(w_n.sum()), dt_loc)},
+            "extract_until_boundary": {"value": m / dt_eub, "unit": "records/s", "cores": threads, "kind": "port",
+                                       "sample": "the first %d of the located records, dst %d: %.2fs" % (m, args.dst_len, dt_eub)},
+            "_check": (k, w_n, w_pos, m, w_arena, w_ln, w_st)}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path on this box's host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores — the C++ restatement of
+    its Java loops (no JVM exists in this image), all host threads.  Nothing of the GPU engine runs here: the index is built by
+    the host producer."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     holder = {}
-    blob = get_index_blob(args.n_text, args.sample_rate, holder, use_gpu_sa=True)
+    blob = get_index_blob(args.n_text, args.sample_rate, holder, use_gpu_sa=False)
     chars, off = get_patterns(args.n_text, args.n_pat, args.min_len, args.max_len, 42, holder)
     holder.clear()
     threads = os.cpu_count() or 1
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import pyoracle
-    o = pyoracle.OracleFmIndex(blob)
+    o, build = load_oracle(blob)
     n_sample = min(args.ref_sample, off.size - 1)
     sub_off = off[: n_sample + 1]
     sub_chars = chars[: int(sub_off[-1])]
@@ -223,12 +259,14 @@ def run_reference(args):
         o.count_batch(sub_chars, sub_off, threads=threads)
     dt = time.perf_counter() - t0
     value = n_sample * args.steps / dt
-    sample = "first %d of the %d patterns per step (C++ restatement of the Java loops; no JVM in this image)" % (n_sample, args.n_pat)
+    scaling = cpu_thread_scaling(o, chars, off, 100_000, threads)
+    sample = "first %d of the %d patterns per step (C++ restatement of the Java loops, %s; no JVM in this image)" % (n_sample, args.n_pat, build)
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic", "config": workload_config(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "build": build,
+                         "patterns_per_s_by_threads": scaling},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -256,6 +294,9 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=1_000_000, help="patterns per step of the CPU reference arm")
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="patterns of the cpu_baseline leg")
     ap.add_argument("--cpu-repeats", type=int, default=3)
+    ap.add_argument("--cpu-locate-sample", type=int, default=20_000, help="patterns of the CPU arm of the locate leg")
+    ap.add_argument("--cpu-eub-sample", type=int, default=50_000, help="records of the CPU arm of the extractUntilBoundary leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs of an N > 1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lf", action="store_true", help="skip the locate / extractUntilBoundary legs (extra keys of the JSON line)")
     ap.add_argument("--max-hits", type=int, default=1000)
@@ -401,15 +442,74 @@ def main():
         lf = {"loc": loc, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
               "d_hit_off": d_hit_off, "d_pos": d_pos, "h2d": int(chars.nbytes + off.nbytes), "d2h": int(p_nh.nbytes + p_ho.nbytes + p_pos.nbytes + h_status.nbytes)}
 
+    # strong scaling (BASELINE.json configs[1] as written: the ONE 1 M-pattern batch sharded over the GPUs).  (a) device-resident:
+    # rank r searches slice r of rank 0's batch, time = max over ranks; (b) one process: rank 0 alone drives all N GPUs through
+    # ONE fmgpu_index replicated by the library (fmgpu_opts.devices) with host buffers — what a single JVM would call.
+    strong = None
+    if world > 1 and not args.no_strong:
+        chars0, off0 = get_patterns(args.n_text, args.n_pat, args.min_len, args.max_len, 42, holder)
+        lo, hi = n_pat * rank // world, n_pat * (rank + 1) // world
+        s_off = off0[lo: hi + 1] - off0[lo]
+        s_chars = chars0[int(off0[lo]): int(off0[hi])]
+        ds_chars = torch.from_numpy(s_chars.view(np.int16)).to(dev)
+        ds_off = torch.from_numpy(s_off.view(np.int64)).to(dev)
+        ds_counts = torch.empty(hi - lo, dtype=torch.int32, device=dev)
+        for _ in range(args.warmup):
+            ix.count_batch_device(ds_chars, ds_off, ds_counts, None)
+        torch.cuda.synchronize()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            ix.count_batch_device(ds_chars, ds_off, ds_counts, None)
+        s1.record()
+        torch.cuda.synchronize()
+        barrier()
+        strong = {"dev_ms": s0.elapsed_time(s1), "one_ms": 0.0, "one_utf8_ms": 0.0}
+        if rank == 0:
+            t_load = time.time()
+            mix = FmIndex.read(blob, devices=list(range(world)))
+            log("strong: one handle on devices %s in %.1fs" % (mix.devices, time.time() - t_load))
+            from index4j_b200.fm_index import pinned_empty
+            m_chars = pinned_empty(chars0.size, np.uint16)
+            m_chars[:] = chars0
+            m_off = pinned_empty(off0.size, np.uint64)
+            m_off[:] = off0
+            m_counts = pinned_empty(n_pat, np.int32)
+            m_status = pinned_empty(n_pat, np.int32)
+            for _ in range(3):
+                mix.count_batch_into(m_chars, m_off, m_counts, m_status)
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                mix.count_batch_into(m_chars, m_off, m_counts, m_status)
+            strong["one_ms"] = (time.perf_counter() - t0) * 1e3
+            if rank == 0 and world > 1:
+                ref_counts = np.empty(n_pat, dtype=np.int32)
+                ix.count_batch_into(np.ascontiguousarray(chars0), np.ascontiguousarray(off0), ref_counts, None)
+                assert np.array_equal(ref_counts, m_counts), "multi-device counts differ from the single-device counts"
+            if int(chars0.max(initial=0)) < 128:
+                m_bytes = pinned_empty(chars0.size, np.uint8)
+                m_bytes[:] = chars0.astype(np.uint8)
+                for _ in range(3):
+                    mix.count_batch_utf8_into(m_bytes, m_off, m_counts, m_status)
+                t0 = time.perf_counter()
+                for _ in range(args.steps):
+                    mix.count_batch_utf8_into(m_bytes, m_off, m_counts, m_status)
+                strong["one_utf8_ms"] = (time.perf_counter() - t0) * 1e3
+            strong["h2d"] = int(chars0.nbytes + off0.nbytes)
+            mix.close()
+        barrier()
+
     times = torch.tensor([ms_total, e2e_s * 1e3, statistics.mean(kernel_ms), lf["loc"]["ms_per_step"] if lf else 0.0,
-                          lf["eub"]["ms_per_step"] if lf else 0.0, lf["loc_e2e_ms"] if lf else 0.0, utf8["s"] * 1e3 if utf8 else 0.0],
+                          lf["eub"]["ms_per_step"] if lf else 0.0, lf["loc_e2e_ms"] if lf else 0.0, utf8["s"] * 1e3 if utf8 else 0.0,
+                          lf["loc"]["kernel_ms"] if lf else 0.0, lf["eub"]["kernel_ms"] if lf else 0.0, strong["dev_ms"] if strong else 0.0],
                          dtype=torch.float64, device=dev)
     sums = torch.tensor([lf["loc"]["hits"] if lf else 0, lf["eub"]["records"] if lf else 0, lf["eub"]["chars"] if lf else 0,
                          lf["loc"]["lf_steps"] if lf else 0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
         dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, kern_ms, loc_ms, eub_ms, loc_e2e_ms, utf8_ms = [float(x) for x in times.cpu()]
+    ms_total, e2e_ms, kern_ms, loc_ms, eub_ms, loc_e2e_ms, utf8_ms, loc_k_ms, eub_k_ms, strong_dev_ms = [float(x) for x in times.cpu()]
     all_hits, all_records, all_chars, all_lf_steps = [float(x) for x in sums.cpu()]
 
     if rank == 0:
@@ -433,6 +533,9 @@ def main():
             "gpu_launches": int(stats["launches"]) * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,
+                         "alg_bytes_per_launch": alg_bytes,
+                         "alg_bytes_formula": "32 * (ranks + level_records) + pattern chars / descriptors: one 32-byte cell per rank and one "
+                                              "32-byte level record per TWO wavelet levels, 32 * (1 + ceil(L / 2)) per rank (DESIGN.md section 5)",
                          "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
                          "level_records_per_launch": stats["level_records"],
                          "records_loaded_per_launch": stats["search_records_loaded"],
@@ -452,13 +555,33 @@ def main():
             out["extract_until_boundary"] = {"metric": "records/sec (extractUntilBoundary('\\n'), dst %d chars, of located hits)" % args.dst_len,
                                              "value": all_records / (eub_ms / 1e3), "unit": "records/s", "chars_per_s": all_chars / (eub_ms / 1e3),
                                              "ms_per_step": eub_ms, "records_per_step": all_records, "launches_per_step": lf["eub"]["launches"]}
-        traffic_file = os.path.join(ROOT, "profiles", "k_count_traffic.json")
+        # roofline objects of the two LF kernels: algorithmic bytes (records the lanes need, workloads.py) over the live kernel time
+        if lf:
+            for key, kname, leg, k_ms in (("locate", "k_locate", lf["loc"], loc_k_ms), ("extract_until_boundary", "k_extract<EUB>", lf["eub"], eub_k_ms)):
+                ach = leg["kernel_alg_bytes"] / (k_ms / 1e3) / 1e9
+                out[key]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                                        "kernel": kname, "kernel_ms": k_ms, "peak_source": peak_src,
+                                        "alg_bytes_per_launch_rank0": leg["kernel_alg_bytes"],
+                                        "records_rank0": leg.get("records") or leg.get("records_read")}
+        # DRAM traffic per launch of each kernel: from the ncu --set full capture of THIS round's kernels (tools/ncu_traffic.py
+        # rewrites profiles/kernel_traffic.json from the capture; the file names the commit and the capture's own kernel times)
+        traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")
         if os.path.exists(traffic_file):
             try:
                 with open(traffic_file) as fh:
-                    out["roofline"]["traffic"] = json.load(fh).get("dram_bytes_per_launch")
+                    tr = json.load(fh)
+                for key, kname in (("roofline", "k_count"), ("locate", "k_locate"), ("extract_until_boundary", "k_extract")):
+                    tgt = out["roofline"] if key == "roofline" else (out.get(key) or {}).get("roofline")
+                    if tgt is not None and kname in tr.get("kernels", {}):
+                        tgt["traffic"] = tr["kernels"][kname].get("dram_bytes_per_launch")
+                        tgt["traffic_source"] = {k: tr.get(k) for k in ("captured_at_commit", "workload", "note")}
+                        tgt["dram_over_requested"] = tr["kernels"][kname].get("dram_over_requested")
             except Exception:
                 pass
+        # the same fraction counting only the records actually loaded (a start / end pair that shares a record loads it once)
+        out["roofline"]["dedup"] = {"records_loaded_bytes": 32.0 * stats["search_records_loaded"],
+                                    "achieved": 32.0 * stats["search_records_loaded"] / (kern_ms / 1e3) / 1e9,
+                                    "frac": 32.0 * stats["search_records_loaded"] / (kern_ms / 1e3) / 1e9 / peak}
         # north-star "fraction of the gather roofline": what the part sustains for dependent, uniformly random 32-byte sector
         # reads (tools/gather_peak.cu -> profiles/r01_gather_peak.jsonl: 38-70 G sectors/s depending on the footprint) next to
         # what k_count moves: record loads it issues, and DRAM sectors (ncu traffic of the committed capture / live kernel time)
@@ -469,30 +592,44 @@ def main():
             "uniform_random_sector_peak_per_s": [38e9, 70e9],
             "note": "k_count runs above the uniform-random rate because cells hit L2 and neighbouring positions share DRAM rows",
         }
+        if strong:
+            out["strong"] = {
+                "workload": "the ONE batch of %d patterns sharded over %d GPUs (BASELINE.json configs[1] as written)" % (n_pat, world),
+                "device_resident": {"value": n_pat * args.steps / (strong_dev_ms / 1e3), "unit": UNIT, "ms_per_step": strong_dev_ms / args.steps,
+                                    "how": "one process per GPU, slice r of the batch resident on GPU r, CUDA events, max over ranks"},
+                "e2e_one_process": {"value": n_pat * args.steps / (strong["one_ms"] / 1e3), "unit": UNIT, "ms_per_step": strong["one_ms"] / args.steps,
+                                    "h2d_bytes_per_step": strong.get("h2d"), "d2h_bytes_per_step": 8 * n_pat,
+                                    "how": "rank 0 alone: one fmgpu_index replicated on all %d GPUs by the library, one fmgpu_count_batch call per step with pinned host buffers" % world},
+                "e2e_one_process_utf8": ({"value": n_pat * args.steps / (strong["one_utf8_ms"] / 1e3), "unit": UNIT,
+                                          "ms_per_step": strong["one_utf8_ms"] / args.steps} if strong["one_utf8_ms"] else None),
+            }
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, dt, cpu_counts, oracle_ix = cpu_count_throughput(blob, chars, off, args.cpu_sample, threads, args.cpu_repeats)
+            oracle_ix, build = load_oracle(blob)
+            v, dt, cpu_counts = cpu_count_throughput(oracle_ix, chars, off, args.cpu_sample, threads, args.cpu_repeats)
             assert np.array_equal(cpu_counts, h_counts[: cpu_counts.size]), "GPU counts differ from the CPU oracle"
-            if lf:  # spot-check the LF legs against the oracle as well (200 patterns / records)
-                k = 200
-                ho = lf["d_hit_off"][: k + 1].cpu().numpy().astype(np.int64)
-                pos = lf["d_pos"][: int(ho[-1])].cpu().numpy()
-                w_n, w_pos, _ = oracle_ix.locate_batch(chars[: int(off[k])], off[: k + 1], args.max_hits, max(args.max_hits, 1), threads=threads)
-                assert np.array_equal(np.diff(ho), w_n), "locate hit counts differ from the CPU oracle"
-                for i in range(k):
-                    assert np.array_equal(pos[ho[i]: ho[i + 1]], w_pos[i, : w_n[i]]), "located positions differ from the CPU oracle"
-                frm = lf["d_from"][:k].cpu().numpy().astype(np.int32)
-                w_arena, w_ln, w_st = oracle_ix.extract_until_boundary_batch(frm, 10, args.dst_len, 0, threads=threads)
-                arena = lf["d_arena"][:k].cpu().numpy().view(np.uint16)
-                assert np.array_equal(lf["d_st"][:k].cpu().numpy(), w_st) and np.array_equal(lf["d_len"][:k].cpu().numpy()[w_st == 0], w_ln[w_st == 0])
-                for i in range(k):
-                    if w_st[i] == 0:
-                        assert np.array_equal(arena[i, : w_ln[i]], w_arena[i, : w_ln[i]]), "extracted record differs from the CPU oracle"
-                out["locate"]["oracle_checked_patterns"] = k
-                out["extract_until_boundary"]["oracle_checked_records"] = k
-            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "build": build,
+                                   "patterns_per_s_by_threads": cpu_thread_scaling(oracle_ix, chars, off, 100_000, threads),
                                    "sample": "first %d of the %d patterns, best of %d passes, %.1fs per pass (C++ restatement of the reference's Java loops; no JVM in this image)"
                                              % (cpu_counts.size, n_pat, args.cpu_repeats, dt)}
+            if lf:  # CPU arms of the LF legs on bounded samples; their outputs double as the parity check of the GPU legs
+                frm = lf["d_from"][: args.cpu_eub_sample].cpu().numpy().astype(np.int32)
+                arms = cpu_lf_arms(oracle_ix, chars, off, args, threads, frm)
+                k, w_n, w_pos, m, w_arena, w_ln, w_st = arms.pop("_check")
+                ho = lf["d_hit_off"][: k + 1].cpu().numpy().astype(np.int64)
+                pos = lf["d_pos"][: int(ho[-1])].cpu().numpy()
+                assert np.array_equal(np.diff(ho), w_n), "locate hit counts differ from the CPU oracle"
+                flat = np.concatenate([w_pos[i, : w_n[i]] for i in range(k)]) if k else np.zeros(0, np.int32)
+                assert np.array_equal(pos, flat), "located positions differ from the CPU oracle"
+                arena = lf["d_arena"][:m].cpu().numpy().view(np.uint16)
+                assert np.array_equal(lf["d_st"][:m].cpu().numpy(), w_st) and np.array_equal(lf["d_len"][:m].cpu().numpy()[w_st == 0], w_ln[w_st == 0])
+                cols = np.arange(arena.shape[1])[None, :]
+                valid = (cols < w_ln[:, None]) & (w_st == 0)[:, None]
+                assert np.array_equal(arena[valid], w_arena[valid]), "extracted records differ from the CPU oracle"
+                out["locate"]["oracle_checked_patterns"] = k
+                out["locate"]["cpu_baseline"] = arms["locate"]
+                out["extract_until_boundary"]["oracle_checked_records"] = m
+                out["extract_until_boundary"]["cpu_baseline"] = arms["extract_until_boundary"]
         emit(out)
     ix.close()
     if world > 1:

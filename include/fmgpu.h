@@ -15,7 +15,9 @@
  *   - "chars" are UTF-16 code units exactly as in a Java char[]; pattern i is
  *     chars[pat_off[i] .. pat_off[i+1]).
  *   - *_device variants take DEVICE pointers and a cudaStream_t (as void*), enqueue asynchronously and
- *     never synchronize; the host-pointer variants copy H2D, run, copy D2H and synchronize.
+ *     do not wait for their work (fmgpu_locate_batch_device synchronizes once to learn the hit total); calls that end up
+ *     sharing internal scratch buffers are ordered on the device by events, whatever streams they were given.  The
+ *     host-pointer variants copy H2D, run, copy D2H and synchronize.
  *   - there is no CPU fallback: without a CUDA device every call fails with FMGPU_ERR_CUDA.
  */
 #ifndef FMGPU_H
@@ -59,9 +61,12 @@ extern "C" {
 typedef struct fmgpu_index fmgpu_index;
 
 typedef struct fmgpu_opts {
-    int32_t device;        /* CUDA device ordinal; -1 = current device */
-    int32_t host_threads;  /* threads used to re-lay the index out at load; 0 = all cores */
-    uint64_t reserved[3];
+    int32_t device;         /* CUDA device ordinal (used when n_devices == 0); -1 = current device */
+    int32_t host_threads;   /* threads used to re-lay the index out at load; 0 = all cores */
+    int32_t n_devices;      /* > 0: replicate the index on devices[0 .. n_devices); < 0: on every visible device; 0: `device` alone */
+    int32_t reserved0;
+    const int32_t* devices; /* device ordinals, distinct */
+    uint64_t reserved[1];
 } fmgpu_opts;
 
 const char* fmgpu_last_error(void);
@@ -70,7 +75,13 @@ const char* fmgpu_version(void);
 /* Replaces Serialization.readFromByteArray(FmIndex::read, bytes) (SER:89-100, FM:983-1025).
  * Accepts the ObjectOutputStream framing (AC ED 00 05 + block-data records) or the bare
  * DataOutput primitives.  Parses the stream, re-lays the structures out into the device format
- *  and uploads them once.  opts may be NULL. */
+ *  and uploads them once.  opts may be NULL.
+ *
+ * The handle is the reference's one immutable, @ThreadSafe FmIndex (FM:82): with a device list in opts the layout is uploaded
+ * to the first device and copied to the others over NVLink (cudaMemcpyPeer); every host-pointer batch call then cuts the
+ * caller's batch into one contiguous slice per device, runs the slices at once and writes disjoint ranges of the caller's
+ * outputs.  Any number of host threads may call into one handle concurrently (each call leases its own streams and scratch
+ * buffers on the devices it uses).  The *_device entry points run on the replica whose device holds the caller's buffers. */
 int fmgpu_index_load_serialized(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_index** out);
 void fmgpu_index_free(fmgpu_index* idx);
 
@@ -78,11 +89,21 @@ int32_t fmgpu_input_length(const fmgpu_index* idx);     /* FmIndex.getInputLengt
 int32_t fmgpu_alphabet_length(const fmgpu_index* idx);  /* FmIndex.getAlphabetLength() FM:939 */
 int32_t fmgpu_sample_rate(const fmgpu_index* idx);
 int32_t fmgpu_extract_enabled(const fmgpu_index* idx);
-int32_t fmgpu_device(const fmgpu_index* idx);
+int32_t fmgpu_device(const fmgpu_index* idx);             /* the first (primary) device */
+int32_t fmgpu_num_devices(const fmgpu_index* idx);        /* replicas */
+int32_t fmgpu_device_at(const fmgpu_index* idx, int32_t i);
 uint64_t fmgpu_device_bytes(const fmgpu_index* idx);    /* bytes of HBM held by the index */
 /* component sizes (bytes): [0] cells [1] level sectors [2] node records [3] block descriptors
  * [4] path overflow [5] sampled-row groups+offsets [6] SA samples [7] ISA samples */
 void fmgpu_layout_bytes(const fmgpu_index* idx, uint64_t out8[8]);
+
+/* Page-locked host memory.  The host-pointer batch calls copy with cudaMemcpyAsync, which only overlaps with the kernels (and
+ * reaches the PCIe rate) from page-locked buffers: register the caller's arrays once (a Java host: the MemorySegments of its
+ * Arena) or allocate them here.  Pageable buffers still work, at a fraction of the rate. */
+int fmgpu_host_register(void* p, size_t bytes);
+int fmgpu_host_unregister(void* p);
+int fmgpu_host_alloc(size_t bytes, void** out);
+int fmgpu_host_free(void* p);
 
 /* FmIndex.count(char[] p, int off, int len)  FM:455-474 — one result per pattern.
  * status_out may be NULL. */
@@ -133,21 +154,26 @@ int fmgpu_locate_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const u
                               int32_t* d_positions_out, uint64_t positions_cap, int32_t* d_status_out,
                               uint64_t* total_hits_out, void* cuda_stream);
 
-/* FmIndex.extract(int start, int stop, char[] dst, int off)  FM:564-608 with dst = the slot
- * arena[arena_off[i] .. arena_off[i+1]) and off = 0.  len_out[i] = stop-start on success. */
+/* FmIndex.extract(int start, int stop, char[] destination, int offset)  FM:564-608 with destination = the slot
+ * arena[arena_off[i] .. arena_off[i+1]) (its length is destination.length) and the same `offset` (>= 0) for every item:
+ * the chars land at slot + offset, "Supplied destination is not large enough" when destination.length - offset < stop - start
+ * (FM:591).  len_out[i] = stop - start on success. */
 int fmgpu_extract_batch(fmgpu_index* idx, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena,
-                        const uint64_t* arena_off, int32_t* len_out, int32_t* status_out);
+                        const uint64_t* arena_off, int32_t offset, int32_t* len_out, int32_t* status_out);
 int fmgpu_extract_batch_device(fmgpu_index* idx, const int32_t* d_start, const int32_t* d_stop, uint32_t n, uint16_t* d_arena,
-                               const uint64_t* d_arena_off, int32_t* d_len_out, int32_t* d_status_out, void* cuda_stream);
+                               const uint64_t* d_arena_off, int32_t offset, int32_t* d_len_out, int32_t* d_status_out, void* cuda_stream);
 
-/* FmIndex.extractUntilBoundary / ...Left / ...Right (FM:640-922) with dst = new char[dst_len],
- * off = 0: slot i is arena[i*dst_len .. (i+1)*dst_len).  len_out[i] = returned length (or N of the
- * "does not fit" message when status is FMGPU_ST_DOES_NOT_FIT).  Only arena[i*dst_len, +len) is
- * defined, like the Java array beyond the returned length. */
+/* FmIndex.extractUntilBoundary / ...Left / ...Right (int from, char[] destination, int offset, char boundary) (FM:640-922) with
+ * destination = new char[dst_len] = the slot arena[i*dst_len .. (i+1)*dst_len) and the same `offset` (>= 0) for every item.  As in
+ * the reference the record lands at slot + offset, the left walk may use the WHOLE destination as scratch (remaining =
+ * destination.length, FM:662) and `offset` enters the "does not fit" test and its N (FM:732-737, :817-821, :894-898) but not
+ * the returned length; a left part that does not fit behind `offset` makes System.arraycopy throw (FM:688-690): status
+ * FMGPU_ST_INDEX_OOB.  len_out[i] = returned length (or N of the "does not fit" message when status is
+ * FMGPU_ST_DOES_NOT_FIT).  Only arena[i*dst_len + offset, +len) is defined, like the Java array beyond the returned length. */
 int fmgpu_extract_until_boundary_batch(fmgpu_index* idx, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len,
-                                       int32_t mode, uint16_t* arena, int32_t* len_out, int32_t* status_out);
+                                       int32_t offset, int32_t mode, uint16_t* arena, int32_t* len_out, int32_t* status_out);
 int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d_from, uint32_t n, uint16_t boundary,
-                                              int32_t dst_len, int32_t mode, uint16_t* d_arena, int32_t* d_len_out,
+                                              int32_t dst_len, int32_t offset, int32_t mode, uint16_t* d_arena, int32_t* d_len_out,
                                               int32_t* d_status_out, void* cuda_stream);
 
 /* The index's wavelet structure (FmIndex.waveletFixedBlockBoosting) queried directly — the reference's public
@@ -204,6 +230,12 @@ int fmgpu_last_stats_ex(fmgpu_index* idx, uint64_t* out, uint32_t n_out);
  * time of the kernel launched `calls_back` calls ago (0 = the most recent; up to 64 are kept). */
 int fmgpu_set_timing(fmgpu_index* idx, int enable);
 int fmgpu_search_kernel_ms(fmgpu_index* idx, uint32_t calls_back, float* ms_out);
+/* The same for each of the three dominant kernels, on replica `device_index` (0 = the primary device): the launch of that
+ * kind `calls_back` launches ago. */
+#define FMGPU_KERNEL_COUNT 0   /* k_count:   backward search */
+#define FMGPU_KERNEL_LOCATE 1  /* k_locate:  LF walks of locate */
+#define FMGPU_KERNEL_EXTRACT 2 /* k_extract: LF walks of extract / extractUntilBoundary* */
+int fmgpu_kernel_ms(fmgpu_index* idx, int32_t kind, uint32_t device_index, uint32_t calls_back, float* ms_out);
 
 #ifdef __cplusplus
 }

@@ -35,7 +35,7 @@ def _newer(target: str, sources: list[str]) -> bool:
     return all(os.path.getmtime(s) <= t for s in sources)
 
 
-def _sources(d: str, exts=(".cu", ".cuh", ".h", ".hpp", ".cpp")) -> list[str]:
+def _sources(d: str, exts=(".cu", ".cuh", ".h", ".hpp", ".cpp", ".inc")) -> list[str]:
     out = []
     for base, _, files in os.walk(d):
         for f in files:

@@ -85,16 +85,16 @@ __global__ void k_expand_rows(const uint32_t* __restrict__ ranges, const int32_t
     }
 }
 
-// arena[i][q] = left[i][down-1-q]: the left part was produced right-to-left (one warp per item)
+// arena[i][offset + q] = left[i][down-1-q]: the left part was produced right-to-left (one warp per item)
 __global__ void k_eub_assemble(const uint16_t* __restrict__ left, const int32_t* __restrict__ down_len, uint32_t n, int32_t dst_len,
-                               uint16_t* __restrict__ arena) {
+                               int32_t offset, uint16_t* __restrict__ arena) {
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t lane = threadIdx.x & 31u;
     for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n; w += warps) {
         int32_t d = down_len[w];
-        if (d > dst_len) d = dst_len;
+        if (d > dst_len - offset) d = dst_len - offset;  // (a left part that does not fit behind `offset` has status 9)
         const uint64_t slot = (uint64_t)w * (uint64_t)dst_len;
-        for (int32_t q = (int32_t)lane; q < d; q += 32) arena[slot + (uint64_t)q] = left[slot + (uint64_t)(d - 1 - q)];
+        for (int32_t q = (int32_t)lane; q < d; q += 32) arena[slot + (uint64_t)(offset + q)] = left[slot + (uint64_t)(d - 1 - q)];
     }
 }
 

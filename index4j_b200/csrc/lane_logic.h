@@ -226,7 +226,10 @@ struct EubOut {
     int32_t status, value;
 };
 
-FMGPU_HD EubOut eub_right_chunks(int32_t from, int32_t down_len, int32_t rel, int32_t length, int32_t dst_len, bool right_only) {
+// `offset` = the reference's offset argument: it shifts where the chars land and enters the "does not fit" test and its N
+// (:732-737, :894-898), not the returned length.
+FMGPU_HD EubOut eub_right_chunks(int32_t from, int32_t down_len, int32_t rel, int32_t length, int32_t dst_len, bool right_only,
+                                 int32_t offset = 0) {
     EubOut o;
     o.status = 0;
     o.value = 0;
@@ -246,7 +249,7 @@ FMGPU_HD EubOut eub_right_chunks(int32_t from, int32_t down_len, int32_t rel, in
                 o.value = 0;
                 return o;  // "return 0" (:719 / :877)
             }
-            const int32_t limit = right_only ? top : down_len + top;
+            const int32_t limit = offset + (right_only ? top : down_len + top);
             if (limit >= dst_len) {
                 o.status = 8;
                 o.value = limit;

@@ -187,8 +187,9 @@ struct ExLane {
             skip = sr - sp % sr;
             if (sp / sr == (int32_t)ix.n_isa - 2) skip = (int32_t)ix.length - sp;
             const int32_t range = sp - st;
-            const int64_t room = (int64_t)(raw.o1 - raw.o0);
+            const int64_t room = (int64_t)(raw.o1 - raw.o0) - (int64_t)P.offset;  // destination.length - offset (:591)
             if (room < (int64_t)range) return finish(P, 5, 0);
+            out0 += (uint64_t)P.offset;
             remaining = range;
             k = range;
             if (range <= 0) return finish(P, 0, range);
@@ -237,7 +238,7 @@ struct ExLane {
                     P.left[slot + (uint64_t)k] = ix.code2char[sym];
                     ++k;
                     down = k;
-                    if (idx - 1 == 0) return finish(P, 8, P.dst_len);  // :817-821
+                    if (idx - 1 == P.offset) return finish(P, 8, P.dst_len - P.offset);  // :817-821
                 } else {
                     P.left[slot + (uint64_t)k] = ix.code2char[sym];
                     ++k;
@@ -248,6 +249,9 @@ struct ExLane {
             ++dist;
             if (!stop_left) return;
             down = k;
+            // System.arraycopy(destination, downStreamPos + 1, destination, offset, downStreamLength) (:688-690, :827-829)
+            // throws when the left part does not fit behind `offset`
+            if ((int64_t)P.offset + k > (int64_t)P.dst_len) return finish(P, 9, 0);
             if (P.eub_mode == 1) return finish(P, 0, k);
             stage = 1;
             cur = from;
@@ -259,10 +263,10 @@ struct ExLane {
         if (p >= from && p < (int32_t)ix.length - 1) {
             if (sym == P.mb) pb = p;
             if (P.eub_mode == 2) {
-                const int32_t idx = p - from - 1;
-                if (idx >= 0 && idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
+                const int64_t idx = (int64_t)P.offset + (p - from - 1);
+                if (p - from - 1 >= 0 && idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
             } else {
-                const int64_t idx = (int64_t)down + (p - from);
+                const int64_t idx = (int64_t)P.offset + down + (p - from);
                 if (idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
             }
         }
@@ -285,7 +289,7 @@ struct ExLane {
             cur = end;
             begin_right(ix);
         } else {
-            const EubOut o = eub_right_chunks(from, down, rel, (int32_t)ix.length, P.dst_len, P.eub_mode == 2);
+            const EubOut o = eub_right_chunks(from, down, rel, (int32_t)ix.length, P.dst_len, P.eub_mode == 2, P.offset);
             finish(P, o.status, o.value);
         }
     }

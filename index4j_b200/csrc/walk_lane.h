@@ -25,6 +25,7 @@ struct WalkParams {
     uint32_t mb;        // alphabet code of the boundary char (0 = not in the alphabet)
     int32_t dst_len;
     int32_t eub_mode;   // FMGPU_MODE_*
+    int32_t offset;     // the reference's `offset` argument (extract :564, extractUntilBoundary* :640 / :772 / :844), >= 0
     uint16_t* left;     // left-part scratch, item i at i*dst_len, chars in walk order (text order reversed)
     int32_t* down_len;  // chars in the left part
     // outputs

@@ -92,10 +92,18 @@ def native():
         L.fmgpu_count_batch_utf8_device.argtypes = [vp, vp, vp, u64, u32, vp, vp, vp]
         L.fmgpu_locate_batch_utf8.argtypes = [vp, vp, vp, u32, i32, vp, vp, vp, u64, vp]
         L.fmgpu_locate_batch_device.argtypes = [vp, vp, vp, u64, u32, i32, vp, vp, vp, u64, vp, C.POINTER(u64), vp]
-        L.fmgpu_extract_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
-        L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
-        L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp]
-        L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, vp, vp, vp, vp]
+        L.fmgpu_extract_batch.argtypes = [vp, vp, vp, u32, vp, vp, i32, vp, vp]
+        L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, i32, vp, vp, vp]
+        L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, i32, vp, vp, vp]
+        L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, i32, vp, vp, vp, vp]
+        L.fmgpu_num_devices.argtypes = [vp]
+        L.fmgpu_num_devices.restype = i32
+        L.fmgpu_device_at.argtypes = [vp, i32]
+        L.fmgpu_device_at.restype = i32
+        L.fmgpu_host_register.argtypes = [vp, C.c_size_t]
+        L.fmgpu_host_unregister.argtypes = [vp]
+        L.fmgpu_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+        L.fmgpu_host_free.argtypes = [vp]
         L.fmgpu_wavelet_load_serialized.argtypes = [vp, u64, vp, vp]
         L.fmgpu_rrr_load_serialized.argtypes = [vp, u64, vp, vp]
         L.fmgpu_rrr_rank_access_batch.argtypes = [vp, vp, u32, vp, vp, vp]
@@ -108,12 +116,38 @@ def native():
         L.fmgpu_set_start_table.argtypes = [vp, i32]
         L.fmgpu_start_table_q.argtypes = [vp]
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
+        L.fmgpu_kernel_ms.argtypes = [vp, i32, u32, u32, C.POINTER(C.c_float)]
         _lib = L
     return _lib
 
 
 class _Opts(C.Structure):
-    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("reserved", C.c_uint64 * 3)]
+    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("n_devices", C.c_int32), ("reserved0", C.c_int32),
+                ("devices", C.POINTER(C.c_int32)), ("reserved", C.c_uint64 * 1)]
+
+
+def pinned_empty(n: int, dtype) -> np.ndarray:
+    """A page-locked numpy array from ``fmgpu_host_alloc`` (what a host hands to the ``*_into`` calls so that the copies overlap
+    with the kernels and run at the PCIe rate).  The memory is released when the array (and every view of it) is gone."""
+    lib = native()
+    dt = np.dtype(dtype)
+    nbytes = max(int(n) * dt.itemsize, 1)
+    p = C.c_void_p()
+    if lib.fmgpu_host_alloc(nbytes, C.byref(p)) != 0:
+        raise FmIndexError(lib.fmgpu_last_error().decode())
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dt, count=int(n))
+    _PINNED[p.value] = buf  # keeps the ctypes view alive; freed by pinned_free / at exit
+    return arr
+
+
+_PINNED = {}
+
+
+def pinned_free(arr: np.ndarray):
+    addr = arr.ctypes.data
+    if _PINNED.pop(addr, None) is not None:
+        native().fmgpu_host_free(addr)
 
 
 def _u16(a) -> np.ndarray:
@@ -141,11 +175,21 @@ class FmIndex:
 
     # --- construction --------------------------------------------------------------------
     @classmethod
-    def read(cls, serialized, device: int | None = None, host_threads: int = 0) -> "FmIndex":
-        """``Serialization.readFromByteArray(FmIndex::read, bytes)`` (Serialization.java:89, FmIndex.java:983)."""
+    def read(cls, serialized, device: int | None = None, host_threads: int = 0, devices=None) -> "FmIndex":
+        """``Serialization.readFromByteArray(FmIndex::read, bytes)`` (Serialization.java:89, FmIndex.java:983).
+
+        ``devices``: a list of CUDA ordinals (or ``"all"``) — the index is replicated on each of them and every host-pointer batch
+        call is cut into one slice per device."""
         lib = native()
         buf = np.frombuffer(serialized, dtype=np.uint8)
         opts = _Opts(-1 if device is None else int(device), int(host_threads))
+        if devices is not None:
+            if isinstance(devices, str):
+                opts.n_devices = -1
+            else:
+                arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+                opts.n_devices = len(devices)
+                opts.devices = C.cast(arr, C.POINTER(C.c_int32))
         h = C.c_void_p()
         rc = lib.fmgpu_index_load_serialized(buf.ctypes.data, buf.size, C.byref(opts), C.byref(h))
         if rc != 0:
@@ -185,6 +229,10 @@ class FmIndex:
     def device(self) -> int:
         return self._lib.fmgpu_device(self._h)
 
+    @property
+    def devices(self) -> list:
+        return [int(self._lib.fmgpu_device_at(self._h, i)) for i in range(int(self._lib.fmgpu_num_devices(self._h)))]
+
     def device_bytes(self) -> int:
         return int(self._lib.fmgpu_device_bytes(self._h))
 
@@ -218,6 +266,12 @@ class FmIndex:
     def search_kernel_ms(self, calls_back: int = 0) -> float:
         ms = C.c_float()
         self._check(self._lib.fmgpu_search_kernel_ms(self._h, calls_back, C.byref(ms)))
+        return float(ms.value)
+
+    def kernel_ms(self, kind: int, calls_back: int = 0, device_index: int = 0) -> float:
+        """Device time of a launch of k_count (kind 0), k_locate (1) or k_extract (2) on replica ``device_index``; needs set_timing."""
+        ms = C.c_float()
+        self._check(self._lib.fmgpu_kernel_ms(self._h, kind, device_index, calls_back, C.byref(ms)))
         return float(ms.value)
 
     def count_batch_into(self, chars: np.ndarray, pat_off: np.ndarray, counts: np.ndarray, status: np.ndarray | None = None):
@@ -309,31 +363,33 @@ class FmIndex:
         self._check(self._lib.fmgpu_wavelet_inverse_select_batch(self._h, pos.ctypes.data, pos.size, out.ctypes.data, st.ctypes.data))
         return out, st
 
-    def extract_batch(self, start, stop, arena_off=None):
-        """-> (arena uint16[..], arena_off, len int32[n], status int32[n]); slot i = arena[arena_off[i]:arena_off[i+1]]"""
+    def extract_batch(self, start, stop, arena_off=None, offset: int = 0):
+        """-> (arena uint16[..], arena_off, len int32[n], status int32[n]); slot i = arena[arena_off[i]:arena_off[i+1]] is the
+        reference's ``destination``, the chars land ``offset`` slots into it"""
         start = np.ascontiguousarray(start, dtype=np.int32)
         stop = np.ascontiguousarray(stop, dtype=np.int32)
         n = start.size
         if arena_off is None:
             arena_off = np.zeros(n + 1, dtype=np.uint64)
-            arena_off[1:] = np.cumsum(np.maximum(stop.astype(np.int64) - start.astype(np.int64), 0))
+            arena_off[1:] = np.cumsum(np.maximum(stop.astype(np.int64) - start.astype(np.int64), 0) + int(offset))
         arena_off = np.ascontiguousarray(arena_off, dtype=np.uint64)
         arena = np.zeros(max(int(arena_off[-1]), 1), dtype=np.uint16)
         ln = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
         self._check(self._lib.fmgpu_extract_batch(self._h, start.ctypes.data, stop.ctypes.data, n, arena.ctypes.data, arena_off.ctypes.data,
-                                                  ln.ctypes.data, st.ctypes.data))
+                                                  int(offset), ln.ctypes.data, st.ctypes.data))
         return arena, arena_off, ln, st
 
-    def extract_until_boundary_batch(self, frm, boundary, dst_len: int, mode: int = MODE_BOTH):
-        """-> (arena uint16[n, dst_len], len int32[n], status int32[n])"""
+    def extract_until_boundary_batch(self, frm, boundary, dst_len: int, mode: int = MODE_BOTH, offset: int = 0):
+        """-> (arena uint16[n, dst_len], len int32[n], status int32[n]); row i is the reference's ``destination`` (dst_len chars),
+        the record starts at column ``offset``"""
         frm = np.ascontiguousarray(frm, dtype=np.int32)
         n = frm.size
         b = ord(boundary) if isinstance(boundary, str) else int(boundary)
         arena = np.zeros((n, max(dst_len, 1)), dtype=np.uint16)
         ln = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
-        self._check(self._lib.fmgpu_extract_until_boundary_batch(self._h, frm.ctypes.data, n, b, dst_len, mode,
+        self._check(self._lib.fmgpu_extract_until_boundary_batch(self._h, frm.ctypes.data, n, b, dst_len, int(offset), mode,
                                                                  arena.ctypes.data if dst_len > 0 else None, ln.ctypes.data, st.ctypes.data))
         return arena, ln, st
 
@@ -376,29 +432,29 @@ class FmIndex:
 
     def extract(self, start: int, stop: int, destination=None, offset: int = 0):
         """``FmIndex.extract(int start, int stop, char[] destination, int offset)`` (:564)."""
-        room = (len(destination) - offset) if destination is not None else max(stop - start, 0)
-        arena, _, ln, st = self.extract_batch([start], [stop], np.array([0, max(room, 0)], dtype=np.uint64))
+        room = len(destination) if destination is not None else max(stop - start, 0) + offset
+        arena, _, ln, st = self.extract_batch([start], [stop], np.array([0, max(room, 0)], dtype=np.uint64), offset)
         if st[0]:
             raise_status(st[0])
-        if destination is None:
-            return arena[: max(int(ln[0]), 0)].copy()
         k = max(int(ln[0]), 0)
-        destination[offset: offset + k] = arena[:k]
+        if destination is None:
+            return arena[offset: offset + k].copy()
+        destination[offset: offset + k] = arena[offset: offset + k]
         return int(ln[0])
 
     def _eub(self, frm, destination, offset, boundary, mode):
-        if isinstance(destination, int):
+        if isinstance(destination, int):  # destination = new char[destination]
             dst_len, dest = destination, None
         else:
-            dst_len, dest = len(destination) - offset, destination
-        arena, ln, st = self.extract_until_boundary_batch([frm], boundary, max(dst_len, 0), mode)
+            dst_len, dest = len(destination), destination
+        arena, ln, st = self.extract_until_boundary_batch([frm], boundary, max(dst_len, 0), mode, offset)
         if st[0]:
             raise_status(st[0], ln[0])
-        k = int(ln[0])
+        k = max(int(ln[0]), 0)
         if dest is None:
-            return arena[0, : max(k, 0)].copy()
-        dest[offset: offset + max(k, 0)] = arena[0, : max(k, 0)]
-        return k
+            return arena[0, offset: offset + k].copy()
+        dest[offset: offset + k] = arena[0, offset: offset + k]
+        return int(ln[0])
 
     def extractUntilBoundary(self, frm: int, destination, offset: int = 0, boundary="\n"):
         """``FmIndex.extractUntilBoundary(int from, char[] destination, int offset, char boundary)`` (:640)."""
@@ -432,17 +488,18 @@ class FmIndex:
                                                         d_status.data_ptr() if d_status is not None else None, C.byref(total), stream))
         return int(total.value)
 
-    def extract_until_boundary_batch_device(self, d_from, boundary, dst_len, mode, d_arena, d_len, d_status, stream: int | None = None):
+    def extract_until_boundary_batch_device(self, d_from, boundary, dst_len, mode, d_arena, d_len, d_status, stream: int | None = None,
+                                            offset: int = 0):
         import torch
         if stream is None:
             stream = torch.cuda.current_stream(d_from.device).cuda_stream
         b = ord(boundary) if isinstance(boundary, str) else int(boundary)
-        self._check(self._lib.fmgpu_extract_until_boundary_batch_device(self._h, d_from.data_ptr(), d_from.numel(), b, dst_len, mode,
+        self._check(self._lib.fmgpu_extract_until_boundary_batch_device(self._h, d_from.data_ptr(), d_from.numel(), b, dst_len, int(offset), mode,
                                                                         d_arena.data_ptr(), d_len.data_ptr(), d_status.data_ptr(), stream))
 
-    def extract_batch_device(self, d_start, d_stop, d_arena, d_arena_off, d_len, d_status, stream: int | None = None):
+    def extract_batch_device(self, d_start, d_stop, d_arena, d_arena_off, d_len, d_status, stream: int | None = None, offset: int = 0):
         import torch
         if stream is None:
             stream = torch.cuda.current_stream(d_start.device).cuda_stream
         self._check(self._lib.fmgpu_extract_batch_device(self._h, d_start.data_ptr(), d_stop.data_ptr(), d_start.numel(), d_arena.data_ptr(),
-                                                         d_arena_off.data_ptr(), d_len.data_ptr(), d_status.data_ptr(), stream))
+                                                         d_arena_off.data_ptr(), int(offset), d_len.data_ptr(), d_status.data_ptr(), stream))

@@ -22,6 +22,11 @@ def _timed(fn, steps: int, warmup: int) -> float:
     return e0.elapsed_time(e1) / steps
 
 
+def _kernel_ms(ix, kind: int, steps: int) -> float:
+    """mean device time of the last `steps` launches of one kernel kind (events recorded by the library on the launching stream)"""
+    return float(np.mean([ix.kernel_ms(kind, i) for i in range(min(steps, 64))]))
+
+
 def _counted(ix, fn) -> dict:
     """Work counters of one extra, untimed pass with the instrumented kernels (the timed passes run the production ones)."""
     ix.set_stats(True)
@@ -44,11 +49,15 @@ def locate_workload(ix, d_chars, d_off, max_hits: int, steps: int, warmup: int):
     d_pos = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     fn = lambda: ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, d_pos, d_status)  # noqa: E731
     ms = _timed(fn, steps, warmup)
+    k_ms = _kernel_ms(ix, 1, steps)
     st = _counted(ix, fn)
     # algorithmic 32-byte records: per sampled-row test 1 group record; per LF step 1 block descriptor; per TWO wavelet levels
-    # 1 level record + 1 node record; per generic rank 1 cell; per hit 1 SA record
+    # 1 level record + 1 node record; per generic rank 1 cell; per hit 1 SA record (+ 4 bytes read and 4 written per hit row)
     recs = st["sampled_tests"] + st["lf_steps"] + 2 * st["level_records"] + st["ranks"] + total
     out = {"patterns": n_pat, "max_hits": max_hits, "hits": int(total), "ms_per_step": ms, "hits_per_s": total / (ms / 1e3),
+           "kernel_ms": k_ms, "kernel_alg_bytes": 32.0 * recs + 8.0 * total,
+           "records": {"sampled_row_groups": st["sampled_tests"], "block_descriptors": st["lf_steps"], "level_records": st["level_records"],
+                       "node_records": st["level_records"], "cells": st["ranks"], "sa_records": int(total)},
            "lf_steps": st["lf_steps"], "lf_steps_per_s": st["lf_steps"] / (ms / 1e3), "lf_levels": st["lf_levels"],
            "sampled_tests": st["sampled_tests"], "generic_ranks": st["ranks"], "launches": st["launches"],
            "alg_bytes": 32.0 * recs, "alg_gb_per_s": 32.0 * recs / (ms / 1e3) / 1e9}
@@ -64,9 +73,17 @@ def eub_workload(ix, d_from, dst_len: int, steps: int, warmup: int, boundary="\n
     d_st = torch.empty(n, dtype=torch.int32, device=dev)
     fn = lambda: ix.extract_until_boundary_batch_device(d_from, boundary, dst_len, mode, d_arena, d_len, d_st)  # noqa: E731
     ms = _timed(fn, steps, warmup)
+    k_ms = _kernel_ms(ix, 2, steps)
     st = _counted(ix, fn)
     ok_chars = int(d_len[d_st == 0].sum().item())
+    # algorithmic bytes of k_extract: per LF step 1 block descriptor, per TWO wavelet levels 1 level + 1 node record, per generic
+    # rank 1 cell, per sample interval walked 1 inverse-SA record (~ LF steps / sampleRate, + 1 per record), 2 bytes per char written
+    isa = st["lf_steps"] // max(ix.sample_rate, 1) + n
+    recs = st["lf_steps"] + 2 * st["level_records"] + st["ranks"] + isa
     out = {"records": n, "dst_len": dst_len, "ms_per_step": ms, "records_per_s": n / (ms / 1e3), "chars": ok_chars,
+           "kernel_ms": k_ms, "kernel_alg_bytes": 32.0 * recs + 2.0 * ok_chars + 12.0 * n,
+           "records_read": {"block_descriptors": st["lf_steps"], "level_records": st["level_records"], "node_records": st["level_records"],
+                            "cells": st["ranks"], "isa_records": isa},
            "chars_per_s": ok_chars / (ms / 1e3), "status_nonzero": int((d_st != 0).sum().item()), "lf_steps": st["lf_steps"],
            "lf_steps_per_s": st["lf_steps"] / (ms / 1e3), "lf_levels": st["lf_levels"], "generic_ranks": st["ranks"],
            "launches": st["launches"]}

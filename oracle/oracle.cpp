@@ -1057,22 +1057,24 @@ void orc_fm_locate_batch(void* h, const uint16_t* chars, const uint64_t* pat_off
         if (status) status[i] = st;
     });
 }
+// every item: extract(start, stop, destination = new char[stride], offset)
 void orc_fm_extract_batch(void* h, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena, int64_t stride, int32_t* len_out,
-                          int32_t* status, int32_t threads) {
+                          int32_t* status, int32_t threads, int32_t offset) {
     FmIndex* f = (FmIndex*)h;
     parallel_for((int64_t)n, threads, [&](int64_t i) {
         int32_t k = 0;
-        int st = orc_fm_extract(f, start[i], stop[i], arena + i * stride, stride, 0, &k);
+        int st = orc_fm_extract(f, start[i], stop[i], arena + i * stride, stride, offset, &k);
         len_out[i] = k;
         status[i] = st;
     });
 }
+// every item: extractUntilBoundary*(from, destination = new char[dst_len], offset, boundary)
 void orc_fm_extract_until_boundary_batch(void* h, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len, int32_t mode,
-                                         uint16_t* arena, int32_t* len_out, int32_t* status, int32_t threads) {
+                                         uint16_t* arena, int32_t* len_out, int32_t* status, int32_t threads, int32_t offset) {
     FmIndex* f = (FmIndex*)h;
     parallel_for((int64_t)n, threads, [&](int64_t i) {
         int32_t k = 0;
-        int st = orc_fm_extract_until_boundary(f, from[i], arena + (int64_t)i * dst_len, dst_len, 0, boundary, mode, &k);
+        int st = orc_fm_extract_until_boundary(f, from[i], arena + (int64_t)i * dst_len, dst_len, offset, boundary, mode, &k);
         len_out[i] = k;
         status[i] = st;
     });

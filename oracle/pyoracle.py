@@ -76,8 +76,8 @@ def lib():
         L.orc_fm_locate_batch_utf8.argtypes = [vp, vp, vp, C.c_uint32, i32, vp, vp, i64, vp, i32]
         L.orc_convert_utf8.argtypes = [vp, i64, i64, i64, vp, C.POINTER(i32)]
         L.orc_convert_utf8.restype = i64
-        L.orc_fm_extract_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, i64, vp, vp, i32]
-        L.orc_fm_extract_until_boundary_batch.argtypes = [vp, vp, C.c_uint32, C.c_uint16, i32, i32, vp, vp, vp, i32]
+        L.orc_fm_extract_batch.argtypes = [vp, vp, vp, C.c_uint32, vp, i64, vp, vp, i32, i32]
+        L.orc_fm_extract_until_boundary_batch.argtypes = [vp, vp, C.c_uint32, C.c_uint16, i32, i32, vp, vp, vp, i32, i32]
         L.orc_fm_stats.argtypes = [vp, vp, i32]
         L.orc_fm_wfbb_rank.argtypes = [vp, i64, i32, C.POINTER(i64)]
         L.orc_fm_wfbb_inverse_select.argtypes = [vp, i64, C.POINTER(i64)]
@@ -220,7 +220,7 @@ class OracleFmIndex:
                                   pos.ctypes.data, stride, status.ctypes.data, threads)
         return n_hits, pos, status
 
-    def extract_batch(self, start, stop, stride, threads=1):
+    def extract_batch(self, start, stop, stride, threads=1, offset=0):
         start = np.ascontiguousarray(start, dtype=np.int32)
         stop = np.ascontiguousarray(stop, dtype=np.int32)
         n = start.size
@@ -228,17 +228,17 @@ class OracleFmIndex:
         ln = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
         lib().orc_fm_extract_batch(self._h, start.ctypes.data, stop.ctypes.data, n, arena.ctypes.data, stride, ln.ctypes.data,
-                                   st.ctypes.data, threads)
+                                   st.ctypes.data, threads, offset)
         return arena, ln, st
 
-    def extract_until_boundary_batch(self, frm, boundary, dst_len, mode=0, threads=1):
+    def extract_until_boundary_batch(self, frm, boundary, dst_len, mode=0, threads=1, offset=0):
         frm = np.ascontiguousarray(frm, dtype=np.int32)
         n = frm.size
         arena = np.zeros((n, max(dst_len, 1)), dtype=np.uint16)
         ln = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
         lib().orc_fm_extract_until_boundary_batch(self._h, frm.ctypes.data, n, boundary, dst_len, mode, arena.ctypes.data,
-                                                  ln.ctypes.data, st.ctypes.data, threads)
+                                                  ln.ctypes.data, st.ctypes.data, threads, offset)
         return arena, ln, st
 
     def stats(self, reset=True):

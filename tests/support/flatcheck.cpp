@@ -281,9 +281,10 @@ uint64_t fc_check_roots(void* hv) {
 }
 
 void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena, const uint64_t* arena_off,
-                int32_t* len_out, int32_t* status, uint64_t* counters) {
+                int32_t* len_out, int32_t* status, uint64_t* counters, int32_t offset) {
     FC& h = *(FC*)hv;
     WalkParams P{};
+    P.offset = offset;
     P.n_items = n;
     P.start = start;
     P.stop = stop;
@@ -295,7 +296,7 @@ void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n,
 }
 
 void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len, int32_t mode, uint16_t* arena,
-            int32_t* len_out, int32_t* status, uint64_t* counters) {
+            int32_t* len_out, int32_t* status, uint64_t* counters, int32_t offset) {
     FC& h = *(FC*)hv;
     std::vector<uint16_t> left((size_t)n * (size_t)(dst_len > 0 ? dst_len : 1), 0);
     std::vector<int32_t> down(n, 0);
@@ -305,6 +306,7 @@ void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_
     P.mb = h.ix.char2code[boundary];
     P.dst_len = dst_len;
     P.eub_mode = mode;
+    P.offset = offset;
     P.left = left.data();
     P.down_len = down.data();
     P.arena = arena;
@@ -313,8 +315,8 @@ void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_
     run_walk<WM_EUB>(h, P, counters);
     if (mode != 2)
         for (uint32_t w = 0; w < n; ++w)  // what k_eub_assemble does
-            for (int32_t q = 0; q < down[w] && q < dst_len; ++q)
-                arena[(size_t)w * dst_len + q] = left[(size_t)w * dst_len + (down[w] - 1 - q)];
+            for (int32_t q = 0; q < down[w] && q < dst_len - offset; ++q)
+                arena[(size_t)w * dst_len + offset + q] = left[(size_t)w * dst_len + (down[w] - 1 - q)];
 }
 
 // locate (k_locate): the straight-line lane code of lf_lane.h, one hit at a time

@@ -42,8 +42,8 @@ def lib():
         L.fc_build_start_table.argtypes = [vp, u32]
         L.fc_build_start_table.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
-        L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp]
-        L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp]
+        L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, i32]
+        L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp, i32]
         L.fc_sampled.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
         L.fc_unrank_table.argtypes = [vp]
         L.fc_utf8_convert.argtypes = [vp, C.c_uint64, vp, C.POINTER(i32)]
@@ -115,7 +115,7 @@ class FlatIndexHost:
         lib().fc_locate_rows(self._h, rp.ctypes.data, rp.size, self.counters.ctypes.data)
         return rp.astype(np.int64)
 
-    def extract(self, start, stop, arena_off):
+    def extract(self, start, stop, arena_off, offset=0):
         start = np.ascontiguousarray(start, dtype=np.int32)
         stop = np.ascontiguousarray(stop, dtype=np.int32)
         arena_off = np.ascontiguousarray(arena_off, dtype=np.uint64)
@@ -124,17 +124,17 @@ class FlatIndexHost:
         ln = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
         lib().fc_extract(self._h, start.ctypes.data, stop.ctypes.data, n, arena.ctypes.data, arena_off.ctypes.data, ln.ctypes.data,
-                         st.ctypes.data, self.counters.ctypes.data)
+                         st.ctypes.data, self.counters.ctypes.data, offset)
         return arena, ln, st
 
-    def eub(self, frm, boundary, dst_len, mode):
+    def eub(self, frm, boundary, dst_len, mode, offset=0):
         frm = np.ascontiguousarray(frm, dtype=np.int32)
         n = frm.size
         arena = np.zeros((n, max(dst_len, 1)), dtype=np.uint16)
         ln = np.zeros(n, dtype=np.int32)
         st = np.zeros(n, dtype=np.int32)
         lib().fc_eub(self._h, frm.ctypes.data, n, boundary, dst_len, mode, arena.ctypes.data, ln.ctypes.data, st.ctypes.data,
-                     self.counters.ctypes.data)
+                     self.counters.ctypes.data, offset)
         return arena, ln, st
 
     def sampled(self, pos):

@@ -190,6 +190,45 @@ def test_extract_until_boundary_matches_oracle(gpu_indexes, name, mode, dst_len)
         assert np.array_equal(arena[i, :k], want_arena[i, :k]), (i, frm[i], k)
 
 
+@pytest.mark.parametrize("name", ["log300k_sr64", "tiny600k_sr4", "multi400k_sr8"])
+@pytest.mark.parametrize("offset", [1, 30, 39, 40, 64])
+def test_offset_argument_matches_oracle(gpu_indexes, name, offset):
+    """The reference's `offset` argument (fm/FmIndex.java:564, :640, :772, :844): where the chars land, the capacity tests, the
+    N of "Currently extracted: N", and System.arraycopy throwing when the left part does not fit behind the offset."""
+    case, g = get_case(name), gpu_indexes(name)
+    n = case.text.size
+    rng = np.random.default_rng(80 + offset)
+    for mode in (0, 1, 2):
+        for dst_len in (40, 512):
+            frm = np.concatenate([rng.integers(0, n, 800), np.arange(n - 9, n + 1), np.arange(0, 4)]).astype(np.int32)
+            w_arena, w_len, w_st = case.oracle.extract_until_boundary_batch(frm, 10, dst_len, mode, threads=4, offset=offset)
+            arena, got_len, st = g.extract_until_boundary_batch(frm, "\n", dst_len, mode, offset=offset)
+            assert np.array_equal(st, w_st), (mode, dst_len)
+            ok = (w_st == 0) | (w_st == 8)
+            assert np.array_equal(got_len[ok], w_len[ok])
+            for i in np.flatnonzero(w_st == 0):
+                if frm[i] >= n:
+                    continue
+                assert np.array_equal(arena[i, offset: offset + w_len[i]], w_arena[i, offset: offset + w_len[i]]), (mode, dst_len, i)
+    m = 1000
+    start = rng.integers(0, n - 100, m).astype(np.int32)
+    stop = (start + rng.integers(0, 80, m)).astype(np.int32)
+    stride = 90
+    aoff = (np.arange(m + 1) * stride).astype(np.uint64)
+    arena, _, got_len, st = g.extract_batch(start, stop, aoff, offset=offset)
+    w_arena, w_len, w_st = case.oracle.extract_batch(start, stop, stride, threads=4, offset=offset)
+    assert np.array_equal(st, w_st) and ((w_st == 5).sum() > 0 or offset < 20) and (w_st == 0).sum() > 0
+    for i in np.flatnonzero(w_st == 0):
+        assert got_len[i] == w_len[i]
+        assert np.array_equal(arena[i * stride + offset: i * stride + offset + w_len[i]], w_arena[i, offset: offset + w_len[i]]), i
+    # the single-query forms with a destination array and an offset, like the Java calls
+    dst = np.zeros(600, dtype=np.uint16)
+    k = g.extractUntilBoundary(int(frm[5]), dst, offset, "\n")
+    assert np.array_equal(dst[offset: offset + k], case.oracle.extract_until_boundary(int(frm[5]), 600, 10, 0, offset=offset)[:k]) or k == 0
+    with pytest.raises(Exception):
+        g.extractUntilBoundary(50, dst, -1, "\n")  # negative offset: rejected (the reference indexes out of bounds)
+
+
 def test_extract_until_boundary_error_contract(gpu_indexes):
     from index4j_b200 import FmIndex
     from index4j_b200.fm_index import FmIndexError, FmIndexIllegalArgument

@@ -163,3 +163,36 @@ def test_extract_until_boundary_lanes(flats, name, mode):
             if frm[i] >= n:
                 continue
             assert np.array_equal(a1[i, : l1[i]], a2[i, : l1[i]]), (dst_len, i, int(frm[i]))
+
+
+@pytest.mark.parametrize("name", ["log300k_sr64", "tiny600k_sr4", "nul1m_sr32"])
+@pytest.mark.parametrize("offset", [1, 7, 30, 39, 40, 64])
+def test_offset_lanes(flats, name, offset):
+    """The reference's `offset` argument of extract / extractUntilBoundary* (fm/FmIndex.java:564, :640, :772, :844): where the
+    chars land, the capacity tests, the N of "does not fit" and the arraycopy that throws when the left part does not fit."""
+    case, f = get_case(name), flats(name)
+    n = case.text.size
+    rng = np.random.default_rng(70 + offset)
+    for mode in (0, 1, 2):
+        for dst_len in (40, 512):
+            frm = np.concatenate([rng.integers(0, n, 500), np.arange(n - 9, n + 1), np.arange(0, 4)]).astype(np.int32)
+            a1, l1, s1 = case.oracle.extract_until_boundary_batch(frm, 10, dst_len, mode, threads=4, offset=offset)
+            a2, l2, s2 = f.eub(frm, 10, dst_len, mode, offset=offset)
+            assert np.array_equal(s1, s2), (mode, dst_len, np.flatnonzero(s1 != s2)[:5], s1[s1 != s2][:5], s2[s1 != s2][:5])
+            ok = (s1 == 0) | (s1 == 8)
+            assert np.array_equal(l1[ok], l2[ok]), (mode, dst_len)
+            for i in np.flatnonzero(s1 == 0):
+                if frm[i] >= n:
+                    continue
+                assert np.array_equal(a1[i, offset: offset + l1[i]], a2[i, offset: offset + l1[i]]), (mode, dst_len, i, int(frm[i]))
+    m = 600
+    start = rng.integers(0, n - 100, m).astype(np.int32)
+    stop = (start + rng.integers(0, 80, m)).astype(np.int32)
+    stride = 90  # destination.length: some items fit behind the offset, some do not
+    aoff = (np.arange(m + 1) * stride).astype(np.uint64)
+    arena, got_len, st = f.extract(start, stop, aoff, offset=offset)
+    w_arena, w_len, w_st = case.oracle.extract_batch(start, stop, stride, threads=4, offset=offset)
+    assert np.array_equal(st, w_st) and ((w_st == 5).sum() > 0 or offset < 20) and (w_st == 0).sum() > 0
+    for i in np.flatnonzero(w_st == 0):
+        assert got_len[i] == w_len[i]
+        assert np.array_equal(arena[i * stride + offset: i * stride + offset + w_len[i]], w_arena[i, offset: offset + w_len[i]]), i
