@@ -383,6 +383,18 @@ def main():
     stats["launches"] = launches_per_step
     ix.set_stats(False)
     clocks = sampler.stop() if rank == 0 else None
+    # for the record: the same launch with the warp-lockstep kernel of round 1 (v5); the timed steps above ran the default (flat, v6)
+    v5_ms = None
+    if os.environ.get("FMGPU_COUNT_KERNEL", "6") != "5":
+        ix.set_count_kernel(5)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        v5_ms = statistics.mean(ix.search_kernel_ms(i) for i in range(5))
+        ix.set_count_kernel(6)
 
     # end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
     p_chars = torch.from_numpy(chars.view(np.int16)).pin_memory()
@@ -541,7 +553,9 @@ def main():
                          "records_loaded_per_launch": stats["search_records_loaded"],
                          "spec_root_loads_wasted_per_launch": stats.get("spec_root_wasted", 0),
                          "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
-                         "ranks_per_s": stats["ranks"] / (kern_ms / 1e3)},
+                         "ranks_per_s": stats["ranks"] / (kern_ms / 1e3),
+                         "kernel_version": os.environ.get("FMGPU_COUNT_KERNEL", "6") + (" (flat: lane per pattern with refill)" if os.environ.get("FMGPU_COUNT_KERNEL", "6") != "5" else " (warp-lockstep)"),
+                         "lockstep_v5_kernel_ms_rank0": v5_ms},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob),
                       "start_table_q": ix.start_table_q()},
         }
@@ -562,7 +576,7 @@ def main():
                 out[key]["roofline"] = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                                         "kernel": kname, "kernel_ms": k_ms, "peak_source": peak_src,
                                         "alg_bytes_per_launch_rank0": leg["kernel_alg_bytes"],
-                                        "records_rank0": leg.get("records") or leg.get("records_read")}
+                                        "records_rank0": leg.get("records_read") if "records_read" in leg else leg.get("records")}
         # DRAM traffic per launch of each kernel: from the ncu --set full capture of THIS round's kernels (tools/ncu_traffic.py
         # rewrites profiles/kernel_traffic.json from the capture; the file names the commit and the capture's own kernel times)
         traffic_file = os.path.join(ROOT, "profiles", "kernel_traffic.json")

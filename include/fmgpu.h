@@ -122,6 +122,12 @@ int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const ui
 int fmgpu_set_start_table(fmgpu_index* idx, int enable);
 int32_t fmgpu_start_table_q(const fmgpu_index* idx);
 
+/* Which backward-search kernel count / locate use: 6 (default) = "flat" — one lane per pattern, every lane fetches the one
+ * record its own pattern needs next and takes the next pattern from a work queue when it is done (csrc/count_flat.h);
+ * 5 = warp-lockstep over length-sorted patterns (csrc/count_lane.h), kept for comparison.  Results are identical.
+ * FMGPU_COUNT_KERNEL=5|6 in the environment sets the default of new handles. */
+int fmgpu_set_count_kernel(fmgpu_index* idx, int version);
+
 /* UTF-8 byte patterns: FmIndex.convertBytePatternToCharPattern(byte[] p, 0, p.length, dst) FM:239-298 followed by
  * count(dst, 0, n) / locate(dst, 0, n, ...).  Pattern i is the byte[] bytes[pat_off[i], pat_off[i+1]) — pat_off are BYTE
  * offsets.  The bytes (1 per char for ASCII / Latin-1 logs instead of the 2 of a char[]) cross PCIe and are decoded on

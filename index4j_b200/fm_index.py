@@ -114,6 +114,7 @@ def native():
         L.fmgpu_set_timing.argtypes = [vp, i32]
         L.fmgpu_set_stats.argtypes = [vp, i32]
         L.fmgpu_set_start_table.argtypes = [vp, i32]
+        L.fmgpu_set_count_kernel.argtypes = [vp, i32]
         L.fmgpu_start_table_q.argtypes = [vp]
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         L.fmgpu_kernel_ms.argtypes = [vp, i32, u32, u32, C.POINTER(C.c_float)]
@@ -256,6 +257,10 @@ class FmIndex:
     def set_start_table(self, enable: bool = True):
         """Use (default) / bypass the q-gram start table of the backward search; results are identical either way."""
         self._check(self._lib.fmgpu_set_start_table(self._h, int(enable)))
+
+    def set_count_kernel(self, version: int):
+        """6 = flat backward-search kernel (default), 5 = warp-lockstep kernel; identical results."""
+        self._check(self._lib.fmgpu_set_count_kernel(self._h, int(version)))
 
     def start_table_q(self) -> int:
         return int(self._lib.fmgpu_start_table_q(self._h))

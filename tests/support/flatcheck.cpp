@@ -10,6 +10,7 @@
 #include "../../index4j_b200/csrc/flatten.hpp"
 #include "../../index4j_b200/csrc/jstream.hpp"
 #include "../../index4j_b200/csrc/count_lane.h"
+#include "../../index4j_b200/csrc/count_flat.h"
 #include "../../index4j_b200/csrc/lf_lane.h"
 #include "../../index4j_b200/csrc/utf8_lane.h"
 
@@ -220,6 +221,38 @@ void fc_count_batch(void* hv, const uint16_t* chars, const uint64_t* pat_off, ui
 void fc_count_batch_table(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
                           uint32_t* ranges, uint64_t* counters) {
     count_batch_impl(*(FC*)hv, chars, pat_off, n_pat, counts, status, ranges, counters, true);
+}
+
+// The flat kernel's lane code (count_flat.h), one lane at a time: descriptor, then trips until the lane is idle again.
+// use_table: with the q-gram start table (fc_build_start_table first).  counters as fc_count_batch; counters[2] += trips.
+void fc_count_batch_flat(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
+                         uint32_t* ranges, uint64_t* counters, int32_t use_table) {
+    FC& h = *(FC*)hv;
+    std::vector<Rec32> descs(n_pat);
+    const uint32_t kq = use_table ? h.ix.kmer_q : 0u;
+    for (uint32_t p = 0; p < n_pat; ++p) descs[p] = flat_make_desc(h.ix, h.ix.C, chars, pat_off[p], pat_off[p + 1], h.ix.char2code, kq);
+    FlatOut O;
+    O.counts = counts;
+    O.status = status;
+    O.ranges = ranges;
+    CountCounters cnt{0, 0, 0, 0, 0};
+    uint64_t trips = 0;
+    for (uint32_t p = 0; p < n_pat; ++p) {
+        FlatLane L{};
+        L.pat = p;
+        L.state = FS_DESC;
+        while (L.state != FS_IDLE) {
+            flat_trip<true>(h.ix, h.CT, L, O, descs.data(), chars, h.ix.char2code, cnt);
+            ++trips;
+        }
+    }
+    if (counters) {
+        counters[0] += cnt.ranks;
+        counters[1] += cnt.levels;
+        counters[2] += trips;
+        counters[6] += cnt.loads;
+        counters[7] += cnt.recs;
+    }
 }
 
 // Host twin of build_start_table (fmgpu.cu): for every q-gram of codes the chars can spell, the (sp, ep) the step-by-step search

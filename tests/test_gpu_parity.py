@@ -26,23 +26,36 @@ def test_count_matches_oracle(gpu_indexes, name):
     assert np.array_equal(got_st, want_st)
     assert np.array_equal(got, want)
     assert int((want > 0).sum()) > 1000
-    # the same without the q-gram start table (every pattern from its last char), with the instrumented kernel: identical
-    # results, and then the kernel walks exactly the ranks the reference's loop performs
-    g.set_stats(True)
-    g.set_start_table(False)
-    try:
-        got, got_st = g.count_batch(chars, off, return_status=True)
-    finally:
-        g.set_stats(False)
-        g.set_start_table(True)
-    assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
-    # work counters agree with the oracle's instrumentation
+    # the same without the q-gram start table (every pattern from its last char), with the instrumented kernels — the flat
+    # kernel (6, the default) and the warp-lockstep kernel (5): identical results, and then both walk exactly the ranks and
+    # levels the reference's loop performs
     case.oracle.stats(reset=True)
     case.oracle.count_batch(chars, off, threads=1)
     st = case.oracle.stats()
-    mine = g.last_stats()
-    assert mine["launches"] == 4
-    assert mine["rank_levels"] == st["rank_levels"]
+    for version, launches in ((6, 2), (5, 4)):
+        g.set_count_kernel(version)
+        g.set_stats(True)
+        g.set_start_table(False)
+        try:
+            got, got_st = g.count_batch(chars, off, return_status=True)
+            mine = g.last_stats()
+        finally:
+            g.set_stats(False)
+            g.set_start_table(True)
+            g.set_count_kernel(6)
+        assert np.array_equal(got_st, want_st) and np.array_equal(got, want), version
+        assert mine["launches"] == launches
+        assert mine["rank_levels"] == st["rank_levels"], version  # work counters agree with the oracle's instrumentation
+    # the lockstep kernel with its start table, production variant
+    g.set_count_kernel(5)
+    try:
+        got, got_st = g.count_batch(chars, off, return_status=True)
+        n5, o5, p5, s5 = g.locate_batch(chars[: int(off[500])], off[:501], 20)
+    finally:
+        g.set_count_kernel(6)
+    assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
+    n6, o6, p6, s6 = g.locate_batch(chars[: int(off[500])], off[:501], 20)
+    assert np.array_equal(n5, n6) and np.array_equal(p5, p6) and np.array_equal(s5, s6)
 
 
 def test_start_table_is_transparent(gpu_indexes):
@@ -222,9 +235,19 @@ def test_offset_argument_matches_oracle(gpu_indexes, name, offset):
         assert got_len[i] == w_len[i]
         assert np.array_equal(arena[i * stride + offset: i * stride + offset + w_len[i]], w_arena[i, offset: offset + w_len[i]]), i
     # the single-query forms with a destination array and an offset, like the Java calls
-    dst = np.zeros(600, dtype=np.uint16)
-    k = g.extractUntilBoundary(int(frm[5]), dst, offset, "\n")
-    assert np.array_equal(dst[offset: offset + k], case.oracle.extract_until_boundary(int(frm[5]), 600, 10, 0, offset=offset)[:k]) or k == 0
+    import pyoracle
+    from index4j_b200.fm_index import FmIndexError
+    for f in frm[:40]:
+        dst = np.zeros(600, dtype=np.uint16)
+        try:
+            want = case.oracle.extract_until_boundary(int(f), 600, 10, 0, offset=offset)
+        except pyoracle.JavaException as e:
+            with pytest.raises(FmIndexError) as ei:
+                g.extractUntilBoundary(int(f), dst, offset, "\n")
+            assert ei.value.status == e.status and (e.status != 8 or ei.value.n == e.n)
+            continue
+        k = g.extractUntilBoundary(int(f), dst, offset, "\n")
+        assert k == want.size and np.array_equal(dst[offset: offset + k], want)
     with pytest.raises(Exception):
         g.extractUntilBoundary(50, dst, -1, "\n")  # negative offset: rejected (the reference indexes out of bounds)
 

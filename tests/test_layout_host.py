@@ -96,6 +96,30 @@ def test_count_and_locate_lanes(flats, name):
     assert np.array_equal(got_pos, np.array(exp, dtype=np.int64))
 
 
+@pytest.mark.parametrize("name", ALL_CASES)
+def test_flat_count_lanes(flats, name):
+    """The lane code of the flat backward-search kernel (count_flat.h: pattern descriptor, then one record fetch per trip) gives
+    the oracle's counts / statuses, the lockstep lane code's SA ranges, and walks the same ranks and levels."""
+    case, f = get_case(name), flats(name)
+    chars, off = make_patterns(case.text, 3000, 0, 48, seed=23)
+    want, want_st = case.oracle.count_batch(chars, off, threads=4)
+    f.counters[:] = 0
+    ref, ref_st, ref_ranges = f.count_batch(chars, off)
+    c_ref = f.counters.copy()
+    f.counters[:] = 0
+    got, got_st, ranges = f.count_batch_flat(chars, off)
+    c_flat = f.counters.copy()
+    assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
+    hit = want > 0
+    assert np.array_equal(ranges[hit], ref_ranges[hit])
+    assert c_flat[0] == c_ref[0] and c_flat[1] == c_ref[1] and c_flat[7] == c_ref[7]  # ranks, levels, level records
+    # with a start table
+    f2 = flatcheck.FlatIndexHost(case.blob)
+    if f2.build_start_table(2) > 0:
+        got, got_st, ranges = f2.count_batch_flat(chars, off, use_table=True)
+        assert np.array_equal(got_st, want_st) and np.array_equal(got, want) and np.array_equal(ranges[hit], ref_ranges[hit])
+
+
 @pytest.mark.parametrize("name,q", [("log300k_sr64", 2), ("log300k_sr64", 3), ("tiny600k_sr4", 5), ("log200k_sr1", 2)])
 def test_start_table_lanes(name, q):
     """The q-gram start table (pattern_start / start_table_lookup of count_lane.h, table built by the step-by-step search itself):
