@@ -296,6 +296,7 @@ def main():
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--cpu-locate-sample", type=int, default=20_000, help="patterns of the CPU arm of the locate leg")
     ap.add_argument("--cpu-eub-sample", type=int, default=50_000, help="records of the CPU arm of the extractUntilBoundary leg")
+    ap.add_argument("--no-alt-kernel", action="store_true", help="skip the comparison launch with the other backward-search kernel")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs of an N > 1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lf", action="store_true", help="skip the locate / extractUntilBoundary legs (extra keys of the JSON line)")
@@ -383,18 +384,19 @@ def main():
     stats["launches"] = launches_per_step
     ix.set_stats(False)
     clocks = sampler.stop() if rank == 0 else None
-    # for the record: the same launch with the warp-lockstep kernel of round 1 (v5); the timed steps above ran the default (flat, v6)
-    v5_ms = None
-    if os.environ.get("FMGPU_COUNT_KERNEL", "6") != "5":
-        ix.set_count_kernel(5)
+    # for the record: the same launch with the flat kernel (v6: lane per pattern with refill); the timed steps above ran the default
+    alt_ms = None
+    default_kernel = os.environ.get("FMGPU_COUNT_KERNEL", "5")
+    if not args.no_alt_kernel:
+        ix.set_count_kernel(6 if default_kernel == "5" else 5)
         for _ in range(3):
             step()
         torch.cuda.synchronize()
         for _ in range(5):
             step()
         torch.cuda.synchronize()
-        v5_ms = statistics.mean(ix.search_kernel_ms(i) for i in range(5))
-        ix.set_count_kernel(6)
+        alt_ms = statistics.mean(ix.search_kernel_ms(i) for i in range(5))
+        ix.set_count_kernel(int(default_kernel))
 
     # end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
     p_chars = torch.from_numpy(chars.view(np.int16)).pin_memory()
@@ -554,8 +556,8 @@ def main():
                          "spec_root_loads_wasted_per_launch": stats.get("spec_root_wasted", 0),
                          "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3),
-                         "kernel_version": os.environ.get("FMGPU_COUNT_KERNEL", "6") + (" (flat: lane per pattern with refill)" if os.environ.get("FMGPU_COUNT_KERNEL", "6") != "5" else " (warp-lockstep)"),
-                         "lockstep_v5_kernel_ms_rank0": v5_ms},
+                         "kernel_version": default_kernel + (" (flat: lane per pattern with refill)" if default_kernel != "5" else " (warp-lockstep)"),
+                         "other_kernel_ms_rank0": {("6 (flat)" if default_kernel == "5" else "5 (warp-lockstep)"): alt_ms}},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob),
                       "start_table_q": ix.start_table_q()},
         }

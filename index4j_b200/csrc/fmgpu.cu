@@ -187,7 +187,7 @@ struct fmgpu_index {
     bool count_stats = false;  // fmgpu_set_stats: kernels with work counters
     bool use_kmer = true;      // fmgpu_set_start_table: patterns start from the q-gram start table when the index has one
     bool timing = false;
-    int count_kernel = 6;      // backward-search kernel: 6 = flat (lane per pattern with refill, count_flat.h), 5 = warp-lockstep (count_lane.h)
+    int count_kernel = 5;      // backward-search kernel: 5 = warp-lockstep (count_lane.h, the default), 6 = flat (lane per pattern with refill, count_flat.h)
     Replica* primary() const { return reps[0].get(); }
 };
 

@@ -259,7 +259,7 @@ class FmIndex:
         self._check(self._lib.fmgpu_set_start_table(self._h, int(enable)))
 
     def set_count_kernel(self, version: int):
-        """6 = flat backward-search kernel (default), 5 = warp-lockstep kernel; identical results."""
+        """5 = warp-lockstep backward-search kernel (default), 6 = flat kernel (lane per pattern with refill); identical results."""
         self._check(self._lib.fmgpu_set_count_kernel(self._h, int(version)))
 
     def start_table_q(self) -> int:
