@@ -442,6 +442,19 @@ def main():
         sel = torch.linspace(0, max(total_hits - 1, 0), max(n_eub, 1), device=dev, dtype=torch.float64).to(torch.int64)
         d_from = d_pos[sel].contiguous()
         eub, d_arena, d_len, d_st = workloads.eub_workload(ix, d_from, args.dst_len, args.lf_steps, 1)
+        # the same hits through the fused locate -> extractUntilBoundary path (distinct records read once), and a clustered
+        # selection (the FIRST n_eub hits of the batch: all hits of the first patterns) where hits share records more often
+        rec, r_idx, r_len, r_st, r_arena = workloads.records_workload(ix, d_from, args.dst_len, args.lf_steps, 1)
+        assert torch.equal(r_st, d_st) and torch.equal(r_len[d_st == 0], d_len[d_st == 0]), "fused record path differs from extractUntilBoundary"
+        samp = torch.arange(0, n_eub, max(n_eub // 20000, 1), device=dev)
+        samp = samp[(d_st[samp] == 0) & (d_len[samp] > 0)]
+        cols = torch.arange(args.dst_len, device=dev)[None, :]
+        m_ok = cols < d_len[samp][:, None]
+        assert torch.equal(r_arena[r_idx[samp].long()][m_ok], d_arena[samp][m_ok]), "fused record contents differ from extractUntilBoundary"
+        del r_arena, r_idx, r_len, r_st
+        rec_first, *_ = workloads.records_workload(ix, d_pos[:n_eub].contiguous(), args.dst_len, args.lf_steps, 1)
+        del _
+        torch.cuda.empty_cache()
         # end to end through the C ABI: host patterns in, host positions out (one call: ranges, hit scan, LF walks, D2H)
         p_nh = torch.empty(n_pat, dtype=torch.int32).pin_memory().numpy()
         p_ho = torch.empty(n_pat + 1, dtype=torch.int64).pin_memory().numpy().view(np.uint64)
@@ -453,7 +466,7 @@ def main():
             ix.locate_batch_into(h_chars, h_off, args.max_hits, p_nh, p_ho, p_pos, h_status)
         loc_e2e_s = (time.perf_counter() - t0) / args.lf_steps
         assert int(p_ho[-1]) == total_hits and np.array_equal(p_pos[:4096], d_pos[:4096].cpu().numpy())
-        lf = {"loc": loc, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
+        lf = {"rec": rec, "rec_first": rec_first, "loc": loc, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
               "d_hit_off": d_hit_off, "d_pos": d_pos, "h2d": int(chars.nbytes + off.nbytes), "d2h": int(p_nh.nbytes + p_ho.nbytes + p_pos.nbytes + h_status.nbytes)}
 
     # strong scaling (BASELINE.json configs[1] as written: the ONE 1 M-pattern batch sharded over the GPUs).  (a) device-resident:
@@ -571,6 +584,11 @@ def main():
             out["extract_until_boundary"] = {"metric": "records/sec (extractUntilBoundary('\\n'), dst %d chars, of located hits)" % args.dst_len,
                                              "value": all_records / (eub_ms / 1e3), "unit": "records/s", "chars_per_s": all_chars / (eub_ms / 1e3),
                                              "ms_per_step": eub_ms, "records_per_step": all_records, "launches_per_step": lf["eub"]["launches"]}
+        if lf:
+            out["locate_records"] = {
+                "metric": "fused locate -> extractUntilBoundary: hits/s with every distinct record read once (fmgpu_extract_records_batch_device, rank 0)",
+                "same_hits_as_extract_until_boundary": lf["rec"], "first_hits_of_the_batch": lf["rec_first"],
+                "checked": "statuses and lengths of all hits, contents of 20,000 sampled hits equal the extractUntilBoundary leg"}
         # roofline objects of the two LF kernels: algorithmic bytes (records the lanes need, workloads.py) over the live kernel time
         if lf:
             for key, kname, leg, k_ms in (("locate", "k_locate", lf["loc"], loc_k_ms), ("extract_until_boundary", "k_extract<EUB>", lf["eub"], eub_k_ms)):

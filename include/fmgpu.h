@@ -183,6 +183,31 @@ int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d
                                               int32_t dst_len, int32_t offset, int32_t mode, uint16_t* d_arena, int32_t* d_len_out,
                                               int32_t* d_status_out, void* cuda_stream);
 
+/* Fused locate -> extractUntilBoundary — the reference's "extracting whole records" flow (README.md:98-107,
+ * jmh/.../FmIndexThroughputBenchmark.java:231-249):
+ *     found = fmi.locate(pattern, 0, len, locations, max);
+ *     for (i < found) length = fmi.extractUntilBoundary(locations[i], destination = new char[dst_len], 0, boundary);
+ * with every DISTINCT record read from the index once: hits that lie in the same record (of one pattern or of different
+ * patterns of the batch) share it.  Per hit h: rec_index_out[h] = row of its record in rec_arena (row u = rec_arena[u*dst_len ..
+ * (u+1)*dst_len)), or -1 when the call has no record for it (status != 0); len_out[h] / status_out[h] = exactly what the
+ * reference's call returns or throws for THAT hit (the "does not fit" test works on 4-char chunks counted from the hit, so
+ * it can differ between two hits of one record, FM:732-737); the hit's record is rec_arena[row][0 .. len_out[h]).
+ * rec_cap = rows the arena has room for (n hits always suffice); *n_records_out = distinct records.  The records keep no
+ * particular order.
+ *   fmgpu_extract_records_batch[_device]: the hits are given (text positions, e.g. of an earlier locate);
+ *   fmgpu_locate_records_batch: patterns in, hits + records out; with positions_out == NULL only n_hits_out / hit_off_out /
+ *   pat_status_out are produced (sizing pass: hits_cap must be >= hit_off_out[n_pat]).  These calls run on the primary device. */
+int fmgpu_extract_records_batch(fmgpu_index* idx, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len,
+                                int32_t* rec_index_out, int32_t* len_out, int32_t* status_out, uint16_t* rec_arena, uint64_t rec_cap,
+                                uint64_t* n_records_out);
+int fmgpu_extract_records_batch_device(fmgpu_index* idx, const int32_t* d_from, uint32_t n, uint16_t boundary, int32_t dst_len,
+                                       int32_t* d_rec_index_out, int32_t* d_len_out, int32_t* d_status_out, uint16_t* d_rec_arena,
+                                       uint64_t rec_cap, uint64_t* n_records_out, void* cuda_stream);
+int fmgpu_locate_records_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t max_hits,
+                               uint16_t boundary, int32_t dst_len, int32_t* n_hits_out, uint64_t* hit_off_out, int32_t* pat_status_out,
+                               int32_t* positions_out, int32_t* rec_index_out, int32_t* len_out, int32_t* status_out, uint64_t hits_cap,
+                               uint16_t* rec_arena, uint64_t rec_cap, uint64_t* n_records_out);
+
 /* The index's wavelet structure (FmIndex.waveletFixedBlockBoosting) queried directly — the reference's public
  * WaveletFixedBlockBoosting.rank(long position, short symbol) WF:1010-1285 and inverseSelect(long position) WF:1305-1537
  * over alphabet CODES (FmIndex maps chars to codes by first appearance, FM:396-435).  out[i] of inverse_select is the

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -27,6 +28,7 @@
 #include "kernels.cuh"
 #include "kernels_lf.cuh"
 #include "kernels_locate.cuh"
+#include "kernels_records.cuh"
 #include "kernels_utf8.cuh"
 #include "kernels_wavelet.cuh"
 #include "kernels_build.cuh"
@@ -149,6 +151,51 @@ struct CallCtx {
     }
 };
 
+// One host thread per replica of a multi-device handle: the slices of a host-pointer batch call are enqueued (dozens of CUDA
+// API calls each) and waited for in parallel instead of one device after the other.
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, quit = false;
+    void start() {
+        th = std::thread([this] {
+            std::unique_lock<std::mutex> lk(mu);
+            for (;;) {
+                cv.wait(lk, [this] { return has_job || quit; });
+                if (quit) return;
+                std::function<void()> j = std::move(job);
+                lk.unlock();
+                j();
+                lk.lock();
+                has_job = false;
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> j) {  // waits for the slot (one job at a time per replica)
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this] { return !has_job; });
+        job = std::move(j);
+        has_job = true;
+        cv.notify_all();
+    }
+    void wait_idle() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this] { return !has_job; });
+    }
+    void stop() {
+        if (!th.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+            cv.notify_all();
+        }
+        th.join();
+    }
+};
+
 // One device's copy of the index + its call contexts.
 struct Replica {
     int device = 0;
@@ -184,6 +231,8 @@ struct fmgpu_index {
     int kind = KIND_FM;  // what the handle was loaded from: an FmIndex stream, a bare WaveletFixedBlockBoosting, a bare RrrVector
     int32_t alphabet_length = 0;
     std::vector<std::unique_ptr<Replica>> reps;
+    std::vector<std::unique_ptr<Worker>> workers;  // one per replica when there are several
+    std::mutex multi_mu;                            // one multi-device call at a time drives the workers
     bool count_stats = false;  // fmgpu_set_stats: kernels with work counters
     bool use_kmer = true;      // fmgpu_set_start_table: patterns start from the q-gram start table when the index has one
     bool timing = false;
@@ -250,6 +299,31 @@ int timing_slot(fmgpu_index* ix, Replica* rp, int kind) {
 
 // slice r of R over n items
 inline uint32_t slice_lo(uint32_t n, size_t r, size_t R) { return (uint32_t)((uint64_t)n * r / R); }
+
+// fn(r) for r in [0, R): inline when R == 1, else on the replicas' worker threads, all at once.  Returns the first failure;
+// its message becomes the caller's fmgpu_last_error().
+template <typename F>
+int run_on_replicas(fmgpu_index* ix, size_t R, F&& fn) {
+    if (R <= 1 || ix->workers.size() < R) {
+        int rc = 0;
+        for (size_t r = 0; r < R && !rc; ++r) rc = fn(r);
+        return rc;
+    }
+    std::vector<int> rcs(R, 0);
+    std::vector<std::string> errs(R);
+    for (size_t r = 0; r < R; ++r)
+        ix->workers[r]->submit([&, r] {
+            rcs[r] = fn(r);
+            if (rcs[r]) errs[r] = g_err;  // the worker thread's own thread-local message
+        });
+    for (size_t r = 0; r < R; ++r) ix->workers[r]->wait_idle();
+    for (size_t r = 0; r < R; ++r)
+        if (rcs[r]) {
+            g_err = errs[r];
+            return rcs[r];
+        }
+    return 0;
+}
 
 template <typename T>
 int upload(Replica* rp, const std::vector<T>& v, const T** dptr, int layout_slot) {
@@ -537,6 +611,7 @@ const char* fmgpu_version(void) { return "fmgpu 0.2 (sm_100a)"; }
 
 void fmgpu_index_free(fmgpu_index* ix) {
     if (!ix) return;
+    for (auto& w : ix->workers) w->stop();
     DeviceRestore keep;
     for (auto& up : ix->reps) {
         Replica* rp = up.get();
@@ -687,6 +762,11 @@ int load_common(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_in
         fmgpu_index_free(ix);
         return rc;
     }
+    if (ix->reps.size() > 1)
+        for (size_t i = 0; i < ix->reps.size(); ++i) {
+            ix->workers.emplace_back(new Worker());
+            ix->workers.back()->start();
+        }
     *out = ix;
     return 0;
 }
@@ -888,19 +968,15 @@ int count_host(fmgpu_index* ix, const void* in, size_t unit, const uint64_t* pat
     if (pat_off[n_pat] > pat_off[0] && !in) return fail(FMGPU_ERR_ARG, "null argument");
     DeviceRestore keep;
     const size_t R = n_pat >= 2 * ix->reps.size() ? ix->reps.size() : 1;
-    std::vector<std::unique_ptr<Lease>> leases;
-    int rc = 0;
-    for (size_t r = 0; r < R && !rc; ++r) {
-        leases.emplace_back(new Lease(ix->reps[r].get()));
-        rc = leases.back()->rc;
-        if (!rc) rc = count_host_enqueue(ix, *leases.back(), in, unit, pat_off, slice_lo(n_pat, r, R), slice_lo(n_pat, r + 1, R), counts_out, status_out);
-    }
-    for (auto& L : leases) {  // wait for whatever was enqueued, also after a failure
-        if (L->rc) continue;
-        const int w = count_host_wait(*L);
-        if (!rc) rc = w;
-    }
-    return rc;
+    std::unique_lock<std::mutex> multi(ix->multi_mu, std::defer_lock);
+    if (R > 1) multi.lock();
+    return run_on_replicas(ix, R, [&](size_t r) -> int {
+        Lease L(ix->reps[r].get());
+        if (L.rc) return L.rc;
+        int rc = count_host_enqueue(ix, L, in, unit, pat_off, slice_lo(n_pat, r, R), slice_lo(n_pat, r + 1, R), counts_out, status_out);
+        const int w = count_host_wait(L);  // wait for whatever was enqueued, also after a failure
+        return rc ? rc : w;
+    });
 }
 
 }  // namespace

@@ -149,7 +149,7 @@ struct ExLane {
     FMGPU_HD void finish(const WalkParams& P, int32_t status, int32_t value) {
         P.len_out[w] = value;
         P.status_out[w] = status;
-        if (MODE == WM_EUB) P.down_len[w] = (status == 0 || status == 8) ? down : 0;
+        if (MODE == WM_EUB && P.down_len) P.down_len[w] = (status == 0 || status == 8) ? down : 0;
         active = false;
     }
     FMGPU_HD void start_isa(uint32_t idx) {
@@ -203,7 +203,11 @@ struct ExLane {
             if (P.dst_len == 0) return finish(P, 6, 0);
             if (P.mb == 0u) return finish(P, 7, 0);
             remaining = P.dst_len;
-            if (P.eub_mode == 2) {
+            if (P.eub_mode == EUB_SCAN) {
+                P.win_of[w] = -1;
+                P.at_bound[w] = 0;
+            }
+            if (P.eub_mode == 2 || P.eub_mode == EUB_RECORD) {
                 stage = 1;
                 cur = from;
                 begin_right(ix);
@@ -213,6 +217,22 @@ struct ExLane {
                 if (from / sr == (int32_t)ix.n_isa - 2) skip = (int32_t)ix.length - from;
                 start_isa((uint32_t)(from / sr + 1));
             }
+        }
+    }
+    // the record that starts at text position S belongs to the first hit that claims it; returns that hit's id
+    FMGPU_HD uint32_t claim_record(const WalkParams& P, uint32_t S, uint32_t me) {
+        const unsigned long long mine = ((unsigned long long)(S + 1u) << 32) | me;
+        uint32_t slot = (S * 2654435761u) & P.claim_mask;
+        for (;;) {
+#if defined(__CUDA_ARCH__)
+            const unsigned long long old = atomicCAS(P.claims + slot, 0ull, mine);
+#else
+            const unsigned long long old = P.claims[slot];
+            if (old == 0ull) P.claims[slot] = mine;
+#endif
+            if (old == 0ull) return me;
+            if ((uint32_t)(old >> 32) == S + 1u) return (uint32_t)old;
+            slot = (slot + 1u) & P.claim_mask;
         }
     }
     // an LF step produced `sym` (the char left of the previous one)
@@ -227,6 +247,27 @@ struct ExLane {
             return;
         }
         const uint64_t slot = (uint64_t)w * (uint64_t)P.dst_len;
+        if (MODE == WM_EUB && P.eub_mode == EUB_SCAN) {
+            // fused locate -> extractUntilBoundary: the left walk of FmIndex.extractUntilBoundary (:664-686) without storing its
+            // chars — it finds the start S of the hit's record, which the first hit to arrive claims
+            if ((int32_t)dist >= skip) {
+                if (sym == P.mb || sym == 0u) {
+                    down = k;
+                    P.win_of[w] = (int32_t)claim_record(P, (uint32_t)(from - k), w);
+                    return finish(P, 0, k);
+                }
+                ++k;
+                --remaining;
+                if (remaining == 0) {  // the left part alone fills the destination: no record start (win_of stays -1)
+                    down = k;
+                    return finish(P, 0, k);
+                }
+            } else if ((int32_t)dist + 1 == skip) {
+                P.at_bound[w] = sym == P.mb ? 1 : 0;  // this step produced text[from]
+            }
+            ++dist;
+            return;
+        }
         if (stage == 0) {  // left walk (:664-686, :797-826)
             bool stop_left = false;
             if ((int32_t)dist >= skip) {
@@ -262,7 +303,10 @@ struct ExLane {
         const int32_t p = end - 1 - (int32_t)dist;
         if (p >= from && p < (int32_t)ix.length - 1) {
             if (sym == P.mb) pb = p;
-            if (P.eub_mode == 2) {
+            if (P.eub_mode == EUB_RECORD) {
+                const int64_t idx = (int64_t)p - from;
+                if (idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
+            } else if (P.eub_mode == 2) {
                 const int64_t idx = (int64_t)P.offset + (p - from - 1);
                 if (p - from - 1 >= 0 && idx < P.dst_len) P.arena[slot + (uint64_t)idx] = ix.code2char[sym];
             } else {
@@ -274,6 +318,27 @@ struct ExLane {
         if (p > cur) return;
         if (rel < 0 && pb >= 0) rel = pb - from;  // intervals go left to right: the first boundary seen is the nearest
         bool more = true;
+        if (P.eub_mode == EUB_RECORD) {
+            // text[S, E) of a distinct record: stop at the first boundary — or go on to the end of the text when the record ends
+            // within a few chars of it (the reference's end-of-text rule, quirk Q5, returns chars beyond the boundary there, and
+            // which ones depends on the hit) — or when the destination is certainly too small
+            int32_t value = rel;
+            if (rel >= 0) {
+                more = (int64_t)from + rel >= (int64_t)ix.length - 10 && end < (int32_t)ix.length;
+            } else if (end >= (int32_t)ix.length) {
+                more = false;  // the text ends first: rel stays -1
+            } else if ((int64_t)end - from > (int64_t)P.dst_len + 8) {
+                more = false;
+                value = REL_NONE;
+            }
+            if (more) {
+                cur = end;
+                begin_right(ix);
+            } else {
+                finish(P, 0, value);
+            }
+            return;
+        }
         if (rel >= 0) {
             // The reference reads whole 4-char chunks; when the boundary's chunk is also the one that reaches the end of
             // the text, its end-of-text rule (quirk Q5) returns chars beyond the boundary: fetch them too.

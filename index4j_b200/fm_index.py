@@ -96,6 +96,9 @@ def native():
         L.fmgpu_extract_batch_device.argtypes = [vp, vp, vp, u32, vp, vp, i32, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch.argtypes = [vp, vp, u32, u16, i32, i32, i32, vp, vp, vp]
         L.fmgpu_extract_until_boundary_batch_device.argtypes = [vp, vp, u32, u16, i32, i32, i32, vp, vp, vp, vp]
+        L.fmgpu_extract_records_batch.argtypes = [vp, vp, u32, u16, i32, vp, vp, vp, vp, u64, C.POINTER(u64)]
+        L.fmgpu_extract_records_batch_device.argtypes = [vp, vp, u32, u16, i32, vp, vp, vp, vp, u64, C.POINTER(u64), vp]
+        L.fmgpu_locate_records_batch.argtypes = [vp, vp, vp, u32, i32, u16, i32, vp, vp, vp, vp, vp, vp, vp, u64, vp, u64, C.POINTER(u64)]
         L.fmgpu_num_devices.argtypes = [vp]
         L.fmgpu_num_devices.restype = i32
         L.fmgpu_device_at.argtypes = [vp, i32]
@@ -397,6 +400,62 @@ class FmIndex:
         self._check(self._lib.fmgpu_extract_until_boundary_batch(self._h, frm.ctypes.data, n, b, dst_len, int(offset), mode,
                                                                  arena.ctypes.data if dst_len > 0 else None, ln.ctypes.data, st.ctypes.data))
         return arena, ln, st
+
+    # --- fused locate -> extractUntilBoundary: every distinct record read once ----------------------------------
+    def extract_records_batch(self, frm, boundary, dst_len: int, rec_cap: int | None = None):
+        """``extractUntilBoundary(from, new char[dst_len], 0, boundary)`` for every hit, each distinct record extracted once.
+        -> (rec_index int32[n], len int32[n], status int32[n], records uint16[n_records, dst_len]); the record of hit h is
+        ``records[rec_index[h], :len[h]]``."""
+        frm = np.ascontiguousarray(frm, dtype=np.int32)
+        n = frm.size
+        b = ord(boundary) if isinstance(boundary, str) else int(boundary)
+        cap = n if rec_cap is None else int(rec_cap)
+        idx = np.zeros(n, dtype=np.int32)
+        ln = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        arena = np.zeros((max(cap, 1), max(dst_len, 1)), dtype=np.uint16)
+        n_rec = C.c_uint64()
+        self._check(self._lib.fmgpu_extract_records_batch(self._h, frm.ctypes.data, n, b, dst_len, idx.ctypes.data, ln.ctypes.data, st.ctypes.data,
+                                                          arena.ctypes.data, cap, C.byref(n_rec)))
+        return idx, ln, st, arena[: int(n_rec.value)]
+
+    def extract_records_batch_device(self, d_from, boundary, dst_len: int, d_rec_index, d_len, d_status, d_rec_arena, stream: int | None = None) -> int:
+        """device-resident form; returns the number of distinct records (synchronizes the stream once)"""
+        import torch
+        if stream is None:
+            stream = torch.cuda.current_stream(d_from.device).cuda_stream
+        b = ord(boundary) if isinstance(boundary, str) else int(boundary)
+        n_rec = C.c_uint64()
+        self._check(self._lib.fmgpu_extract_records_batch_device(self._h, d_from.data_ptr(), d_from.numel(), b, dst_len, d_rec_index.data_ptr(),
+                                                                 d_len.data_ptr(), d_status.data_ptr(), d_rec_arena.data_ptr(),
+                                                                 d_rec_arena.shape[0], C.byref(n_rec), stream))
+        return int(n_rec.value)
+
+    def locate_records_batch(self, chars, pat_off, max_hits: int, boundary, dst_len: int):
+        """``locate`` + ``extractUntilBoundary`` of every hit in one call.
+        -> dict(n_hits, hit_off, pat_status, positions, rec_index, len, status, records)"""
+        chars = _u16(chars)
+        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
+        n = pat_off.size - 1
+        b = ord(boundary) if isinstance(boundary, str) else int(boundary)
+        n_hits = np.zeros(n, dtype=np.int32)
+        hit_off = np.zeros(n + 1, dtype=np.uint64)
+        pst = np.zeros(n, dtype=np.int32)
+        n_rec = C.c_uint64()
+        self._check(self._lib.fmgpu_locate_records_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, b, dst_len, n_hits.ctypes.data,
+                                                         hit_off.ctypes.data, pst.ctypes.data, None, None, None, None, 0, None, 0, C.byref(n_rec)))
+        total = int(hit_off[-1])
+        pos = np.zeros(max(total, 1), dtype=np.int32)
+        idx = np.zeros(max(total, 1), dtype=np.int32)
+        ln = np.zeros(max(total, 1), dtype=np.int32)
+        st = np.zeros(max(total, 1), dtype=np.int32)
+        arena = np.zeros((max(total, 1), max(dst_len, 1)), dtype=np.uint16)
+        if total:
+            self._check(self._lib.fmgpu_locate_records_batch(self._h, chars.ctypes.data, pat_off.ctypes.data, n, max_hits, b, dst_len,
+                                                             n_hits.ctypes.data, hit_off.ctypes.data, pst.ctypes.data, pos.ctypes.data, idx.ctypes.data,
+                                                             ln.ctypes.data, st.ctypes.data, total, arena.ctypes.data, total, C.byref(n_rec)))
+        return dict(n_hits=n_hits, hit_off=hit_off, pat_status=pst, positions=pos[:total], rec_index=idx[:total], len=ln[:total], status=st[:total],
+                    records=arena[: int(n_rec.value)])
 
     # --- the reference's single-query methods -----------------------------------------------------
     def count(self, pattern, offset: int = 0, length: int | None = None) -> int:

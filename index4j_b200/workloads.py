@@ -90,6 +90,25 @@ def eub_workload(ix, d_from, dst_len: int, steps: int, warmup: int, boundary="\n
     return out, d_arena, d_len, d_st
 
 
+def records_workload(ix, d_from, dst_len: int, steps: int, warmup: int, boundary="\n"):
+    """Fused locate -> extractUntilBoundary (fmgpu_extract_records_batch_device): per hit its record, every distinct record read once."""
+    dev = d_from.device
+    n = d_from.numel()
+    d_idx = torch.empty(n, dtype=torch.int32, device=dev)
+    d_len = torch.empty(n, dtype=torch.int32, device=dev)
+    d_st = torch.empty(n, dtype=torch.int32, device=dev)
+    d_arena = torch.empty((n, dst_len), dtype=torch.int16, device=dev)
+    box = {}
+
+    def fn():
+        box["n_rec"] = ix.extract_records_batch_device(d_from, boundary, dst_len, d_idx, d_len, d_st, d_arena)
+
+    ms = _timed(fn, steps, warmup)
+    out = {"hits": n, "distinct_records": box["n_rec"], "hits_per_record": n / max(box["n_rec"], 1), "dst_len": dst_len, "ms_per_step": ms,
+           "hits_per_s": n / (ms / 1e3), "records_per_s": box["n_rec"] / (ms / 1e3)}
+    return out, d_idx, d_len, d_st, d_arena
+
+
 def extract_workload(ix, n_text: int, n_ext: int, chars_each: int, steps: int, warmup: int, seed: int = 7):
     """FmIndex.extract of n_ext random ranges of chars_each chars (the reference's JMH extract workload shape)."""
     dev = torch.device("cuda", ix.device)

@@ -352,6 +352,75 @@ void fc_eub(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_
                 arena[(size_t)w * dst_len + offset + q] = left[(size_t)w * dst_len + (down[w] - 1 - q)];
 }
 
+// fused locate -> extractUntilBoundary (kernels_records.cuh) replayed on the host: scan + claim, record numbering, record
+// extraction, per-hit arithmetic — the same lane code and the same per-hit formula as the kernels
+static void rec_results_host(const FC& h, const int32_t* from, const int32_t* down, const int32_t* win, const int32_t* atb,
+                             const std::vector<uint64_t>& uidx, const std::vector<int32_t>& rel_of, uint32_t n, int32_t dst_len, int32_t* rec_index,
+                             int32_t* len_out, int32_t* status) {
+    for (uint32_t i = 0; i < n; ++i) {
+        if (status[i] != 0) {
+            rec_index[i] = -1;
+            len_out[i] = 0;
+            continue;
+        }
+        const int32_t f = from[i], d = down[i], w = win[i];
+        int32_t rel, u = -1;
+        if (w < 0) {
+            rel = atb[i] ? 0 : REL_NONE;
+        } else {
+            u = (int32_t)uidx[(size_t)w];
+            const int32_t r = rel_of[(size_t)u];
+            rel = (r >= 0 && r != REL_NONE) ? r - d : r;
+        }
+        const EubOut o = eub_right_chunks(f, d, rel, (int32_t)h.ix.length, dst_len, false, 0);
+        rec_index[i] = u;
+        len_out[i] = o.value;
+        status[i] = o.status;
+    }
+}
+uint64_t fc_records(void* hv, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len, int32_t* rec_index, int32_t* len_out,
+                    int32_t* status, uint16_t* rec_arena, uint64_t* counters) {
+    FC& h = *(FC*)hv;
+    uint32_t table = 1024;
+    while (table < 2u * n) table <<= 1;
+    std::vector<unsigned long long> claims(table, 0ull);
+    std::vector<int32_t> down(n, 0), win(n, -1), atb(n, 0);
+    WalkParams P{};
+    P.n_items = n;
+    P.from = from;
+    P.mb = h.ix.char2code[boundary];
+    P.dst_len = dst_len;
+    P.eub_mode = EUB_SCAN;
+    P.claims = claims.data();
+    P.claim_mask = table - 1u;
+    P.win_of = win.data();
+    P.at_bound = atb.data();
+    P.len_out = down.data();
+    P.status_out = status;
+    run_walk<WM_EUB>(h, P, counters);
+    std::vector<uint64_t> uidx(n + 1, 0);
+    uint64_t n_rec = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        uidx[i] = n_rec;
+        if (win[i] == (int32_t)i) ++n_rec;
+    }
+    std::vector<int32_t> start((size_t)n_rec + 1, 0), rel((size_t)n_rec + 1, 0), dummy((size_t)n_rec + 1, 0);
+    for (uint32_t i = 0; i < n; ++i)
+        if (win[i] == (int32_t)i) start[(size_t)uidx[i]] = from[i] - down[i];
+    WalkParams Q{};
+    Q.n_items = (uint32_t)n_rec;
+    Q.from = start.data();
+    Q.mb = P.mb;
+    Q.dst_len = dst_len;
+    Q.eub_mode = EUB_RECORD;
+    Q.arena = rec_arena;
+    Q.len_out = rel.data();
+    Q.status_out = dummy.data();
+    run_walk<WM_EUB>(h, Q, counters);
+    rec_results_host(h, from, down.data(), win.data(), atb.data(), uidx, rel, n, dst_len, rec_index, len_out, status);
+    return n_rec;
+}
+
 // locate (k_locate): the straight-line lane code of lf_lane.h, one hit at a time
 void fc_locate_rows(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* counters) {
     FC& h = *(FC*)hv;

@@ -45,6 +45,8 @@ def lib():
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
         L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, i32]
         L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp, i32]
+        L.fc_records.argtypes = [vp, vp, u32, C.c_uint16, i32, vp, vp, vp, vp, vp]
+        L.fc_records.restype = C.c_uint64
         L.fc_sampled.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
         L.fc_unrank_table.argtypes = [vp]
         L.fc_utf8_convert.argtypes = [vp, C.c_uint64, vp, C.POINTER(i32)]
@@ -149,6 +151,18 @@ class FlatIndexHost:
         lib().fc_eub(self._h, frm.ctypes.data, n, boundary, dst_len, mode, arena.ctypes.data, ln.ctypes.data, st.ctypes.data,
                      self.counters.ctypes.data, offset)
         return arena, ln, st
+
+    def records(self, frm, boundary, dst_len):
+        """host replay of the fused locate -> extractUntilBoundary pipeline (kernels_records.cuh)"""
+        frm = np.ascontiguousarray(frm, dtype=np.int32)
+        n = frm.size
+        idx = np.zeros(n, dtype=np.int32)
+        ln = np.zeros(n, dtype=np.int32)
+        st = np.zeros(n, dtype=np.int32)
+        arena = np.zeros((max(n, 1), max(dst_len, 1)), dtype=np.uint16)
+        n_rec = lib().fc_records(self._h, frm.ctypes.data, n, boundary, dst_len, idx.ctypes.data, ln.ctypes.data, st.ctypes.data, arena.ctypes.data,
+                                 self.counters.ctypes.data)
+        return idx, ln, st, arena[: int(n_rec)]
 
     def sampled(self, pos):
         b, r = C.c_int32(), C.c_int32()

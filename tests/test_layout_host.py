@@ -220,3 +220,39 @@ def test_offset_lanes(flats, name, offset):
     for i in np.flatnonzero(w_st == 0):
         assert got_len[i] == w_len[i]
         assert np.array_equal(arena[i * stride + offset: i * stride + offset + w_len[i]], w_arena[i, offset: offset + w_len[i]]), i
+
+
+def _check_records(case, frm, dst_len, idx, ln, st, records):
+    """per hit: exactly what the oracle's extractUntilBoundary(from, new char[dst_len], 0, '\\n') returns / throws"""
+    n = case.text.size
+    w_arena, w_len, w_st = case.oracle.extract_until_boundary_batch(frm, 10, dst_len, 0, threads=4)
+    assert np.array_equal(st, w_st), np.flatnonzero(st != w_st)[:10]
+    ok = (w_st == 0) | (w_st == 8)
+    assert np.array_equal(ln[ok], w_len[ok])
+    for i in np.flatnonzero(w_st == 0):
+        if frm[i] >= n or w_len[i] == 0:
+            continue
+        assert idx[i] >= 0
+        assert np.array_equal(records[idx[i], : w_len[i]], w_arena[i, : w_len[i]]), (i, int(frm[i]), int(w_len[i]))
+    return int((w_st == 0).sum())
+
+
+@pytest.mark.parametrize("name", ["log300k_sr64", "log1m_sr32", "tiny600k_sr4", "multi400k_sr8", "nul1m_sr32"])
+@pytest.mark.parametrize("dst_len", [512, 130, 37, 5])
+def test_record_lanes(flats, name, dst_len):
+    """Fused locate -> extractUntilBoundary (scan + claim, one extraction per distinct record, per-hit chunk arithmetic): every hit
+    gets what the reference's extractUntilBoundary returns or throws for it — hits clustered in the same records, at boundary
+    chars, at both ends of the text."""
+    case, f = get_case(name), flats(name)
+    n = case.text.size
+    rng = np.random.default_rng(90 + dst_len)
+    centers = rng.integers(0, n, 150)
+    near = (centers[:, None] + rng.integers(-60, 60, (150, 8))).reshape(-1)  # several hits per record
+    nl = np.flatnonzero(case.text == 10)
+    at_nl = nl[rng.integers(0, nl.size, 60)]
+    frm = np.concatenate([near, at_nl, at_nl + 1, at_nl - 1, rng.integers(0, n, 400), np.arange(n - 14, n + 2), np.arange(-1, 8)])
+    frm = np.clip(frm, -1, n + 1).astype(np.int32)
+    idx, ln, st, records = f.records(frm, 10, dst_len)
+    good = _check_records(case, frm, dst_len, idx, ln, st, records)
+    if dst_len >= 130 and name.startswith("log"):
+        assert good > 500 and records.shape[0] < 0.7 * frm.size  # the clustered hits share records
