@@ -324,8 +324,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side waiting (an NCCL barrier is a kernel that spins on the GPU)
 
     def barrier():
         if world > 1:
@@ -493,6 +495,7 @@ def main():
         torch.cuda.synchronize()
         barrier()
         strong = {"dev_ms": s0.elapsed_time(s1), "one_ms": 0.0, "one_utf8_ms": 0.0}
+        dist.barrier(group=cpu_group)  # the other ranks now wait on the HOST until rank 0 is done: their GPUs stay idle
         if rank == 0:
             t_load = time.time()
             mix = FmIndex.read(blob, devices=list(range(world)))
@@ -525,7 +528,7 @@ def main():
                 strong["one_utf8_ms"] = (time.perf_counter() - t0) * 1e3
             strong["h2d"] = int(chars0.nbytes + off0.nbytes)
             mix.close()
-        barrier()
+        dist.barrier(group=cpu_group)
 
     times = torch.tensor([ms_total, e2e_s * 1e3, statistics.mean(kernel_ms), lf["loc"]["ms_per_step"] if lf else 0.0,
                           lf["eub"]["ms_per_step"] if lf else 0.0, lf["loc_e2e_ms"] if lf else 0.0, utf8["s"] * 1e3 if utf8 else 0.0,

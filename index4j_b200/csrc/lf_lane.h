@@ -196,6 +196,10 @@ struct ExLane {
             start_isa((uint32_t)idx);
         } else {
             from = raw.a;
+            if (P.eub_mode == EUB_SCAN) {  // before any early exit: a hit the reference throws on owns no record
+                P.win_of[w] = -1;
+                P.at_bound[w] = 0;
+            }
             if (P.eub_mode == 1) ++from;  // :774
             if (!ix.extract_enabled) return finish(P, 1, 0);
             if (from < 0) return finish(P, 2, 0);
@@ -203,10 +207,6 @@ struct ExLane {
             if (P.dst_len == 0) return finish(P, 6, 0);
             if (P.mb == 0u) return finish(P, 7, 0);
             remaining = P.dst_len;
-            if (P.eub_mode == EUB_SCAN) {
-                P.win_of[w] = -1;
-                P.at_bound[w] = 0;
-            }
             if (P.eub_mode == 2 || P.eub_mode == EUB_RECORD) {
                 stage = 1;
                 cur = from;

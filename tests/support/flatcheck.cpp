@@ -384,7 +384,8 @@ uint64_t fc_records(void* hv, const int32_t* from, uint32_t n, uint16_t boundary
     uint32_t table = 1024;
     while (table < 2u * n) table <<= 1;
     std::vector<unsigned long long> claims(table, 0ull);
-    std::vector<int32_t> down(n, 0), win(n, -1), atb(n, 0);
+    std::vector<int32_t> down(n, 0), win(n, 0), atb(n, 0);
+    for (uint32_t i = 0; i < n; ++i) win[i] = (int32_t)i;  // poisoned: the lane code must initialise every entry
     WalkParams P{};
     P.n_items = n;
     P.from = from;

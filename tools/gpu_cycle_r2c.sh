@@ -2,7 +2,7 @@
 # round 2, cycle C (2 GPUs): full GPU parity suite (incl. replicated index + fused records), N=2 bench with strong-scaling legs
 TAG=${1:-r2c}; N=${2:-2}
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -25 > gpurun_out/${TAG}_pytest.txt
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -150 > gpurun_out/${TAG}_pytest.txt
 tail -6 gpurun_out/${TAG}_pytest.txt
 python bench.py --build-only 2> gpurun_out/${TAG}_build.log
 timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 10 --warmup 3 \
