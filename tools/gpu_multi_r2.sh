@@ -12,10 +12,3 @@ import json
 d=json.load(open("gpurun_out/${TAG}_bench_n${N}.json"))
 print("value %.3g e2e %.3g strong %s" % (d["value"], d["e2e"]["value"], json.dumps(d.get("strong"))[:900]))
 PY
-FMGPU_COUNT_KERNEL=6 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 10 --warmup 3 --no-lf \
-    > gpurun_out/${TAG}_bench_n${N}_flat.json 2> gpurun_out/${TAG}_bench_n${N}_flat.log
-python - <<PY
-import json
-d=json.load(open("gpurun_out/${TAG}_bench_n${N}_flat.json"))
-print("flat: value %.3g strong dev %s" % (d["value"], json.dumps((d.get("strong") or {}).get("device_resident"))))
-PY
