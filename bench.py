@@ -273,6 +273,25 @@ def run_reference(args):
     emit(out)
 
 
+def run_sharded(args):
+    """--mode sharded (BASELINE.json configs[4]): the text is split into one FmIndex shard per GPU with pattern-length overlap;
+    count = per-shard counts summed over NCCL, locate = owned hits of every shard exchanged over NCCL and merged in rank order
+    (index4j_b200/sharded.py, csrc/kernels_shard.cuh).  Launch under torchrun like the default mode."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_sharded
+    ns = argparse.Namespace(shard_chars=args.shard_chars, n_pat=args.sharded_n_pat, min_len=8, max_len=args.max_len, max_hits=args.sharded_max_hits,
+                            sample_rate=args.sample_rate, steps=max(args.steps, 1), verify=args.verify)
+    res = bench_sharded.run(ns)
+    if res is None:
+        return
+    out = {"metric": "sharded index: " + METRIC + " and located hits/sec", "value": res["count"]["patterns_per_s"], "unit": UNIT,
+           "n_gpus": res["n_gpus"], "steps": ns.steps, "warmup": 1, "ms_per_step": res["count"]["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": {"workload": res["workload"], "index": "one shard per GPU", "text_chars": res["text_chars"]},
+           "locate": res["locate"], "sharded": res}
+    emit(out)
+
+
 def workload_config(args):
     return {"workload": "count: %d patterns len %d-%d (substrings of the text) per GPU per step over FmIndex(sampleRate=%d) of %d chars of synthetic log text"
                         % (args.n_pat, args.min_len, args.max_len, args.sample_rate, args.n_text),
@@ -304,6 +323,13 @@ def main():
     ap.add_argument("--lf-steps", type=int, default=2)
     ap.add_argument("--n-eub", type=int, default=1_000_000)
     ap.add_argument("--dst-len", type=int, default=512)
+    ap.add_argument("--mode", default="replicated", choices=["replicated", "sharded"],
+                    help="sharded = BASELINE.json configs[4]: one FmIndex shard of --shard-chars chars per GPU (text beyond 2^31 chars), "
+                         "counts all-reduced, located positions exchanged over NCCL")
+    ap.add_argument("--shard-chars", type=int, default=1 << 30)
+    ap.add_argument("--sharded-n-pat", type=int, default=200_000)
+    ap.add_argument("--sharded-max-hits", type=int, default=100)
+    ap.add_argument("--verify", type=int, default=20000, help="sharded mode: located hits read back with extract")
     ap.add_argument("--build-only", action="store_true", help="build + cache the index and the pattern batches, then exit")
     args = ap.parse_args()
     claim_stdout()
@@ -312,6 +338,8 @@ def main():
 
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "sharded":
+        return run_sharded(args)
 
     import torch
     import torch.distributed as dist

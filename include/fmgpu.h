@@ -239,6 +239,30 @@ int fmgpu_build_bwt_samples_device(const uint16_t* d_codes, const int32_t* d_sa,
                                    uint32_t* d_mask_words_out, int32_t* d_suffixes_out, int64_t suffixes_cap, int32_t* d_positions_out,
                                    int64_t* n_sampled_out, void* cuda_stream);
 
+/* Sharded index — texts beyond the reference's 2^31-char limit (int length / char[] input, FM:131,155,335-341): one FmIndex per
+ * GPU over a text shard that also holds the first max_pattern_len - 1 chars of the next shard.  The reference has no such
+ * mode; each shard's results are bit-exact with the Java FmIndex of that shard, and these kernels compose them: a hit is OWNED
+ * by the shard in which it starts before owned_len, at most max_hits hits per pattern survive globally — lowest shard first,
+ * SA order inside a shard (max_hits <= 0: all).  Device pointers, the caller's stream, no synchronization; the host
+ * (index4j_b200/sharded.py, one process per GPU) runs the two NCCL exchanges between them.
+ *   keep : d_kept[p] = owned hits of pattern p among the local hits d_pos[d_hit_off[p] .. d_hit_off[p+1]), capped at max_hits
+ *          -> all-gather of d_kept over the ranks = d_all_kept[world][n_pat]
+ *   plan : d_take[r][p] = what rank r contributes after the global cut, d_n_hits[p] / d_hit_off[n_pat + 1] = global hits per
+ *          pattern and their offsets, d_roff[r][n_pat + 1] = offsets inside rank r's contribution, d_totals[world + 1] = size of
+ *          every rank's contribution + the merged total, d_rank_base[world] = where rank r's contribution starts in the receive buffer
+ *   pack : this rank's contribution as global positions (local + text_start, int64) in pattern order, d_send[d_totals[rank]]
+ *          -> exchange: every rank receives every contribution, rank r's at d_recv + d_rank_base[r]
+ *   merge: d_out[d_hit_off[p] ..] = the contributions of pattern p in rank order */
+int fmgpu_shard_keep_device(const int32_t* d_pos, const uint64_t* d_hit_off, uint32_t n_pat, int32_t owned_len, int32_t max_hits,
+                            int32_t* d_kept, void* cuda_stream);
+int fmgpu_shard_plan_device(const int32_t* d_all_kept, uint32_t n_pat, uint32_t world, uint32_t rank, int32_t max_hits, int32_t* d_take,
+                            int32_t* d_n_hits, uint64_t* d_hit_off, uint64_t* d_roff, uint64_t* d_totals, uint64_t* d_rank_base,
+                            void* cuda_stream);
+int fmgpu_shard_pack_device(const int32_t* d_pos, const uint64_t* d_hit_off, uint32_t n_pat, int32_t owned_len, int64_t text_start,
+                            const int32_t* d_take_mine, const uint64_t* d_send_off, int64_t* d_send, void* cuda_stream);
+int fmgpu_shard_merge_device(const int64_t* d_recv, const uint64_t* d_rank_base, const uint64_t* d_roff, const int32_t* d_take,
+                             const uint64_t* d_out_off, uint32_t n_pat, uint32_t world, int64_t* d_out, void* cuda_stream);
+
 /* Work counters of the most recent batch call on this index (device-side counted, read back here):
  * [0] rank queries that touched memory  [1] wavelet levels walked by rank queries
  * [2] LF steps (inverseSelect walks)     [3] wavelet levels walked by LF steps

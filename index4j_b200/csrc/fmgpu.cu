@@ -29,6 +29,7 @@
 #include "kernels_lf.cuh"
 #include "kernels_locate.cuh"
 #include "kernels_records.cuh"
+#include "kernels_shard.cuh"
 #include "kernels_utf8.cuh"
 #include "kernels_wavelet.cuh"
 #include "kernels_build.cuh"
@@ -603,6 +604,7 @@ Replica* replica_of(fmgpu_index* ix, const void* p) {
 #include "api_lf.inc"
 #include "api_wavelet.inc"
 #include "api_build.inc"
+#include "api_shard.inc"
 
 extern "C" {
 

@@ -3,7 +3,7 @@
 The composition logic (ownership filter, overlap correction, all-reduce of counts, all-gather of
 positions, global max_hits cut) is the product code; only the per-shard engine is a stand-in here
 (the CPU oracle behind the same tensor interface the GPU engine offers), because no GPU exists in
-this container.  tests/test_gpu_parity.py::test_sharded_single_gpu runs the same layer on the GPU engine.
+this container.  tests/test_gpu_sharded.py runs the same layer — with its CUDA composition kernels — on the GPU engine.
 """
 import os
 import socket
