@@ -316,6 +316,8 @@ def main():
     ap.add_argument("--cpu-locate-sample", type=int, default=20_000, help="patterns of the CPU arm of the locate leg")
     ap.add_argument("--cpu-eub-sample", type=int, default=50_000, help="records of the CPU arm of the extractUntilBoundary leg")
     ap.add_argument("--no-alt-kernel", action="store_true", help="skip the comparison launch with the other backward-search kernel")
+    ap.add_argument("--no-sr-sweep", action="store_true", help="skip the sampleRate 16 / 64 locate legs (BASELINE.json configs[2])")
+    ap.add_argument("--sweep-patterns", type=int, default=250_000, help="patterns of the sampleRate-sweep locate legs")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs of an N > 1 run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lf", action="store_true", help="skip the locate / extractUntilBoundary legs (extra keys of the JSON line)")
@@ -362,8 +364,11 @@ def main():
             dist.barrier()
 
     holder = {}
+    sweep_rates = [] if (args.no_sr_sweep or args.no_lf) else [sr for sr in (16, 64) if sr != args.sample_rate]
     if rank == 0:
         get_index_blob(args.n_text, args.sample_rate, holder)  # build + cache once per box
+        for sr in sweep_rates:
+            get_index_blob(args.n_text, sr, holder)
         for r in range(world):
             get_patterns(args.n_text, args.n_pat, args.min_len, args.max_len, 42 + r, holder)
     barrier()
@@ -498,6 +503,35 @@ def main():
         assert int(p_ho[-1]) == total_hits and np.array_equal(p_pos[:4096], d_pos[:4096].cpu().numpy())
         lf = {"rec": rec, "rec_first": rec_first, "loc": loc, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
               "d_hit_off": d_hit_off, "d_pos": d_pos, "h2d": int(chars.nbytes + off.nbytes), "d2h": int(p_nh.nbytes + p_ho.nbytes + p_pos.nbytes + h_status.nbytes)}
+
+    # BASELINE.json configs[2]: locate (max 1000 hits per pattern) over sampleRate 16 / 32 / 64 — LF-walk length against index
+    # size; every rank runs its own patterns over its replica (query-sharded), hits summed over ranks, time = max over ranks
+    sweep = {}
+    if lf and sweep_rates:
+        ns = min(args.sweep_patterns, n_pat)
+        sw_off = d_off[: ns + 1].contiguous()
+        sw_chars = d_chars[: int(off[ns])].contiguous()
+        ix.set_timing(False)
+        base_leg, _, _ = workloads.locate_workload_nostats(ix, sw_chars, sw_off, args.max_hits, args.lf_steps, 1)
+        sweep[args.sample_rate] = dict(base_leg, hbm_bytes=ix.device_bytes(), serialized_bytes=len(blob))
+        for sr in sweep_rates:
+            blob_sr = get_index_blob(args.n_text, sr, holder)
+            ix_sr = FmIndex.read(blob_sr, device=local)
+            leg, _, _ = workloads.locate_workload_nostats(ix_sr, sw_chars, sw_off, args.max_hits, args.lf_steps, 1)
+            sweep[sr] = dict(leg, hbm_bytes=ix_sr.device_bytes(), serialized_bytes=len(blob_sr))
+            ix_sr.close()
+            del blob_sr
+            torch.cuda.empty_cache()
+        ix.set_timing(True)
+        sw_t = torch.tensor([[sweep[sr]["ms_per_step"], 0.0] for sr in sorted(sweep)], dtype=torch.float64, device=dev)
+        sw_h = torch.tensor([[float(sweep[sr]["hits"]), float(sweep[sr]["lf_steps_est"])] for sr in sorted(sweep)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(sw_t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sw_h, op=dist.ReduceOp.SUM)
+        for k, sr in enumerate(sorted(sweep)):
+            sweep[sr]["ms_per_step_max_over_ranks"] = float(sw_t[k, 0])
+            sweep[sr]["hits_all_ranks"] = float(sw_h[k, 0])
+            sweep[sr]["hits_per_s"] = float(sw_h[k, 0]) / (float(sw_t[k, 0]) / 1e3)
 
     # strong scaling (BASELINE.json configs[1] as written: the ONE 1 M-pattern batch sharded over the GPUs).  (a) device-resident:
     # rank r searches slice r of rank 0's batch, time = max over ranks; (b) one process: rank 0 alone drives all N GPUs through
@@ -657,6 +691,13 @@ def main():
             "uniform_random_sector_peak_per_s": [38e9, 70e9],
             "note": "k_count runs above the uniform-random rate because cells hit L2 and neighbouring positions share DRAM rows",
         }
+        if sweep:
+            out["locate_sample_rate_sweep"] = {
+                "workload": "locate, max %d hits per pattern, the first %d patterns of every rank's batch, FmIndex(sampleRate 16 / 32 / 64) over the same text; %d GPU(s), query-sharded"
+                            % (args.max_hits, min(args.sweep_patterns, n_pat), world),
+                "by_sample_rate": {str(sr): {"hits_per_s": sweep[sr]["hits_per_s"], "ms_per_step": sweep[sr]["ms_per_step_max_over_ranks"],
+                                             "hits_per_step": sweep[sr]["hits_all_ranks"], "index_hbm_bytes": sweep[sr]["hbm_bytes"],
+                                             "serialized_bytes": sweep[sr]["serialized_bytes"]} for sr in sorted(sweep)}}
         if strong:
             out["strong"] = {
                 "workload": "the ONE batch of %d patterns sharded over %d GPUs (BASELINE.json configs[1] as written)" % (n_pat, world),

@@ -728,6 +728,13 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
     }
     flatten_sampled(fm.sampled, F);
     if ((uint64_t)(uint32_t)fm.sampled.total_ones > (uint64_t)fm.suffixes.length) throw FormatError("more sampled rows than suffix-array samples");
+    // the sampled structures must cover the text the way the constructor lays them out (fm/FmIndex.java:343-370): one SA sample per
+    // sampleRate text positions, length / sampleRate + 2 inverse-SA samples (the LF kernels index them without further checks)
+    if (fm.sample_rate < 1) throw FormatError("sampleRate < 1");
+    if ((int64_t)fm.suffixes.length < ((int64_t)fm.length - 1) / fm.sample_rate + 1) throw FormatError("fewer suffix-array samples than length / sampleRate");
+    if (fm.enable_extract && (int64_t)fm.positions.length != (int64_t)fm.length / fm.sample_rate + 2)
+        throw FormatError("inverse suffix-array samples: expected length / sampleRate + 2 entries");
+    if ((int64_t)fm.sampled.length != (int64_t)fm.length) throw FormatError("sampled-row vector length differs from the index length");
     unpack_samples(fm.suffixes, F.sa, (uint64_t)fm.length, "suffix-array");
     if (fm.enable_extract) unpack_samples(fm.positions, F.isa, (uint64_t)fm.length, "inverse suffix-array");
     else F.isa.assign(1, Rec32{});

@@ -64,6 +64,20 @@ def locate_workload(ix, d_chars, d_off, max_hits: int, steps: int, warmup: int):
     return out, d_hit_off, d_pos
 
 
+def locate_workload_nostats(ix, d_chars, d_off, max_hits: int, steps: int, warmup: int):
+    """locate_workload without the instrumented pass / kernel timing (the sampleRate sweep of bench.py)."""
+    dev = d_chars.device
+    n_pat = d_off.numel() - 1
+    d_n_hits = torch.empty(n_pat, dtype=torch.int32, device=dev)
+    d_hit_off = torch.empty(n_pat + 1, dtype=torch.int64, device=dev)
+    total = ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, None, None)
+    d_pos = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    fn = lambda: ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, d_pos, None)  # noqa: E731
+    ms = _timed(fn, steps, warmup)
+    out = {"patterns": n_pat, "hits": int(total), "ms_per_step": ms, "lf_steps_est": float(total) * (ix.sample_rate - 1) / 2.0}
+    return out, d_hit_off, d_pos
+
+
 def eub_workload(ix, d_from, dst_len: int, steps: int, warmup: int, boundary="\n", mode: int = 0):
     """FmIndex.extractUntilBoundary for every position of d_from into an n x dst_len device arena."""
     dev = d_from.device
