@@ -315,7 +315,6 @@ def main():
     ap.add_argument("--cpu-repeats", type=int, default=3)
     ap.add_argument("--cpu-locate-sample", type=int, default=20_000, help="patterns of the CPU arm of the locate leg")
     ap.add_argument("--cpu-eub-sample", type=int, default=50_000, help="records of the CPU arm of the extractUntilBoundary leg")
-    ap.add_argument("--no-alt-kernel", action="store_true", help="skip the comparison launch with the other backward-search kernel")
     ap.add_argument("--no-sr-sweep", action="store_true", help="skip the sampleRate 16 / 64 locate legs (BASELINE.json configs[2])")
     ap.add_argument("--sweep-patterns", type=int, default=250_000, help="patterns of the sampleRate-sweep locate legs")
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling legs of an N > 1 run")
@@ -419,20 +418,6 @@ def main():
     stats["launches"] = launches_per_step
     ix.set_stats(False)
     clocks = sampler.stop() if rank == 0 else None
-    # for the record: the same launch with the flat kernel (v6: lane per pattern with refill); the timed steps above ran the default
-    alt_ms = None
-    default_kernel = os.environ.get("FMGPU_COUNT_KERNEL", "5")
-    if not args.no_alt_kernel:
-        ix.set_count_kernel(6 if default_kernel == "5" else 5)
-        for _ in range(3):
-            step()
-        torch.cuda.synchronize()
-        for _ in range(5):
-            step()
-        torch.cuda.synchronize()
-        alt_ms = statistics.mean(ix.search_kernel_ms(i) for i in range(5))
-        ix.set_count_kernel(int(default_kernel))
-
     # end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
     p_chars = torch.from_numpy(chars.view(np.int16)).pin_memory()
     p_off = torch.from_numpy(off.view(np.int64)).pin_memory()
@@ -626,16 +611,15 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes,
-                         "alg_bytes_formula": "32 * (ranks + level_records) + pattern chars / descriptors: one 32-byte cell per rank and one "
-                                              "32-byte level record per TWO wavelet levels, 32 * (1 + ceil(L / 2)) per rank (DESIGN.md section 5)",
+                         "alg_bytes_formula": "32 * (ranks + occurrence records) + pattern chars / descriptors: one 32-byte (block, symbol) cell per rank "
+                                              "and at most one 32-byte occurrence record (none for absent / run / <= 10-occurrence symbols) (DESIGN.md section 5)",
                          "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
                          "level_records_per_launch": stats["level_records"],
                          "records_loaded_per_launch": stats["search_records_loaded"],
                          "spec_root_loads_wasted_per_launch": stats.get("spec_root_wasted", 0),
                          "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3),
-                         "kernel_version": default_kernel + (" (flat: lane per pattern with refill)" if default_kernel != "5" else " (warp-lockstep)"),
-                         "other_kernel_ms_rank0": {("6 (flat)" if default_kernel == "5" else "5 (warp-lockstep)"): alt_ms}},
+                         "occurrence_records_per_launch": stats["level_records"]},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob),
                       "start_table_q": ix.start_table_q()},
         }

@@ -93,8 +93,8 @@ int32_t fmgpu_device(const fmgpu_index* idx);             /* the first (primary)
 int32_t fmgpu_num_devices(const fmgpu_index* idx);        /* replicas */
 int32_t fmgpu_device_at(const fmgpu_index* idx, int32_t i);
 uint64_t fmgpu_device_bytes(const fmgpu_index* idx);    /* bytes of HBM held by the index */
-/* component sizes (bytes): [0] cells [1] level sectors [2] node records [3] block descriptors
- * [4] path overflow [5] sampled-row groups+offsets [6] SA samples [7] ISA samples */
+/* component sizes (bytes): [0] cells [1] level records [2] node records [3] block descriptors
+ * [4] occurrence records [5] sampled-row groups+offsets [6] SA samples [7] ISA samples */
 void fmgpu_layout_bytes(const fmgpu_index* idx, uint64_t out8[8]);
 
 /* Page-locked host memory.  The host-pointer batch calls copy with cudaMemcpyAsync, which only overlaps with the kernels (and
@@ -121,13 +121,6 @@ int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const ui
  * building it, FMGPU_START_TABLE_LOG2=n caps it at 2^n entries.  fmgpu_start_table_q: q, 0 = no table. */
 int fmgpu_set_start_table(fmgpu_index* idx, int enable);
 int32_t fmgpu_start_table_q(const fmgpu_index* idx);
-
-/* Which backward-search kernel count / locate use: 5 (default) = warp-lockstep over length-sorted patterns
- * (csrc/count_lane.h); 6 = "flat" — one lane per pattern, every lane fetches the one record its own pattern needs next and
- * takes the next pattern from a work queue when it is done (csrc/count_flat.h): fewer memory round trips per pattern, but
- * twice the issued instructions (measured slower on the 1 M-pattern batch).  Results are identical.
- * FMGPU_COUNT_KERNEL=5|6 in the environment sets the default of new handles. */
-int fmgpu_set_count_kernel(fmgpu_index* idx, int version);
 
 /* UTF-8 byte patterns: FmIndex.convertBytePatternToCharPattern(byte[] p, 0, p.length, dst) FM:239-298 followed by
  * count(dst, 0, n) / locate(dst, 0, n, ...).  Pattern i is the byte[] bytes[pat_off[i], pat_off[i+1]) — pat_off are BYTE
@@ -267,9 +260,10 @@ int fmgpu_shard_merge_device(const int64_t* d_recv, const uint64_t* d_rank_base,
  * [0] rank queries that touched memory  [1] wavelet levels walked by rank queries
  * [2] LF steps (inverseSelect walks)     [3] wavelet levels walked by LF steps
  * [4] sampled-row bit tests              [5] kernels launched by the call
- * [6] 32-byte records actually loaded by the backward-search kernel (two positions of one pattern
- *     that fall into the same level record share one load)
- * [7] level records a query needs (one per TWO wavelet levels): by rank queries and by LF steps
+ * [6] 32-byte records actually loaded by the backward-search kernel (cells + occurrence records; two positions of one
+ *     pattern that fall into the same cell / record share one load)
+ * [7] records beyond the cell / descriptor the queries need: occurrence records of rank queries (0 or 1 each), level records
+ *     of LF steps (one per TWO wavelet levels)
  * Used by bench.py for the roofline's algorithmic-bytes figure. */
 int fmgpu_last_stats(fmgpu_index* idx, uint64_t out8[8]);
 /* The kernels keep these counters only while enabled (default: off — the production instantiations carry none;

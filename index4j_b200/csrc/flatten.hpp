@@ -91,8 +91,7 @@ struct FlatIndex {
     std::vector<uint32_t> C;
     std::vector<uint16_t> char2code, code2char;
     std::vector<fmgpu::SbDesc> sb;
-    std::vector<fmgpu::U32x2> sbroot, blkmap;  // root-record directory (layout.h)
-    std::vector<Rec32> cells, sectors, ovf, blocks, nodes, sgroups, sa, isa;
+    std::vector<Rec32> cells, sectors, occ, blocks, nodes, sgroups, sa, isa;
     std::vector<uint32_t> soffsets;
     int32_t alphabet_length = 0;
 };
@@ -116,8 +115,9 @@ struct BlockTree {
     std::vector<Leaf> leaves;     // by block-local symbol index (canonical code order)
     std::vector<uint16_t> sym;    // header symbol per leaf
     std::vector<uint32_t> brank;  // rankAtBlockBoundary per leaf
+    std::vector<uint32_t> occ;    // occurrences of the leaf's symbol in the block (= elements that reach the leaf)
     int h = 0;
-    uint32_t n_sectors = 0, n_ovf_chunks = 0, n_even = 0;  // Rec32 units (root excluded) / chunks / even-depth internal nodes
+    uint32_t n_sectors = 0, n_occ = 0, n_even = 0;  // level records / occurrence records / even-depth internal nodes
 };
 
 struct VarReader {
@@ -140,6 +140,21 @@ struct VarReader {
     }
 };
 
+// occurrence records a (block, symbol) pair with `occ` occurrences in a block of `block_size` positions needs (layout.h):
+// none when its positions fit the cell, a sorted position list while that is the smaller form, else one bit per position
+inline uint32_t occ_kind(uint32_t occ, uint32_t block_size) {
+    if (occ <= fmgpu::OCC_INLINE_MAX) return fmgpu::CELL_OCC_INLINE;
+    const uint32_t list = (occ + fmgpu::OCC_LIST_PER_REC - 1) / fmgpu::OCC_LIST_PER_REC;
+    const uint32_t bits = block_size / fmgpu::OCC_BITS_PER_REC + 1;
+    return (occ <= fmgpu::OCC_LIST_MAX && list <= bits) ? fmgpu::CELL_OCC_LIST : fmgpu::CELL_OCC_BITS;
+}
+inline uint32_t occ_records(uint32_t occ, uint32_t block_size) {
+    const uint32_t k = occ_kind(occ, block_size);
+    if (k == fmgpu::CELL_OCC_INLINE) return 0;
+    if (k == fmgpu::CELL_OCC_LIST) return (occ + fmgpu::OCC_LIST_PER_REC - 1) / fmgpu::OCC_LIST_PER_REC;
+    return block_size / fmgpu::OCC_BITS_PER_REC + 1;
+}
+
 // `sigma`: the wavelet alphabet size — header symbols must lie below it (the kernels index C[] and the rank directories with them)
 inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_block_size, BlockTree& T, int32_t sigma) {
     const BlockHdr& H = S.blocks[b];
@@ -150,8 +165,9 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
     T.leaves.clear();
     T.sym.clear();
     T.brank.clear();
+    T.occ.clear();
     T.n_sectors = 0;
-    T.n_ovf_chunks = 0;
+    T.n_occ = 0;
     T.n_even = 0;
     if (sig < 1 || h < 0) throw FormatError("block header out of range");
     VarReader R(S.var);
@@ -169,6 +185,7 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
     if (h == 0) return;  // run block: no tree
     if (sig < 2) throw FormatError("tree block with a single symbol");
     T.leaves.resize((size_t)sig);
+    T.occ.assign((size_t)sig, 0);
     int64_t third = ptr32 + 5 * (int64_t)sig;
     std::vector<uint32_t> level;  // node ids of the current depth, left to right
     T.nodes.push_back({(uint32_t)H.bv_offset, cur_block_size, {0, 0}, 0, 0, 0});
@@ -202,6 +219,7 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
                     T.nodes[id].child[bit] = (int32_t)(-(li + 1));
                     T.leaves[(size_t)li].parent = (int32_t)id;
                     T.leaves[(size_t)li].bit = (uint8_t)bit;
+                    T.occ[(size_t)li] = csize;
                 } else {
                     const uint32_t nid = (uint32_t)T.nodes.size();
                     T.nodes[id].child[bit] = (int32_t)nid;
@@ -240,16 +258,14 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
         if (len > 32) throw FormatError("Huffman code longer than 32 bits");
         L.len = (uint8_t)len;
         L.code = code;  // bit (len-1) = root decision
-        // the cell holds the records of the even-depth nodes on the path: (len+1)/2 entries, 5 inline
-        const int pairs = (len + 1) / 2;
-        if (pairs > (int)fmgpu::CELL_INLINE_PAIRS) T.n_ovf_chunks += (uint32_t)((pairs - ((int)fmgpu::CELL_INLINE_PAIRS - 1) + 7) / 8);
+        if (len > 2) T.n_occ += occ_records(T.occ[(size_t)i], cur_block_size);  // codes of 1-2 bits use the root's level records
     }
-    // records of the even-depth nodes; the root's records live in the superblock's root area (fixed stride per block)
+    // level records of the even-depth nodes (inverseSelect walks them, lf_lane.h)
     for (size_t id = 0; id < T.nodes.size(); ++id) {
         const auto& n = T.nodes[id];
         if ((n.depth & 1u) == 0) {
             if (n.size > 65536u) throw FormatError("wavelet node larger than a block");
-            if (id != 0) T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
+            T.n_sectors += n.size / fmgpu::SECTOR_BITS + 1;
             ++T.n_even;
         }
     }
@@ -257,13 +273,9 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
 
 struct SbPlan {
     uint32_t first_block = 0, rows = 0;
-    uint64_t sector_base = 0, node_base = 0, ovf_base = 0;
-    uint64_t n_sectors = 0, n_nodes = 0, n_ovf = 0;  // n_sectors includes the root area (n_tree_blocks * root_stride)
-    uint32_t n_tree_blocks = 0, root_stride = 0;
-    std::vector<uint8_t> has_tree;  // per block
+    uint64_t sector_base = 0, node_base = 0, occ_base = 0;
+    uint64_t n_sectors = 0, n_nodes = 0, n_occ = 0;
 };
-
-inline uint32_t root_stride_of(int block_size_log) { return (1u << block_size_log) / fmgpu::SECTOR_BITS + 1u; }
 
 inline uint32_t sb_block_size(const WfbbStream& W, size_t sb, size_t b) {
     const int64_t bs = 1LL << W.sbs[sb].block_size_log;
@@ -302,6 +314,53 @@ inline void put_cell(Rec32& c, uint32_t kind, uint32_t value) {
     c.w[2] = kind << 8;
 }
 
+// occurrence structure of one (block, symbol) pair: positions (ascending, block-relative) of the symbol's occurrences
+// -> the cell words w1, w3..w7 and its records in F.occ[at ..] (layout.h)
+inline void put_occ(Rec32& cell, const std::vector<uint16_t>& pos, uint32_t block_size, uint32_t at, std::vector<Rec32>& occ) {
+    const uint32_t n = (uint32_t)pos.size();
+    const uint32_t kind = occ_kind(n, block_size);
+    cell.w[2] = (cell.w[2] & 0xffu) | (kind << 8);
+    auto put16 = [](Rec32& r, uint32_t first_word, uint32_t k, uint16_t v) {  // k-th u16 slot from word `first_word`
+        uint32_t& w = r.w[first_word + (k >> 1)];
+        w = (k & 1u) ? ((w & 0x0000ffffu) | ((uint32_t)v << 16)) : ((w & 0xffff0000u) | v);
+    };
+    if (kind == fmgpu::CELL_OCC_INLINE) {
+        cell.w[1] = n;
+        for (uint32_t k = 0; k < fmgpu::OCC_INLINE_MAX; ++k) put16(cell, 3, k, k < n ? pos[k] : 0xffffu);
+        return;
+    }
+    cell.w[1] = at;
+    if (kind == fmgpu::CELL_OCC_LIST) {
+        const uint32_t nrec = (n + fmgpu::OCC_LIST_PER_REC - 1) / fmgpu::OCC_LIST_PER_REC;
+        for (uint32_t q = 0; q < nrec; ++q) {
+            Rec32& R = occ[(size_t)at + q];
+            for (uint32_t k = 0; k < fmgpu::OCC_LIST_PER_REC; ++k) {
+                const uint32_t i = q * fmgpu::OCC_LIST_PER_REC + k;
+                put16(R, 0, k, i < n ? pos[i] : 0xffffu);
+            }
+        }
+        // splitter j = first position of record j + 1
+        for (uint32_t j = 0; j < fmgpu::OCC_INLINE_MAX; ++j) {
+            const uint32_t i = (j + 1) * fmgpu::OCC_LIST_PER_REC;
+            put16(cell, 3, j, i < n ? pos[i] : 0xffffu);
+        }
+        return;
+    }
+    const uint32_t nrec = block_size / fmgpu::OCC_BITS_PER_REC + 1;
+    size_t i = 0;
+    for (uint32_t q = 0; q < nrec; ++q) {
+        Rec32& R = occ[(size_t)at + q];
+        memset(&R, 0, sizeof R);
+        R.w[0] = (uint32_t)i;  // occurrences before the record
+        const uint32_t lo = q * fmgpu::OCC_BITS_PER_REC, hi = lo + fmgpu::OCC_BITS_PER_REC;
+        while (i < n && pos[i] < hi) {
+            const uint32_t bit = pos[i] - lo;
+            R.w[1 + (bit >> 5)] |= 1u << (bit & 31u);
+            ++i;
+        }
+    }
+}
+
 inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, FlatIndex& F) {
     const SuperBlockHdr& S = W.sbs[sb];
     const int32_t sigma = W.sigma;
@@ -315,15 +374,16 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
     rrr_decode_all(S.rank_support, bits);
     const uint64_t nbits = (uint64_t)S.rank_support.length;
 
-    // --- per block: tree, sectors, node records, descriptors
+    // --- per block: tree, level + node records (inverseSelect), descriptors, and per leaf the positions of its occurrences
     std::vector<BlockTree> trees(nblk);
-    // root records first (fixed stride per tree block, block order), the other even-depth nodes after them
-    uint64_t root_sec = P.sector_base, sec = P.sector_base + (uint64_t)P.n_tree_blocks * P.root_stride;
-    uint64_t node = P.node_base, ovf = P.ovf_base;
-    std::vector<uint64_t> block_node_base(nblk, 0), block_ovf_base(nblk, 0);
+    std::vector<std::vector<std::vector<uint16_t>>> leaf_pos(nblk);  // [block][leaf] -> ascending positions in the block
+    uint64_t sec = P.sector_base, node = P.node_base, occ_at = P.occ_base;
+    std::vector<uint64_t> block_occ_base(nblk, 0);
+    std::vector<uint16_t> cur, nxt;
     for (size_t b = 0; b < nblk; ++b) {
         BlockTree& T = trees[b];
-        build_block_tree(S, b, sb_block_size(W, sb, b), T, W.sigma);
+        const uint32_t bsize = sb_block_size(W, sb, b);
+        build_block_tree(S, b, bsize, T, W.sigma);
         Rec32& D = F.blocks[(size_t)P.first_block + b];
         memset(&D, 0, sizeof D);
         if (T.h == 0) {
@@ -335,24 +395,15 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                 D.w[5] = (uint32_t)((uint64_t)W.hyper_rank[c8] + (uint64_t)(int64_t)W.sb_rank[sb * (size_t)sigma + c8] + T.brank[0]);
             continue;
         }
-        block_node_base[b] = node;
-        block_ovf_base[b] = ovf;
+        block_occ_base[b] = occ_at;
+        occ_at += T.n_occ;
         // record arrays and node-record indices of the even-depth nodes
-        {
-            uint64_t e = node;
-            for (size_t id = 0; id < T.nodes.size(); ++id) {
-                auto& n = T.nodes[id];
-                if (n.depth & 1u) continue;
-                n.enode = (uint32_t)e++;
-                if (id == 0) {
-                    if (n.size / fmgpu::SECTOR_BITS + 1 > P.root_stride) throw FormatError("root node larger than its block");
-                    n.sector = (uint32_t)root_sec;
-                    root_sec += P.root_stride;
-                } else {
-                    n.sector = (uint32_t)sec;
-                    sec += n.size / fmgpu::SECTOR_BITS + 1;
-                }
-            }
+        for (size_t id = 0; id < T.nodes.size(); ++id) {
+            auto& n = T.nodes[id];
+            if (n.depth & 1u) continue;
+            n.enode = (uint32_t)node++;
+            n.sector = (uint32_t)sec;
+            sec += n.size / fmgpu::SECTOR_BITS + 1;
         }
         auto leaf_entry = [&](int32_t c, uint32_t flag, uint32_t* e) {
             const size_t li = (size_t)(-c - 1);
@@ -364,14 +415,14 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         };
         for (size_t id = 0; id < T.nodes.size(); ++id) {
             const BlockTree::Node& n = T.nodes[id];
-            if (n.depth & 1u) continue;
             if ((uint64_t)n.start + n.size > nbits) throw FormatError("wavelet node exceeds the level bitvector");
+            if (n.depth & 1u) continue;
             const BlockTree::Node* ch[2] = {n.child[0] >= 0 ? &T.nodes[(size_t)n.child[0]] : nullptr,
                                             n.child[1] >= 0 ? &T.nodes[(size_t)n.child[1]] : nullptr};
             for (int t = 0; t < 2; ++t)
                 if (ch[t] && (uint64_t)ch[t]->start + ch[t]->size > nbits) throw FormatError("wavelet node exceeds the level bitvector");
-            // level records (layout.h): {c1, c01 | c11 << 16, 96 bits of this node, for the same 96 positions the bit each
-            // element has one level further down (in the child it goes to; 0 if that child is a leaf)}
+            // level records (layout.h): {c00 | c01 << 16, c10 | c11 << 16, 96 bits of this node, for the same 96 positions the bit
+            // each element has one level further down (in the child it goes to; 0 if that child is a leaf)}
             const uint32_t nrec = n.size / fmgpu::SECTOR_BITS + 1;
             uint32_t cnt2[2][2] = {{0, 0}, {0, 0}}, cpos[2] = {0, 0};  // elements so far by (bit here, bit one level down)
             for (uint32_t q = 0; q < nrec; ++q) {
@@ -421,15 +472,34 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                 D.w[4] = n.enode;
             }
         }
-        node += T.n_even;
-        ovf += T.n_ovf_chunks;
+        // which leaf every position of the block ends in: the tree's bitvectors are stable partitions of the block, level by
+        // level; the elements of a node in node order are the block positions that reach it, ascending
+        auto& LP = leaf_pos[b];
+        LP.assign(T.leaves.size(), {});
+        for (size_t li = 0; li < T.leaves.size(); ++li) LP[li].reserve(T.occ[li]);
+        std::vector<std::vector<uint16_t>> elems(T.nodes.size());
+        elems[0].resize(bsize);
+        for (uint32_t i = 0; i < bsize; ++i) elems[0][i] = (uint16_t)i;
+        for (size_t id = 0; id < T.nodes.size(); ++id) {  // BFS order: parents before children
+            const BlockTree::Node& n = T.nodes[id];
+            std::vector<uint16_t>& E = elems[id];
+            if (E.size() != n.size) throw FormatError("wavelet node size differs from the elements that reach it");
+            for (uint32_t i = 0; i < n.size; ++i) {
+                const uint32_t t = bits_get(bits, (uint64_t)n.start + i, 1);
+                const int32_t c = n.child[t];
+                if (c >= 0) elems[(size_t)c].push_back(E[i]);
+                else LP[(size_t)(-c - 1)].push_back(E[i]);
+            }
+            std::vector<uint16_t>().swap(E);
+        }
+        for (size_t li = 0; li < T.leaves.size(); ++li)
+            if (LP[li].size() != T.occ[li]) throw FormatError("wavelet leaf size differs from the elements that reach it");
     }
 
-    // --- cells: rank(pos in block b, sym) with everything but the level walk pre-evaluated
-    const bool last_sb = (sb + 1 == W.sbs.size());
-    std::vector<uint32_t> ovf_next(nblk);
-    for (size_t b = 0; b < nblk; ++b) ovf_next[b] = (uint32_t)block_ovf_base[b];
+    // --- cells: rank(pos in block b, sym) with everything but the position-dependent part pre-evaluated
     VarReader R(S.var);
+    std::vector<uint32_t> occ_next(nblk);
+    for (size_t b = 0; b < nblk; ++b) occ_next[b] = (uint32_t)block_occ_base[b];
     for (int32_t sym = 0; sym < sigma; ++sym) {
         const int64_t sb_c = W.global_mapping[sb * (size_t)sigma + (size_t)sym];
         const uint64_t rank_sb = (uint64_t)(int64_t)W.sb_rank[sb * (size_t)sigma + (size_t)sym];
@@ -493,34 +563,30 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                     } else if (bc < 0 || (size_t)bc >= T.leaves.size()) {
                         put_cell(cell, fmgpu::CELL_THROW, 0);
                     } else {
+                        // the level walk of :1185-1279 along the leaf's code counts the elements among the first r positions
+                        // of the block that reach the leaf: stored as the leaf's occurrence structure (layout.h)
                         const BlockTree::Leaf& L = T.leaves[(size_t)bc];
                         memset(&cell, 0, sizeof cell);
                         cell.w[0] = (uint32_t)(rank_hb + rank_sb + rank_blk);
-                        cell.w[1] = L.code;
-                        cell.w[2] = (uint32_t)L.len | (fmgpu::CELL_NORMAL << 8);
-                        // records of the even-depth nodes along the path, root first
-                        uint32_t path[17];
-                        const int pairs = (L.len + 1) / 2;
-                        {
-                            int32_t id = 0;
-                            for (int d = 0; d < L.len; ++d) {
-                                if ((d & 1) == 0) path[d >> 1] = T.nodes[(size_t)id].sector;
-                                if (d + 1 < L.len) id = T.nodes[(size_t)id].child[(L.code >> (L.len - 1 - d)) & 1];
-                            }
-                        }
-                        if (pairs <= (int)fmgpu::CELL_INLINE_PAIRS) {
-                            for (int k = 0; k < pairs; ++k) cell.w[3 + k] = path[k];
+                        cell.w[2] = (uint32_t)L.len;  // code length: what the reference's walk costs (work counters)
+                        const std::vector<uint16_t>& pos = leaf_pos[(size_t)b][(size_t)bc];
+                        const uint32_t bsize = sb_block_size(W, sb, (size_t)b);
+                        const uint32_t need = L.len > 2 ? occ_records((uint32_t)pos.size(), bsize) : 0u;
+                        const uint32_t at = occ_next[(size_t)b];
+                        if (L.len <= 2) {
+                            // the root's level record of the position resolves a code of one or two bits (u = 0 for one bit)
+                            cell.w[2] |= fmgpu::CELL_OCC_LEVEL << 8;
+                            cell.w[1] = T.nodes[0].sector;
+                            const uint32_t t = (L.code >> (L.len - 1)) & 1u;
+                            const uint32_t u = L.len == 2 ? (L.code & 1u) : 0u;
+                            cell.w[3] = t | (u << 1);
+                        } else if ((uint64_t)at + need > block_occ_base[(size_t)b] + T.n_occ) {
+                            // two alphabet symbols mapped to the same leaf (a corrupt header): the block's occurrence records are
+                            // sized for one structure per leaf
+                            put_cell(cell, fmgpu::CELL_THROW, 0);
                         } else {
-                            const int inl = (int)fmgpu::CELL_INLINE_PAIRS - 1;
-                            for (int k = 0; k < inl; ++k) cell.w[3 + k] = path[k];
-                            const uint32_t chunks = (uint32_t)((pairs - inl + 7) / 8);
-                            const uint32_t at = ovf_next[(size_t)b];
-                            ovf_next[(size_t)b] += chunks;
-                            cell.w[7] = at;
-                            for (uint32_t k = 0; k < chunks * 8; ++k) {
-                                const int q = inl + (int)k;
-                                F.ovf[(size_t)at + k / 8].w[k % 8] = q < pairs ? path[q] : 0xffffffffu;
-                            }
+                            occ_next[(size_t)b] += need;
+                            put_occ(cell, pos, bsize, at, F.occ);
                         }
                     }
                 }
@@ -528,10 +594,9 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
             if (in_range && !absent) next_present = b;
         }
     }
-    (void)last_sb;
 
     // single-symbol blocks: the LF step needs rank(j, c') for the symbol c' inverseSelect decodes (low byte only) and
-    // j inside the same block; that is the (block, c') cell, which never has a level walk here — copy it into the descriptor
+    // j inside the same block; that is the (block, c') cell, which never needs a record here — copy it into the descriptor
     for (size_t b = 0; b < nblk; ++b) {
         if (trees[b].h != 0) continue;
         Rec32& D = F.blocks[(size_t)P.first_block + b];
@@ -543,7 +608,8 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         }
         const Rec32& cell = F.cells[((size_t)P.first_block + b) * (size_t)sigma + c];
         const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
-        if (kind == fmgpu::CELL_NORMAL) throw FormatError("single-symbol block with a level walk");
+        if (kind != fmgpu::CELL_CONST && kind != fmgpu::CELL_RUN && kind != fmgpu::CELL_THROW)
+            throw FormatError("single-symbol block with a tree walk");
         D.w[2] = cell.w[0];
         D.w[3] = kind;
     }
@@ -649,71 +715,39 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
         SbPlan& P = plan[sb];
         P.rows = (uint32_t)expect;
         if (sb + 1 == nsb && (sb_size % bs) == 0 && sb_size != (1LL << 20)) P.rows += 1;  // row for position == size
-        P.root_stride = root_stride_of(S.block_size_log);
-        P.has_tree.assign(P.rows, 0);
         BlockTree T;
         for (size_t b = 0; b < S.blocks.size(); ++b) {
             build_block_tree(S, b, sb_block_size(W, sb, b), T, W.sigma);
-            if (T.h != 0) {
-                P.has_tree[b] = 1;
-                ++P.n_tree_blocks;
-            }
             P.n_sectors += T.n_sectors;
             P.n_nodes += T.n_even;
-            P.n_ovf += T.n_ovf_chunks;
+            P.n_occ += T.n_occ;
         }
-        P.n_sectors += (uint64_t)P.n_tree_blocks * P.root_stride;
     });
-    uint64_t blocks_total = 0, sectors_total = 0, nodes_total = 0, ovf_total = 0;
+    uint64_t blocks_total = 0, sectors_total = 0, nodes_total = 0, occ_total = 0;
     F.sb.assign(nsb + 1, fmgpu::SbDesc{0, 16});  // +1: a lane may form the (unused) descriptor address of position == length
     for (size_t sb = 0; sb < nsb; ++sb) {
         SbPlan& P = plan[sb];
         P.first_block = (uint32_t)blocks_total;
         P.sector_base = sectors_total;
         P.node_base = nodes_total;
-        P.ovf_base = ovf_total;
+        P.occ_base = occ_total;
         blocks_total += P.rows;
         sectors_total += P.n_sectors;
         nodes_total += P.n_nodes;
-        ovf_total += P.n_ovf;
+        occ_total += P.n_occ;
         F.sb[sb].first_block = P.first_block;
         F.sb[sb].block_log = (uint32_t)W.sbs[sb].block_size_log;
     }
-    // root-record directory: blkmap[w] = {tree-block bits of blocks 32w.., tree blocks before block 32w},
-    // sbroot[sb] = {root area base - G(first block) * stride, stride}
-    F.blkmap.assign((size_t)(blocks_total / 32 + 2), fmgpu::U32x2{0, 0});
-    F.sbroot.assign(nsb + 1, fmgpu::U32x2{0, 1});
-    {
-        uint64_t g = 0;
-        std::vector<uint32_t> gfirst(nsb, 0);
-        for (size_t sb = 0; sb < nsb; ++sb) {
-            const SbPlan& P = plan[sb];
-            gfirst[sb] = (uint32_t)g;
-            for (uint32_t b = 0; b < P.rows; ++b)
-                if (P.has_tree[b]) {
-                    const uint64_t blk = (uint64_t)P.first_block + b;
-                    F.blkmap[(size_t)(blk >> 5)].x |= 1u << (blk & 31u);
-                    ++g;
-                }
-            F.sbroot[sb].y = P.root_stride;
-            F.sbroot[sb].x = (uint32_t)P.sector_base - gfirst[sb] * P.root_stride;  // wraps; undone by + G(block) * stride
-        }
-        uint32_t acc = 0;
-        for (auto& m : F.blkmap) {
-            m.y = acc;
-            acc += (uint32_t)__builtin_popcount(m.x);
-        }
-    }
-    M.n_blkmap = (uint32_t)F.blkmap.size();
-    if (sectors_total >= 0xffffffffULL || nodes_total >= 0x7fffffffULL || ovf_total >= 0xffffffffULL || blocks_total >= 0xffffffffULL)
+    if (sectors_total >= 0xffffffffULL || nodes_total >= 0x7fffffffULL || occ_total >= 0xffffffffULL || blocks_total >= 0xffffffffULL)
         throw FormatError("index too large for 32-bit record indices");
     const uint64_t cell_bytes = blocks_total * (uint64_t)W.sigma * 32;
     if (cell_bytes > MAX_CELL_BYTES)
         throw FormatError("alphabet x block count too large for the dense cell table (" + std::to_string(cell_bytes >> 20) + " MiB)");
+    if (blocks_total * (uint64_t)W.sigma >= 0xffffffffULL) throw FormatError("more than 2^32 (block, symbol) cells");
     F.cells.assign((size_t)(blocks_total * (uint64_t)W.sigma), Rec32{});
     F.sectors.assign((size_t)sectors_total + 1, Rec32{});
     F.nodes.assign((size_t)nodes_total + 1, Rec32{});
-    F.ovf.assign((size_t)ovf_total + 1, Rec32{});
+    F.occ.assign((size_t)occ_total + 1, Rec32{});
     F.blocks.assign((size_t)blocks_total + 1, Rec32{});
 
     // pass 2: fill
@@ -751,9 +785,7 @@ inline void flatten_rrr(const RrrStream& r, FlatIndex& F) {
     F.char2code.assign(65536, 0);
     F.code2char.assign(1, 0);
     F.sb.assign(1, fmgpu::SbDesc{0, 16});
-    F.sbroot.assign(1, fmgpu::U32x2{0, 1});
-    F.blkmap.assign(1, fmgpu::U32x2{0, 0});
-    for (auto* v : {&F.cells, &F.sectors, &F.ovf, &F.blocks, &F.nodes, &F.sa, &F.isa}) v->assign(1, Rec32{});
+    for (auto* v : {&F.cells, &F.sectors, &F.occ, &F.blocks, &F.nodes, &F.sa, &F.isa}) v->assign(1, Rec32{});
     flatten_sampled(r, F);
 }
 

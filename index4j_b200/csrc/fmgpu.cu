@@ -211,7 +211,7 @@ struct Replica {
     uint64_t layout_bytes[8] = {0};
     uint64_t total_bytes = 0;
     int sm_count = 0;
-    int count_ctas = 0, flat_ctas = 0, locate_ctas = 0, extract_ctas = 0, eub_ctas = 0;
+    int count_ctas = 0, locate_ctas = 0, extract_ctas = 0, eub_ctas = 0;
     size_t tables_smem = 0;
     static constexpr int NCTX = 4;  // concurrent batch calls per device
     std::mutex mu;
@@ -237,7 +237,6 @@ struct fmgpu_index {
     bool count_stats = false;  // fmgpu_set_stats: kernels with work counters
     bool use_kmer = true;      // fmgpu_set_start_table: patterns start from the q-gram start table when the index has one
     bool timing = false;
-    int count_kernel = 5;      // backward-search kernel: 5 = warp-lockstep (count_lane.h, the default), 6 = flat (lane per pattern with refill, count_flat.h)
     Replica* primary() const { return reps[0].get(); }
 };
 
@@ -408,39 +407,7 @@ int count_on_stream(fmgpu_index* ix, Replica* rp, CallCtx* cx, const uint16_t* d
     const DevIndex& D = rp->dev;
     const int pre_grid = prepass_grid(n_pat, rp->sm_count);
     const uint32_t kq = ix->use_kmer ? D.kmer_q : 0u;  // 0: every pattern starts from its last char
-    if (ix->count_kernel >= 6) {
-        // v6, flat: one 32-byte descriptor per pattern (s_pats), then lanes that run their patterns independently (count_flat.h)
-        CU(s_pats.reserve(((size_t)n_pat + 2) * sizeof(Rec32)));
-        const PatDesc* d_pd = nullptr;
-        if (u8) {  // UTF-8: decode first (chars + offset / length per pattern, kept in the order buffer)
-            CU(s_order.reserve(((size_t)n_pat + 2) * sizeof(PatDesc)));
-            k_prepass_utf8<<<pre_grid, 256, 0, pre>>>(u8->d_bytes, d_pat_off, n_pat, D.char2code, u8->d_chars, (PatDesc*)s_order.p,
-                                                     (uint32_t*)s_bins.p, u8->d_conv_status, u8->d_conv_value, 0u, D.kmer_stride, D.sigma);
-            d_pd = (const PatDesc*)s_order.p;
-            cx->last_launches += 1;
-        }
-        k_prep_flat<<<pre_grid, 256, 0, pre>>>(D, d_chars, d_pat_off, d_pd, n_pat, (Rec32*)s_pats.p, kq);
-        if (pre != st) {
-            CU(cudaEventRecord(pre_ev, pre));
-            CU(cudaStreamWaitEvent(st, pre_ev, 0));
-        }
-        const int slot = timing_slot(ix, rp, FMGPU_KERNEL_COUNT);
-        if (slot >= 0) CU(cudaEventRecord(rp->ev0[FMGPU_KERNEL_COUNT][slot], st));
-        int grid = rp->flat_ctas;
-        const int need = (int)(((uint64_t)n_pat + FLAT_THREADS - 1) / FLAT_THREADS);
-        if (need < grid) grid = need;
-        const uint64_t warps = (uint64_t)grid * (FLAT_THREADS / 32);
-        const uint32_t chunk = n_pat >= warps * 512 ? 128u : (n_pat >= warps * 128 ? 64u : 32u);
-        if (ix->count_stats)
-            k_count_flat<true><<<grid, FLAT_THREADS, rp->tables_smem, st>>>(D, d_chars, (const Rec32*)s_pats.p, n_pat, d_counts, d_status, d_ranges, chunk,
-                                                                              ctrl + CTRL_QUEUE, (unsigned long long*)(ctrl + CTRL_STATS));
-        else
-            k_count_flat<false><<<grid, FLAT_THREADS, rp->tables_smem, st>>>(D, d_chars, (const Rec32*)s_pats.p, n_pat, d_counts, d_status, d_ranges, chunk,
-                                                                               ctrl + CTRL_QUEUE, (unsigned long long*)(ctrl + CTRL_STATS));
-        if (slot >= 0) CU(cudaEventRecord(rp->ev1[FMGPU_KERNEL_COUNT][slot], st));
-        cx->last_launches += 2;
-    } else {
-    // v5, lockstep: descriptors + length histogram, then a counting sort by length so that a warp's 32 patterns run in lockstep
+    // descriptors + length histogram, then a counting sort by length so that a warp's 32 patterns run in lockstep
     if (u8)
         k_prepass_utf8<<<pre_grid, 256, 0, pre>>>(u8->d_bytes, d_pat_off, n_pat, D.char2code, u8->d_chars, (PatDesc*)s_pats.p,
                                                  (uint32_t*)s_bins.p, u8->d_conv_status, u8->d_conv_value, kq, D.kmer_stride, D.sigma);
@@ -469,7 +436,6 @@ int count_on_stream(fmgpu_index* ix, Replica* rp, CallCtx* cx, const uint16_t* d
                                                                  (unsigned long long*)(ctrl + CTRL_STATS));
     if (slot >= 0) CU(cudaEventRecord(rp->ev1[FMGPU_KERNEL_COUNT][slot], st));
     cx->last_launches += 4;
-    }
     if (u8) {  // a pattern whose conversion throws never reaches the search in the reference: its status wins
         k_utf8_merge<<<(n_pat + 255) / 256, 256, 0, st>>>(u8->d_conv_status, u8->d_conv_value, n_pat, d_counts, d_status, d_ranges ? 0 : 1);
         cx->last_launches += 1;
@@ -577,14 +543,6 @@ int replica_setup(Replica* rp) {
     if (!rc) rc = grid_for((const void*)k_count<true>, rp->sm_count, rp->tables_smem, &g1);
     if (rc) return rc;
     rp->count_ctas = g0 < g1 ? g0 : g1;
-    if (cudaFuncSetAttribute((const void*)k_count_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess ||
-        cudaFuncSetAttribute((const void*)k_count_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess)
-        return fail(FMGPU_ERR_CUDA, "k_count_flat: cannot reserve %zu bytes of shared memory", rp->tables_smem);
-    int f0 = 0, f1 = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f0, (const void*)k_count_flat<false>, FLAT_THREADS, rp->tables_smem));
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&f1, (const void*)k_count_flat<true>, FLAT_THREADS, rp->tables_smem));
-    if (f0 < 1 || f1 < 1) return fail(FMGPU_ERR_CUDA, "k_count_flat does not fit on an SM");
-    rp->flat_ctas = (f0 < f1 ? f0 : f1) * rp->sm_count;
     return lf_setup(rp);
 }
 
@@ -718,8 +676,6 @@ int load_common(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_in
     fmgpu_index* ix = new fmgpu_index();
     ix->kind = kind;
     ix->alphabet_length = F.alphabet_length;
-    if (const char* e = getenv("FMGPU_COUNT_KERNEL"))
-        if (atoi(e) == 5 || atoi(e) == 6) ix->count_kernel = atoi(e);
     ix->reps.emplace_back(new Replica());
     Replica* rp = ix->primary();
     rp->device = devices[0];
@@ -732,13 +688,11 @@ int load_common(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_in
     up(upload(rp, F.char2code, &rp->dev.char2code, -1));
     up(upload(rp, F.code2char, &rp->dev.code2char, -1));
     up(upload(rp, F.sb, &rp->dev.sb, -1));
-    up(upload(rp, F.sbroot, &rp->dev.sbroot, -1));
-    up(upload(rp, F.blkmap, &rp->dev.blkmap, -1));
     up(upload(rp, F.cells, &rp->dev.cells, 0));
     up(upload(rp, F.sectors, &rp->dev.sectors, 1));
     up(upload(rp, F.nodes, &rp->dev.nodes, 2));
     up(upload(rp, F.blocks, &rp->dev.blocks, 3));
-    up(upload(rp, F.ovf, &rp->dev.ovf, 4));
+    up(upload(rp, F.occ, &rp->dev.occ, 4));
     up(upload(rp, F.sgroups, &rp->dev.sgroups, 5));
     up(upload(rp, F.soffsets, &rp->dev.soffsets, 5));
     {
@@ -1019,12 +973,6 @@ int fmgpu_set_start_table(fmgpu_index* ix, int enable) {
     return 0;
 }
 int32_t fmgpu_start_table_q(const fmgpu_index* ix) { return ix ? (int32_t)ix->primary()->dev.kmer_q : -1; }
-
-int fmgpu_set_count_kernel(fmgpu_index* ix, int version) {
-    if (!ix || (version != 5 && version != 6)) return fail(FMGPU_ERR_ARG, "null handle / unknown kernel version (5 = lockstep, 6 = flat)");
-    ix->count_kernel = version;
-    return 0;
-}
 
 int fmgpu_set_stats(fmgpu_index* ix, int enable) {
     if (!ix) return fail(FMGPU_ERR_ARG, "null argument");

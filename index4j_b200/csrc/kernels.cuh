@@ -10,7 +10,6 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
-#include "count_flat.h"
 #include "count_lane.h"
 #include "lane_logic.h"
 #include "layout.h"
@@ -27,11 +26,8 @@ constexpr int PIPE_CTA_THREADS = COUNT_THREADS >= 128 ? COUNT_THREADS - 64 : COU
 constexpr uint32_t SMEM_C_MAX = 4096;   // entries of C kept in shared memory
 constexpr uint32_t SMEM_SB_MAX = 2048;  // superblock descriptors kept in shared memory
 
-// Index tables small enough for shared memory: C array, superblock descriptors and — with ROOTS — the root-record directory
-// (layout.h) that the speculative root fetches need.
-constexpr uint32_t SMEM_BLKMAP_MAX = 8192;  // blkmap entries (32 blocks each) kept in shared memory
-template <bool ROOTS>
-__device__ __forceinline__ SmemTables stage_tables_t(const DevIndex& ix, uint32_t* smem) {
+// Index tables small enough for shared memory: C array and superblock descriptors.
+__device__ __forceinline__ SmemTables stage_tables(const DevIndex& ix, uint32_t* smem) {
     SmemTables t;
     uint32_t used = 0;
     auto stage = [&](const uint32_t* src, uint32_t words, bool fits) -> const uint32_t* {
@@ -43,26 +39,16 @@ __device__ __forceinline__ SmemTables stage_tables_t(const DevIndex& ix, uint32_
     };
     t.C = stage(ix.C, ix.n_c, ix.n_c <= SMEM_C_MAX);
     t.sb = reinterpret_cast<const SbDesc*>(stage(reinterpret_cast<const uint32_t*>(ix.sb), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
-    t.sbroot = ix.sbroot;
-    t.blkmap = ix.blkmap;
-    if (ROOTS) {
-        t.sbroot = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.sbroot), 2 * ix.n_sb, ix.n_sb <= SMEM_SB_MAX));
-        t.blkmap = reinterpret_cast<const U32x2*>(stage(reinterpret_cast<const uint32_t*>(ix.blkmap), 2 * ix.n_blkmap, ix.n_blkmap <= SMEM_BLKMAP_MAX));
-    }
     __syncthreads();
     return t;
 }
-template <bool ROOTS>
-inline size_t tables_smem_bytes_t(const DevIndex& ix) {
+inline size_t tables_smem_bytes(const DevIndex& ix) {
     size_t n = 0;
     if (ix.n_c <= SMEM_C_MAX) n += (ix.n_c + 1u) & ~1u;
-    if (ix.n_sb <= SMEM_SB_MAX) n += (ROOTS ? 4 : 2) * (size_t)ix.n_sb;
-    if (ROOTS && ix.n_blkmap <= SMEM_BLKMAP_MAX) n += 2 * (size_t)ix.n_blkmap;
+    if (ix.n_sb <= SMEM_SB_MAX) n += 2 * (size_t)ix.n_sb;
     return n * 4 + 16;
 }
-constexpr size_t TABLES_SMEM_MAX_BYTES = (SMEM_C_MAX + 4 * (size_t)SMEM_SB_MAX + 2 * (size_t)SMEM_BLKMAP_MAX) * 4 + 16;
-__device__ __forceinline__ SmemTables stage_tables(const DevIndex& ix, uint32_t* smem) { return stage_tables_t<false>(ix, smem); }
-inline size_t tables_smem_bytes(const DevIndex& ix) { return tables_smem_bytes_t<false>(ix); }
+constexpr size_t TABLES_SMEM_MAX_BYTES = (SMEM_C_MAX + 2 * (size_t)SMEM_SB_MAX) * 4 + 16;
 
 // ---------------------------------------------------------------------------------------------
 // Pre-pass: one descriptor per pattern (offset, length, alphabet code of the last char =
@@ -164,9 +150,9 @@ __global__ void __launch_bounds__(256, 8) k_len_scatter(const PatDesc* __restric
 // than the lane state machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...); the price is that a step
 // lasts as long as its deepest walk.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ CountTables stage_count_tables(const DevIndex& ix, uint32_t* smem) { return stage_tables_t<COUNT_SPEC_ROOT != 0>(ix, smem); }
+__device__ __forceinline__ CountTables stage_count_tables(const DevIndex& ix, uint32_t* smem) { return stage_tables(ix, smem); }
 constexpr size_t COUNT_SMEM_MAX_BYTES = TABLES_SMEM_MAX_BYTES;
-inline size_t count_smem_bytes(const DevIndex& ix) { return tables_smem_bytes_t<COUNT_SPEC_ROOT != 0>(ix); }
+inline size_t count_smem_bytes(const DevIndex& ix) { return tables_smem_bytes(ix); }
 
 #ifndef COUNT_MIN_CTAS
 #define COUNT_MIN_CTAS 2
@@ -300,97 +286,6 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
         atomicAdd(stats + 6, (unsigned long long)cnt.loads);
         atomicAdd(stats + 7, (unsigned long long)cnt.recs);
         atomicAdd(stats + 8, (unsigned long long)cnt.spec_wasted);
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Backward search, v6: lane-per-pattern with refill (count_flat.h).  k_prep_flat writes one 32-byte descriptor per pattern (a
-// streaming, coalesced pass: offsets, the q-gram start-table lookup, the first two chars), k_count_flat's lanes take patterns
-// from a global queue (one atomic per warp chunk) and run them independently: every trip each lane fetches the one record its
-// own pattern needs next.  No length sort, no lockstep.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_prep_flat(const DevIndex ix, const uint16_t* __restrict__ chars, const uint64_t* __restrict__ pat_off,
-                                                   const PatDesc* __restrict__ pats, uint32_t n_pat, Rec32* __restrict__ descs, uint32_t kmer_q) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_pat; i += gridDim.x * blockDim.x) {
-        uint64_t a, b;
-        if (pats) {  // patterns decoded by the UTF-8 pre-pass: offset + length in chars
-            a = pats[i].off;
-            b = a + pats[i].len;
-        } else {
-            a = pat_off[i];
-            b = pat_off[i + 1];
-        }
-        descs[i] = flat_make_desc(ix, ix.C, chars, a, b, ix.char2code, kmer_q);
-    }
-}
-
-#ifndef FLAT_THREADS
-#define FLAT_THREADS 512
-#endif
-#ifndef FLAT_MIN_CTAS
-#define FLAT_MIN_CTAS 2
-#endif
-template <bool STATS>
-__global__ void __launch_bounds__(FLAT_THREADS, FLAT_MIN_CTAS)
-k_count_flat(const DevIndex ix, const uint16_t* __restrict__ chars, const Rec32* __restrict__ descs, uint32_t n_pat, int32_t* __restrict__ counts,
-             int32_t* __restrict__ status, uint32_t* __restrict__ ranges, uint32_t chunk, unsigned int* queue, unsigned long long* stats) {
-    extern __shared__ __align__(8) uint32_t smem[];
-    const SmemTables T = stage_tables(ix, smem);
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    CountCounters cnt;
-    cnt.ranks = cnt.levels = cnt.loads = cnt.recs = cnt.spec_wasted = 0;
-    FlatOut O;
-    O.counts = counts;
-    O.status = status;
-    O.ranges = ranges;
-    FlatLane L;
-    L.state = FS_IDLE;
-    L.err = 0;
-    uint32_t next = 0, end = 0;  // warp-uniform: the warp's chunk of the work queue
-    bool exhausted = false;
-    for (;;) {
-        const unsigned idle = __ballot_sync(FULL, L.state == FS_IDLE);
-        if (idle && !exhausted) {
-            if (next == end) {
-                unsigned base = 0;
-                if (lane == 0) base = atomicAdd(queue, chunk);
-                base = __shfl_sync(FULL, base, 0);
-                if (base >= n_pat) {
-                    exhausted = true;
-                } else {
-                    next = base;
-                    end = base + chunk < n_pat ? base + chunk : n_pat;
-                }
-            }
-            const uint32_t avail = end - next;
-            const uint32_t mine = __popc(idle & lt_mask);
-            if (L.state == FS_IDLE && mine < avail) {
-                L.pat = next + mine;
-                L.err = 0;
-                L.state = FS_DESC;
-            }
-            const uint32_t need = __popc(idle);
-            next += need < avail ? need : avail;
-        }
-        if (!__any_sync(FULL, L.state != FS_IDLE)) {
-            if (exhausted) break;
-            continue;
-        }
-        if (L.state != FS_IDLE) flat_trip<STATS>(ix, T, L, O, descs, chars, ix.char2code, cnt);
-    }
-    if (!STATS) return;
-    for (int o = 16; o; o >>= 1) {
-        cnt.ranks += __shfl_xor_sync(FULL, cnt.ranks, o);
-        cnt.levels += __shfl_xor_sync(FULL, cnt.levels, o);
-        cnt.loads += __shfl_xor_sync(FULL, cnt.loads, o);
-        cnt.recs += __shfl_xor_sync(FULL, cnt.recs, o);
-    }
-    if (lane == 0 && stats) {
-        atomicAdd(stats + 0, (unsigned long long)cnt.ranks);
-        atomicAdd(stats + 1, (unsigned long long)cnt.levels);
-        atomicAdd(stats + 6, (unsigned long long)cnt.loads);
-        atomicAdd(stats + 7, (unsigned long long)cnt.recs);
     }
 }
 

@@ -51,21 +51,42 @@ FMGPU_HD uint32_t low_mask_clamped(int width) {
 #endif
 }
 
-struct SmemTables {  // C array, superblock descriptors and the root-record directory (shared memory when they fit)
+struct SmemTables {  // C array and superblock descriptors (shared memory when they fit)
     const uint32_t* C;
     const SbDesc* sb;
-    const U32x2* sbroot;
-    const U32x2* blkmap;
 };
 
-// root level record of (superblock sbi, block blk) from the root-record directory (layout.h), or false when the block has
-// no tree (single-symbol block, or the extra row of position == size)
-FMGPU_HD bool root_record(const SmemTables& T, uint32_t sbi, uint32_t blk, uint32_t* rec) {
-    const U32x2 m = T.blkmap[blk >> 5];
-    const uint32_t bit = blk & 31u;
-    const U32x2 sr = T.sbroot[sbi];
-    *rec = sr.x + (m.y + popc32(m.x & ((1u << bit) - 1u))) * sr.y;
-    return ((m.x >> bit) & 1u) != 0u;
+// ------------------------------------------------------------------------------------------
+// occurrence structures of the (block, symbol) cells (layout.h): rank inside the block = occurrences among its first r positions
+// ------------------------------------------------------------------------------------------
+// how many of the n_words * 2 ascending u16 values packed in w[first ..] are < r (padding 0xffff never is: r <= 65535)
+FMGPU_HD uint32_t count_u16_below(const Rec32& x, int first, int n_words, uint32_t r) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (k >= first && k < first + n_words) n += ((x.w[k] & 0xffffu) < r ? 1u : 0u) + ((x.w[k] >> 16) < r ? 1u : 0u);
+    return n;
+}
+// Does the cell need a record for position r of its block?  If so *rec = its address and *part = what the cell alone already
+// knows (list records wholly below r).  If not, *part = the occurrences below r.
+FMGPU_HD bool occ_locate(const DevIndex& ix, const Rec32& cell, uint32_t kind, uint32_t r, const Rec32** rec, uint32_t* part) {
+    *part = 0u;
+    if (kind == CELL_OCC_LEVEL) {
+        *rec = ix.sectors + (cell.w[1] + r / SECTOR_BITS);
+        return true;
+    }
+    if (kind == CELL_OCC_BITS) {
+        *rec = ix.occ + (cell.w[1] + r / OCC_BITS_PER_REC);
+        return true;
+    }
+    const uint32_t below = count_u16_below(cell, 3, 5, r);  // inline positions / list splitters below r
+    if (kind == CELL_OCC_LIST) {
+        *rec = ix.occ + (cell.w[1] + below);
+        *part = below * OCC_LIST_PER_REC;
+        return true;
+    }
+    *part = below;
+    return false;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -95,6 +116,17 @@ FMGPU_HD uint32_t plane_bit(const Rec32& x, uint32_t plane, uint32_t b) {
 // record (b = r mod 96, r = position in the even-depth node), code bits t (this level) and u (next level; 0 when the code
 // ends at this level).  Returns the position in grandchild (t, u) — in child t when the code ends here.
 FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t b, uint32_t t, uint32_t u) { return dlevel_base(x, t, u) + dlevel_count(x, b, t, u); }
+
+// occurrences below r inside the record occ_locate pointed at (y), for the cell's kind
+FMGPU_HD uint32_t occ_in_record(const Rec32& cell, const Rec32& y, uint32_t kind, uint32_t r) {
+    if (kind == CELL_OCC_LIST) return count_u16_below(y, 0, 8, r);
+    if (kind == CELL_OCC_LEVEL) return dlevel_rank(y, r % SECTOR_BITS, cell.w[3] & 1u, (cell.w[3] >> 1) & 1u);
+    const uint32_t b = r % OCC_BITS_PER_REC;
+    uint32_t n = y.w[0];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) n += popc32(y.w[1 + k] & low_mask_clamped((int)b - 32 * k));
+    return n;
+}
 
 // The descent of WaveletFixedBlockBoosting.inverseSelect (:1386-1505) through the two levels of a record with the node
 // record N of the even-depth node.  Returns true at a leaf (*sym, *rank = rank(pos, sym) incl. the boundary rank);
@@ -142,7 +174,7 @@ FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t 
     if (ix.q4 && pos == ix.length) return 9u;
     const SbDesc sd = T.sb[pos >> SB_LOG];
     const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
-    uint32_t r = pos & ((1u << sd.block_log) - 1u);
+    const uint32_t r = pos & ((1u << sd.block_log) - 1u);
     const Rec32 cell = FMGPU_LD256(ix.cells + ((uint64_t)blk * ix.sigma + sym));
     ++*n_rank;
     const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
@@ -154,29 +186,16 @@ FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t 
         *out = cell.w[0] + r;
         return 0u;
     }
-    if (kind == CELL_THROW) return 9u;
-    const uint32_t code = cell.w[1];
-    const uint32_t L = cell.w[2] & 0xffu;
-    const uint32_t pairs = (L + 1u) >> 1;
-    const uint32_t inl = pairs > CELL_INLINE_PAIRS ? CELL_INLINE_PAIRS - 1u : pairs;
-    for (uint32_t k = 0; k < pairs; ++k) {
-        uint32_t node;
-        if (k < inl) {
-            node = rec_word(cell, 3u + k);
-        } else {
-            const uint32_t* more = reinterpret_cast<const uint32_t*>(ix.ovf + cell.w[7]);
-            node = FMGPU_LDG32(more + (k - inl));
-        }
-        const uint32_t d = 2u * k;
-        const bool two = d + 1u < L;
-        const Rec32 x = FMGPU_LD256(ix.sectors + (node + r / SECTOR_BITS));
-        const uint32_t t = (code >> (L - 1u - d)) & 1u;
-        const uint32_t u = two ? (code >> (L - 2u - d)) & 1u : 0u;
-        r = dlevel_rank(x, r % SECTOR_BITS, t, u);
+    if (kind == CELL_THROW || kind == CELL_NORMAL) return 9u;
+    *n_level += cell.w[2] & 0xffu;
+    const Rec32* rec = nullptr;
+    uint32_t part = 0;
+    if (occ_locate(ix, cell, kind, r, &rec, &part)) {
+        const Rec32 y = FMGPU_LD256(rec);
+        ++*n_rec;
+        part += occ_in_record(cell, y, kind, r);
     }
-    *n_level += L;
-    *n_rec += pairs;
-    *out = cell.w[0] + r;
+    *out = cell.w[0] + part;
     return 0u;
 }
 

@@ -16,16 +16,34 @@ struct alignas(32) Rec32 {
     uint32_t w[8];
 };
 
-// --- (block, symbol) cell: everything WaveletFixedBlockBoosting.rank(pos, sym) reads besides the
-// level bits, flattened (wavelet/WaveletFixedBlockBoosting.java:1022-1184).
-//   w0 value : hyper+super+block boundary rank (NORMAL/RUN) or the complete answer (CONST)
-//   w1 code  : canonical Huffman code of sym in this block, MSB = root decision
-//   w2       : codeLen (bits 0-7) | kind (bits 8-15)
-//   w3..w7   : first record of the even-depth node visited at depth 0, 2, 4, 6, 8 (one record resolves two levels);
-//              when codeLen > 10, w3..w6 hold depth 0..6 and w7 is an index into the overflow array (chunks of 8
-//              record indices, depth 8, 10, ..)
-enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3 };
-constexpr uint32_t CELL_INLINE_PAIRS = 5;
+// --- (block, symbol) cell: WaveletFixedBlockBoosting.rank(pos, sym) for every position of the block, flattened
+// (wavelet/WaveletFixedBlockBoosting.java:1022-1285).
+//   w0 value : hyper+super+block boundary rank (RUN / OCC_*) or the complete answer (CONST)
+//   w2       : code length of sym in the block's tree (bits 0-7: what the reference's level walk costs, kept for the work
+//              counters) | kind (bits 8-15)
+//   kinds    : CONST   the symbol does not occur in the block (or the superblock): the answer is w0, whatever the position
+//              RUN     single-symbol block: w0 + position in block (:1141-1146)
+//              THROW   the reference indexes out of its arrays
+//              OCC_*   the symbol occurs in the block: the reference walks the block's Huffman-shaped wavelet tree along the
+//                      symbol's code (:1185-1279), one RRR rank per level, which counts the occurrences of the symbol among the
+//                      first r positions of the block.  That count is stored directly, per (block, symbol), in one of three
+//                      forms — so a rank is the cell plus AT MOST ONE further record, whatever the code length:
+//              OCC_LEVEL   code length 1 or 2 (the block's most frequent symbols): w1 = first level record of the block's root
+//                          node in `sectors` (below), w3 = the code's two bits t | u << 1 — the root's level record of the
+//                          position resolves both levels, so these symbols need no structure of their own
+//              OCC_INLINE  <= 10 occurrences: their positions (u16, ascending, padded 0xffff) in w3..w7
+//              OCC_LIST    <= 176 occurrences: w1 = first record of a sorted position list in `occ` (16 u16 per record, padded
+//                          0xffff), w3..w7 = 10 splitters (splitter j = first position of list record j + 1)
+//              OCC_BITS    w1 = first record of a bit vector over the block's positions in `occ`: record q covers positions
+//                          [224 q, 224 q + 224): w0 = occurrences before the record, w1..w7 = 224 bits
+// (Rounds 1-2 kept the wavelet levels on this path too: one level record per two tree levels, up to three dependent records per
+// rank, and a warp of 64 rank tracks in lockstep ran 2.9 record trips per step for 1.15 needed per track.  The level records
+// remain what inverseSelect walks — the LF kernels — where the symbol is not known in advance.)
+enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3, CELL_OCC_INLINE = 4, CELL_OCC_LIST = 5, CELL_OCC_BITS = 6, CELL_OCC_LEVEL = 7 };
+constexpr uint32_t OCC_INLINE_MAX = 10;      // positions that fit w3..w7 of the cell
+constexpr uint32_t OCC_LIST_PER_REC = 16;    // u16 positions per list record
+constexpr uint32_t OCC_LIST_MAX = 176;       // (10 splitters + 1) list records
+constexpr uint32_t OCC_BITS_PER_REC = 224;   // positions per bit-vector record
 
 // --- level record (32 bytes): TWO tree levels of 96 positions.  Only the wavelet-tree nodes at EVEN depth own records;
 // record q of a node covers its positions [96q, 96q + 96):
@@ -65,14 +83,6 @@ struct U32x2 {
     uint32_t x, y;
 };
 
-// --- root-record directory (speculative root fetch of the backward search, count_lane.h).  The level records of the
-// ROOT nodes of a superblock's tree blocks are stored first in the superblock's record range, `root_stride` records per
-// block (every block of a superblock has 2^block_log positions, so every root has the same number of records), in block
-// order, single-symbol blocks skipped.  The root record of (block, position r) is therefore computable without touching
-// memory:  sbroot[sb].x + G(block) * sbroot[sb].y + r / 96,  G(block) = number of tree blocks before `block` (global),
-// from blkmap[block / 32] = {bit k set <=> block 32w + k has a tree, tree blocks before block 32w}.
-// sbroot[sb].x is stored pre-biased by -G(first block of sb) * stride (wrapping 32-bit arithmetic).
-
 struct PatDesc {  // one per pattern, written by the pre-pass
     uint64_t off;     // offset of the pattern's first char in the concatenated code array
     uint32_t len;
@@ -93,7 +103,7 @@ struct DevIndex {
     uint32_t n_isa;        // entries of positions (ISA samples)
     uint32_t n_sa;
     uint32_t s_total_ones;
-    uint32_t n_blkmap;     // entries of blkmap
+    uint32_t reserved0;
     // q-gram start table of the backward search (0 = none): for every q-gram of alphabet codes the SA range after its q chars,
     // i.e. the state of FmIndex.count after q - 1 steps, computed at load by the search kernel itself.  Entry of the q-gram
     // whose LAST char has code a, the one before b, ... : index ((a * stride + b) * stride + ...); {0xffffffff, .} = not usable
@@ -102,14 +112,12 @@ struct DevIndex {
     uint32_t kmer_stride;
     const U32x2* kmer;
     const uint32_t* C;
-    const U32x2* sbroot;        // [n_sb + 1] root-record directory (see above)
-    const U32x2* blkmap;        // [n_blkmap]
     const uint16_t* char2code;  // [65536], 0 = not in alphabet (monotonicMap.getOrDefault(c, 0))
     const uint16_t* code2char;  // monotonicLookUp
     const SbDesc* sb;
     const Rec32* cells;    // [n_blocks_total][sigma]
-    const Rec32* sectors;  // level records (two Rec32 each)
-    const Rec32* ovf;      // chunks of 8 sector indices
+    const Rec32* sectors;  // level records of the even-depth wavelet nodes (inverseSelect)
+    const Rec32* occ;      // occurrence records of the (block, symbol) pairs (position lists / bit vectors)
     const Rec32* blocks;   // block descriptors
     const Rec32* nodes;    // node records of the even-depth nodes
     const Rec32* sgroups;

@@ -117,7 +117,6 @@ def native():
         L.fmgpu_set_timing.argtypes = [vp, i32]
         L.fmgpu_set_stats.argtypes = [vp, i32]
         L.fmgpu_set_start_table.argtypes = [vp, i32]
-        L.fmgpu_set_count_kernel.argtypes = [vp, i32]
         L.fmgpu_start_table_q.argtypes = [vp]
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         L.fmgpu_kernel_ms.argtypes = [vp, i32, u32, u32, C.POINTER(C.c_float)]
@@ -243,7 +242,7 @@ class FmIndex:
     def layout_bytes(self) -> dict:
         out = np.zeros(8, dtype=np.uint64)
         self._lib.fmgpu_layout_bytes(self._h, out.ctypes.data)
-        names = ["cells", "level_sectors", "node_records", "block_descriptors", "path_overflow", "sampled_rows", "sa_samples", "isa_samples"]
+        names = ["cells", "level_sectors", "node_records", "block_descriptors", "occurrence_records", "sampled_rows", "sa_samples", "isa_samples"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def last_stats(self) -> dict:
@@ -260,10 +259,6 @@ class FmIndex:
     def set_start_table(self, enable: bool = True):
         """Use (default) / bypass the q-gram start table of the backward search; results are identical either way."""
         self._check(self._lib.fmgpu_set_start_table(self._h, int(enable)))
-
-    def set_count_kernel(self, version: int):
-        """5 = warp-lockstep backward-search kernel (default), 6 = flat kernel (lane per pattern with refill); identical results."""
-        self._check(self._lib.fmgpu_set_count_kernel(self._h, int(version)))
 
     def start_table_q(self) -> int:
         return int(self._lib.fmgpu_start_table_q(self._h))

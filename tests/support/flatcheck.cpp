@@ -10,7 +10,6 @@
 #include "../../index4j_b200/csrc/flatten.hpp"
 #include "../../index4j_b200/csrc/jstream.hpp"
 #include "../../index4j_b200/csrc/count_lane.h"
-#include "../../index4j_b200/csrc/count_flat.h"
 #include "../../index4j_b200/csrc/lf_lane.h"
 #include "../../index4j_b200/csrc/utf8_lane.h"
 
@@ -73,23 +72,17 @@ int fc_load(const uint8_t* buf, uint64_t len, int threads, void** out) {
         h->ix.sb = h->F.sb.data();
         h->ix.cells = h->F.cells.data();
         h->ix.sectors = h->F.sectors.data();
-        h->ix.ovf = h->F.ovf.data();
+        h->ix.occ = h->F.occ.data();
         h->ix.blocks = h->F.blocks.data();
         h->ix.nodes = h->F.nodes.data();
         h->ix.sgroups = h->F.sgroups.data();
         h->ix.soffsets = h->F.soffsets.data();
         h->ix.sa = h->F.sa.data();
         h->ix.isa = h->F.isa.data();
-        h->ix.sbroot = h->F.sbroot.data();
-        h->ix.blkmap = h->F.blkmap.data();
         h->T.C = h->ix.C;
         h->T.sb = h->ix.sb;
-        h->T.sbroot = h->ix.sbroot;
-        h->T.blkmap = h->ix.blkmap;
         h->CT.C = h->ix.C;
         h->CT.sb = h->ix.sb;
-        h->CT.sbroot = h->ix.sbroot;
-        h->CT.blkmap = h->ix.blkmap;
         fill_binom(h->binom);
         *out = h;
         return 0;
@@ -106,7 +99,7 @@ void fc_sizes(void* hv, uint64_t* out8) {
     out8[1] = h->F.sectors.size() * 32;
     out8[2] = h->F.nodes.size() * 32;
     out8[3] = h->F.blocks.size() * 32;
-    out8[4] = h->F.ovf.size() * 32;
+    out8[4] = h->F.occ.size() * 32;
     out8[5] = h->F.sgroups.size() * 32 + h->F.soffsets.size() * 4;
     out8[6] = h->F.sa.size() * 32;
     out8[7] = h->F.isa.size() * 32;
@@ -223,38 +216,6 @@ void fc_count_batch_table(void* hv, const uint16_t* chars, const uint64_t* pat_o
     count_batch_impl(*(FC*)hv, chars, pat_off, n_pat, counts, status, ranges, counters, true);
 }
 
-// The flat kernel's lane code (count_flat.h), one lane at a time: descriptor, then trips until the lane is idle again.
-// use_table: with the q-gram start table (fc_build_start_table first).  counters as fc_count_batch; counters[2] += trips.
-void fc_count_batch_flat(void* hv, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
-                         uint32_t* ranges, uint64_t* counters, int32_t use_table) {
-    FC& h = *(FC*)hv;
-    std::vector<Rec32> descs(n_pat);
-    const uint32_t kq = use_table ? h.ix.kmer_q : 0u;
-    for (uint32_t p = 0; p < n_pat; ++p) descs[p] = flat_make_desc(h.ix, h.ix.C, chars, pat_off[p], pat_off[p + 1], h.ix.char2code, kq);
-    FlatOut O;
-    O.counts = counts;
-    O.status = status;
-    O.ranges = ranges;
-    CountCounters cnt{0, 0, 0, 0, 0};
-    uint64_t trips = 0;
-    for (uint32_t p = 0; p < n_pat; ++p) {
-        FlatLane L{};
-        L.pat = p;
-        L.state = FS_DESC;
-        while (L.state != FS_IDLE) {
-            flat_trip<true>(h.ix, h.CT, L, O, descs.data(), chars, h.ix.char2code, cnt);
-            ++trips;
-        }
-    }
-    if (counters) {
-        counters[0] += cnt.ranks;
-        counters[1] += cnt.levels;
-        counters[2] += trips;
-        counters[6] += cnt.loads;
-        counters[7] += cnt.recs;
-    }
-}
-
 // Host twin of build_start_table (fmgpu.cu): for every q-gram of codes the chars can spell, the (sp, ep) the step-by-step search
 // reports for it as a pattern; q-grams that end in an error are left unusable.  Returns the number of usable entries.
 uint64_t fc_build_start_table(void* hv, uint32_t q) {
@@ -288,29 +249,6 @@ uint64_t fc_build_start_table(void* hv, uint32_t q) {
     h.ix.kmer_q = q;
     h.ix.kmer_stride = (uint32_t)S;
     return usable;
-}
-
-// every NORMAL cell's first record must be the root record the directory computes (speculative root fetch); returns the
-// number of violations
-uint64_t fc_check_roots(void* hv) {
-    FC& h = *(FC*)hv;
-    uint64_t bad = 0;
-    for (uint32_t sb = 0; sb < h.ix.n_sb; ++sb) {
-        const uint32_t lo = h.ix.sb[sb].first_block;
-        const uint32_t hi = sb + 1 < h.ix.n_sb ? h.ix.sb[sb + 1].first_block : (uint32_t)(h.F.blocks.size() - 1);
-        for (uint32_t blk = lo; blk < hi; ++blk) {
-            uint32_t root = 0;
-            const bool tree = root_record(h.CT, sb, blk, &root);
-            const bool run = (h.F.blocks[blk].w[1] & 1u) != 0u;
-            if (tree && h.F.blocks[blk].w[0] != root) ++bad;
-            for (uint32_t sym = 0; sym < h.ix.sigma; ++sym) {
-                const Rec32& cell = h.F.cells[(size_t)blk * h.ix.sigma + sym];
-                if (((cell.w[2] >> 8) & 0xffu) != CELL_NORMAL) continue;
-                if (!tree || run || cell.w[3] != root || (cell.w[2] & 0xffu) == 0u) ++bad;
-            }
-        }
-    }
-    return bad;
 }
 
 void fc_extract(void* hv, const int32_t* start, const int32_t* stop, uint32_t n, uint16_t* arena, const uint64_t* arena_off,

@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "flatcheck.cpp")] + [
-        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "lf_lane.h", "ldrec.h", "layout.h", "count_lane.h", "count_flat.h", "utf8_lane.h")
+        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "lf_lane.h", "ldrec.h", "layout.h", "count_lane.h", "utf8_lane.h")
     ]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
@@ -36,10 +36,7 @@ def lib():
         L.fc_rank.argtypes = [vp, u32, u32, C.POINTER(C.c_int64)]
         L.fc_count_batch.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
         L.fc_inverse_select.argtypes = [vp, C.c_int64, C.POINTER(C.c_int64)]
-        L.fc_check_roots.argtypes = [vp]
-        L.fc_check_roots.restype = C.c_uint64
         L.fc_count_batch_table.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp]
-        L.fc_count_batch_flat.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, i32]
         L.fc_build_start_table.argtypes = [vp, u32]
         L.fc_build_start_table.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
@@ -95,9 +92,6 @@ class FlatIndexHost:
         st = lib().fc_inverse_select(self._h, int(pos), C.byref(out))
         return st, int(out.value)
 
-    def check_roots(self) -> int:
-        return int(lib().fc_check_roots(self._h))
-
     def build_start_table(self, q: int) -> int:
         return int(lib().fc_build_start_table(self._h, q))
 
@@ -111,18 +105,6 @@ class FlatIndexHost:
         ranges = np.zeros(2 * n, dtype=np.uint32)
         lib().fc_count_batch_table(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data,
                                    ranges.ctypes.data, self.counters.ctypes.data)
-        return counts, status, ranges.reshape(n, 2)
-
-    def count_batch_flat(self, chars, pat_off, use_table=False):
-        """the flat kernel's lane code (count_flat.h): descriptor + trips, one lane at a time"""
-        chars = np.ascontiguousarray(chars, dtype=np.uint16)
-        pat_off = np.ascontiguousarray(pat_off, dtype=np.uint64)
-        n = pat_off.size - 1
-        counts = np.zeros(n, dtype=np.int32)
-        status = np.zeros(n, dtype=np.int32)
-        ranges = np.zeros(2 * n, dtype=np.uint32)
-        lib().fc_count_batch_flat(self._h, chars.ctypes.data, pat_off.ctypes.data, n, counts.ctypes.data, status.ctypes.data,
-                                  ranges.ctypes.data, self.counters.ctypes.data, int(use_table))
         return counts, status, ranges.reshape(n, 2)
 
     def locate_rows(self, rows):
