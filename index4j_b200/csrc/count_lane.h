@@ -28,7 +28,8 @@ namespace fmgpu {
 using CountTables = SmemTables;  // C, superblock descriptors
 
 struct CountCounters {
-    uint32_t ranks, levels, loads, recs, spec_wasted;
+    uint32_t ranks, levels, loads, recs;
+    uint32_t kinds[8];  // rank tracks by cell kind (CellKind)
 };
 
 // --- q-gram start table (layout.h) ---------------------------------------------------------------------------------
@@ -97,6 +98,8 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
         cnt.loads += (need_b ? 1u : 0u) + (need_a && !shared ? 1u : 0u);
         cnt.recs += (need_b ? 1u : 0u) + (need_a ? 1u : 0u);
         cnt.levels += (kind_b >= CELL_OCC_INLINE ? cell_b.w[2] & 0xffu : 0u) + (kind_a >= CELL_OCC_INLINE ? cell_a.w[2] & 0xffu : 0u);
+        ++cnt.kinds[kind_b & 7u];
+        if (on_a) ++cnt.kinds[kind_a & 7u];
     }
     if (need_b) part_b += occ_in_record(cell_b, yb, kind_b, rb);
     if (need_a) part_a += occ_in_record(cell_a, shared ? yb : ya, kind_a, ra);

@@ -258,7 +258,7 @@ inline void build_block_tree(const SuperBlockHdr& S, size_t b, uint32_t cur_bloc
         if (len > 32) throw FormatError("Huffman code longer than 32 bits");
         L.len = (uint8_t)len;
         L.code = code;  // bit (len-1) = root decision
-        if (len > 2) T.n_occ += occ_records(T.occ[(size_t)i], cur_block_size);  // codes of 1-2 bits use the root's level records
+        T.n_occ += occ_records(T.occ[(size_t)i], cur_block_size);
     }
     // level records of the even-depth nodes (inverseSelect walks them, lf_lane.h)
     for (size_t id = 0; id < T.nodes.size(); ++id) {
@@ -571,16 +571,9 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                         cell.w[2] = (uint32_t)L.len;  // code length: what the reference's walk costs (work counters)
                         const std::vector<uint16_t>& pos = leaf_pos[(size_t)b][(size_t)bc];
                         const uint32_t bsize = sb_block_size(W, sb, (size_t)b);
-                        const uint32_t need = L.len > 2 ? occ_records((uint32_t)pos.size(), bsize) : 0u;
+                        const uint32_t need = occ_records((uint32_t)pos.size(), bsize);
                         const uint32_t at = occ_next[(size_t)b];
-                        if (L.len <= 2) {
-                            // the root's level record of the position resolves a code of one or two bits (u = 0 for one bit)
-                            cell.w[2] |= fmgpu::CELL_OCC_LEVEL << 8;
-                            cell.w[1] = T.nodes[0].sector;
-                            const uint32_t t = (L.code >> (L.len - 1)) & 1u;
-                            const uint32_t u = L.len == 2 ? (L.code & 1u) : 0u;
-                            cell.w[3] = t | (u << 1);
-                        } else if ((uint64_t)at + need > block_occ_base[(size_t)b] + T.n_occ) {
+                        if ((uint64_t)at + need > block_occ_base[(size_t)b] + T.n_occ) {
                             // two alphabet symbols mapped to the same leaf (a corrupt header): the block's occurrence records are
                             // sized for one structure per leaf
                             put_cell(cell, fmgpu::CELL_THROW, 0);

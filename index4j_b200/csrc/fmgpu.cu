@@ -88,7 +88,7 @@ struct Scratch {
     }
 };
 
-enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x 9 at word 2.. */, CTRL_WORDS = 32 };
+enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x FMGPU_N_STATS at word 2.. */, CTRL_WORDS = 64 };
 
 enum { KIND_FM = 0, KIND_WAVELET = 1, KIND_RRR = 2 };
 

@@ -170,7 +170,8 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
     const CountTables T = stage_count_tables(ix, smem);
     const unsigned lane = threadIdx.x & 31u;
     CountCounters cnt;
-    cnt.ranks = cnt.levels = cnt.loads = cnt.recs = cnt.spec_wasted = 0;
+    cnt.ranks = cnt.levels = cnt.loads = cnt.recs = 0;
+    for (int k = 0; k < 8; ++k) cnt.kinds[k] = 0;
 
     // Work distribution: the first batch of every warp is static — CTA b takes the contiguous batches [b*W, (b+1)*W) of the
     // length-ordered batch, so the warps of a CTA run patterns of (nearly) the same length and the CTA retires as a whole
@@ -278,14 +279,14 @@ k_count(const DevIndex ix, const uint16_t* __restrict__ chars, const PatDesc* __
         cnt.levels += __shfl_xor_sync(FULL, cnt.levels, o);
         cnt.loads += __shfl_xor_sync(FULL, cnt.loads, o);
         cnt.recs += __shfl_xor_sync(FULL, cnt.recs, o);
-        cnt.spec_wasted += __shfl_xor_sync(FULL, cnt.spec_wasted, o);
+        for (int k = 0; k < 8; ++k) cnt.kinds[k] += __shfl_xor_sync(FULL, cnt.kinds[k], o);
     }
     if (lane == 0 && stats) {
         atomicAdd(stats + 0, (unsigned long long)cnt.ranks);
         atomicAdd(stats + 1, (unsigned long long)cnt.levels);
         atomicAdd(stats + 6, (unsigned long long)cnt.loads);
         atomicAdd(stats + 7, (unsigned long long)cnt.recs);
-        atomicAdd(stats + 8, (unsigned long long)cnt.spec_wasted);
+        for (int k = 0; k < 8; ++k) atomicAdd(stats + 8 + k, (unsigned long long)cnt.kinds[k]);
     }
 }
 

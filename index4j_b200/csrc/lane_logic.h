@@ -71,10 +71,6 @@ FMGPU_HD uint32_t count_u16_below(const Rec32& x, int first, int n_words, uint32
 // knows (list records wholly below r).  If not, *part = the occurrences below r.
 FMGPU_HD bool occ_locate(const DevIndex& ix, const Rec32& cell, uint32_t kind, uint32_t r, const Rec32** rec, uint32_t* part) {
     *part = 0u;
-    if (kind == CELL_OCC_LEVEL) {
-        *rec = ix.sectors + (cell.w[1] + r / SECTOR_BITS);
-        return true;
-    }
     if (kind == CELL_OCC_BITS) {
         *rec = ix.occ + (cell.w[1] + r / OCC_BITS_PER_REC);
         return true;
@@ -120,7 +116,6 @@ FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t b, uint32_t t, uint32_t u
 // occurrences below r inside the record occ_locate pointed at (y), for the cell's kind
 FMGPU_HD uint32_t occ_in_record(const Rec32& cell, const Rec32& y, uint32_t kind, uint32_t r) {
     if (kind == CELL_OCC_LIST) return count_u16_below(y, 0, 8, r);
-    if (kind == CELL_OCC_LEVEL) return dlevel_rank(y, r % SECTOR_BITS, cell.w[3] & 1u, (cell.w[3] >> 1) & 1u);
     const uint32_t b = r % OCC_BITS_PER_REC;
     uint32_t n = y.w[0];
 #pragma unroll

@@ -28,9 +28,6 @@ struct alignas(32) Rec32 {
 //                      symbol's code (:1185-1279), one RRR rank per level, which counts the occurrences of the symbol among the
 //                      first r positions of the block.  That count is stored directly, per (block, symbol), in one of three
 //                      forms — so a rank is the cell plus AT MOST ONE further record, whatever the code length:
-//              OCC_LEVEL   code length 1 or 2 (the block's most frequent symbols): w1 = first level record of the block's root
-//                          node in `sectors` (below), w3 = the code's two bits t | u << 1 — the root's level record of the
-//                          position resolves both levels, so these symbols need no structure of their own
 //              OCC_INLINE  <= 10 occurrences: their positions (u16, ascending, padded 0xffff) in w3..w7
 //              OCC_LIST    <= 176 occurrences: w1 = first record of a sorted position list in `occ` (16 u16 per record, padded
 //                          0xffff), w3..w7 = 10 splitters (splitter j = first position of list record j + 1)
@@ -38,8 +35,11 @@ struct alignas(32) Rec32 {
 //                          [224 q, 224 q + 224): w0 = occurrences before the record, w1..w7 = 224 bits
 // (Rounds 1-2 kept the wavelet levels on this path too: one level record per two tree levels, up to three dependent records per
 // rank, and a warp of 64 rank tracks in lockstep ran 2.9 record trips per step for 1.15 needed per track.  The level records
-// remain what inverseSelect walks — the LF kernels — where the symbol is not known in advance.)
-enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3, CELL_OCC_INLINE = 4, CELL_OCC_LIST = 5, CELL_OCC_BITS = 6, CELL_OCC_LEVEL = 7 };
+// remain what inverseSelect walks — the LF kernels — where the symbol is not known in advance.  Measured on the configs[1]
+// batch, 39 % of the rank queries end in a bit vector, 26 % in what could be served by the root's level record (codes of 1-2
+// bits; giving those their own bit vectors costs 9 % more occurrence records and removes a third code path from the kernel),
+// 32 % in RUN cells, 2.5 % in CONST cells, < 1 % in position lists.)
+enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3, CELL_OCC_INLINE = 4, CELL_OCC_LIST = 5, CELL_OCC_BITS = 6 };
 constexpr uint32_t OCC_INLINE_MAX = 10;      // positions that fit w3..w7 of the cell
 constexpr uint32_t OCC_LIST_PER_REC = 16;    // u16 positions per list record
 constexpr uint32_t OCC_LIST_MAX = 176;       // (10 splitters + 1) list records

@@ -178,8 +178,8 @@ static void count_one(FC& h, const uint16_t* pat, int64_t len, bool use_table, C
 
 static void count_batch_impl(FC& h, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat, int32_t* counts, int32_t* status,
                              uint32_t* ranges, uint64_t* counters, bool use_table) {
-    CountCounters cnt{0, 0, 0, 0, 0};
-    uint64_t n_rank = 0, n_level = 0, n_rec = 0, n_load = 0, n_waste = 0;
+    CountCounters cnt{};
+    uint64_t n_rank = 0, n_level = 0, n_rec = 0, n_load = 0, kinds[8] = {0};
     for (uint32_t p = 0; p < n_pat; ++p) {
         int32_t result = 0, st = 0;
         uint32_t sp = 0, ep = 0;
@@ -194,13 +194,13 @@ static void count_batch_impl(FC& h, const uint16_t* chars, const uint64_t* pat_o
         n_level += cnt.levels;
         n_rec += cnt.recs;
         n_load += cnt.loads;
-        n_waste += cnt.spec_wasted;
-        cnt = CountCounters{0, 0, 0, 0, 0};
+        for (int k = 0; k < 8; ++k) kinds[k] += cnt.kinds[k];
+        cnt = CountCounters{};
     }
     if (counters) {
         counters[0] += n_rank;
         counters[1] += n_level;
-        counters[5] += n_waste;
+        for (int k = 0; k < 8; ++k) counters[8 + k] += kinds[k];
         counters[6] += n_load;
         counters[7] += n_rec;
     }
@@ -226,7 +226,7 @@ uint64_t fc_build_start_table(void* hv, uint32_t q) {
     h.kmer.assign((size_t)n_entries, U32x2{0xffffffffu, 0u});
     h.ix.kmer_q = 0;
     std::vector<uint16_t> pat(q);
-    CountCounters cnt{0, 0, 0, 0, 0};
+    CountCounters cnt{};
     uint64_t usable = 0;
     for (uint64_t idx = 0; idx < n_entries; ++idx) {
         uint64_t v = idx;

@@ -59,7 +59,7 @@ class FlatIndexHost:
         rc = lib().fc_load(buf.ctypes.data, buf.size, threads, C.byref(self._h))
         if rc:
             raise IOError(lib().fc_last_error().decode())
-        self.counters = np.zeros(8, dtype=np.uint64)
+        self.counters = np.zeros(16, dtype=np.uint64)
 
     def __del__(self):
         if getattr(self, "_h", None):
