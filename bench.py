@@ -458,6 +458,15 @@ def main():
         from index4j_b200 import workloads
         loc, d_hit_off, d_pos = workloads.locate_workload(ix, d_chars, d_off, args.max_hits, args.lf_steps, 1)
         total_hits = loc["hits"]
+        # the same call with the walks ending at the serialized index's OWN samples (the device-side dense samples switched off):
+        # identical positions, (sampleRate - 1) / 2 LF steps per hit instead of (dense rate - 1) / 2
+        loc_own = None
+        if ix.dense_sample_bytes():
+            ix.set_locate_dense(False)
+            loc_own, _, d_pos_own = workloads.locate_workload(ix, d_chars, d_off, args.max_hits, args.lf_steps, 1)
+            ix.set_locate_dense(True)
+            assert torch.equal(d_pos_own, d_pos), "dense samples changed the located positions"
+            del d_pos_own
         n_eub = min(args.n_eub, total_hits)
         sel = torch.linspace(0, max(total_hits - 1, 0), max(n_eub, 1), device=dev, dtype=torch.float64).to(torch.int64)
         d_from = d_pos[sel].contiguous()
@@ -486,7 +495,7 @@ def main():
             ix.locate_batch_into(h_chars, h_off, args.max_hits, p_nh, p_ho, p_pos, h_status)
         loc_e2e_s = (time.perf_counter() - t0) / args.lf_steps
         assert int(p_ho[-1]) == total_hits and np.array_equal(p_pos[:4096], d_pos[:4096].cpu().numpy())
-        lf = {"rec": rec, "rec_first": rec_first, "loc": loc, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
+        lf = {"rec": rec, "rec_first": rec_first, "loc": loc, "loc_own": loc_own, "eub": eub, "loc_e2e_ms": loc_e2e_s * 1e3, "d_from": d_from, "d_arena": d_arena, "d_len": d_len, "d_st": d_st,
               "d_hit_off": d_hit_off, "d_pos": d_pos, "h2d": int(chars.nbytes + off.nbytes), "d2h": int(p_nh.nbytes + p_ho.nbytes + p_pos.nbytes + h_status.nbytes)}
 
     # BASELINE.json configs[2]: locate (max 1000 hits per pattern) over sampleRate 16 / 32 / 64 — LF-walk length against index
@@ -497,18 +506,26 @@ def main():
         sw_off = d_off[: ns + 1].contiguous()
         sw_chars = d_chars[: int(off[ns])].contiguous()
         ix.set_timing(False)
-        base_leg, _, _ = workloads.locate_workload_nostats(ix, sw_chars, sw_off, args.max_hits, args.lf_steps, 1)
-        sweep[args.sample_rate] = dict(base_leg, hbm_bytes=ix.device_bytes(), serialized_bytes=len(blob))
+        def sweep_leg(ix_x, blob_len):
+            # own samples (what the sweep is about: LF-walk length against index size), then with the device-side dense samples
+            ix_x.set_locate_dense(False)
+            own, _, _ = workloads.locate_workload_nostats(ix_x, sw_chars, sw_off, args.max_hits, args.lf_steps, 1)
+            ix_x.set_locate_dense(True)
+            d = dict(own, hbm_bytes=ix_x.device_bytes() - ix_x.dense_sample_bytes(), serialized_bytes=blob_len, dense_ms_per_step=0.0)
+            if ix_x.dense_sample_bytes():
+                den, _, _ = workloads.locate_workload_nostats(ix_x, sw_chars, sw_off, args.max_hits, args.lf_steps, 1)
+                d.update(dense_ms_per_step=den["ms_per_step"], dense_rate=ix_x.locate_sample_rate, dense_bytes=ix_x.dense_sample_bytes())
+            return d
+        sweep[args.sample_rate] = sweep_leg(ix, len(blob))
         for sr in sweep_rates:
             blob_sr = get_index_blob(args.n_text, sr, holder)
             ix_sr = FmIndex.read(blob_sr, device=local)
-            leg, _, _ = workloads.locate_workload_nostats(ix_sr, sw_chars, sw_off, args.max_hits, args.lf_steps, 1)
-            sweep[sr] = dict(leg, hbm_bytes=ix_sr.device_bytes(), serialized_bytes=len(blob_sr))
+            sweep[sr] = sweep_leg(ix_sr, len(blob_sr))
             ix_sr.close()
             del blob_sr
             torch.cuda.empty_cache()
         ix.set_timing(True)
-        sw_t = torch.tensor([[sweep[sr]["ms_per_step"], 0.0] for sr in sorted(sweep)], dtype=torch.float64, device=dev)
+        sw_t = torch.tensor([[sweep[sr]["ms_per_step"], sweep[sr]["dense_ms_per_step"]] for sr in sorted(sweep)], dtype=torch.float64, device=dev)
         sw_h = torch.tensor([[float(sweep[sr]["hits"]), float(sweep[sr]["lf_steps_est"])] for sr in sorted(sweep)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(sw_t, op=dist.ReduceOp.MAX)
@@ -517,6 +534,7 @@ def main():
             sweep[sr]["ms_per_step_max_over_ranks"] = float(sw_t[k, 0])
             sweep[sr]["hits_all_ranks"] = float(sw_h[k, 0])
             sweep[sr]["hits_per_s"] = float(sw_h[k, 0]) / (float(sw_t[k, 0]) / 1e3)
+            sweep[sr]["dense_hits_per_s"] = float(sw_h[k, 0]) / (float(sw_t[k, 1]) / 1e3) if float(sw_t[k, 1]) > 0 else None
 
     # strong scaling (BASELINE.json configs[1] as written: the ONE 1 M-pattern batch sharded over the GPUs).  (a) device-resident:
     # rank r searches slice r of rank 0's batch, time = max over ranks; (b) one process: rank 0 alone drives all N GPUs through
@@ -621,7 +639,8 @@ def main():
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3),
                          "occurrence_records_per_launch": stats["level_records"]},
             "index": {"hbm_bytes": ix.device_bytes(), "layout_bytes": ix.layout_bytes(), "serialized_bytes": len(blob),
-                      "start_table_q": ix.start_table_q()},
+                      "start_table_q": ix.start_table_q(), "sample_rate": ix.sample_rate, "locate_sample_rate": ix.locate_sample_rate,
+                      "dense_sample_bytes": ix.dense_sample_bytes()},
         }
         if lf:
             out["locate"] = {"metric": "located hits/sec (max %d hits per pattern)" % args.max_hits, "value": all_hits / (loc_ms / 1e3),
@@ -629,7 +648,16 @@ def main():
                              "lf_steps_per_s": all_lf_steps / (loc_ms / 1e3),
                              "e2e": {"value": all_hits / (loc_e2e_ms / 1e3), "unit": "hits/s", "h2d_bytes_per_step": lf["h2d"],
                                      "d2h_bytes_per_step": lf["d2h"]},
-                             "alg_gb_per_s_rank0": lf["loc"]["alg_gb_per_s"], "launches_per_step": lf["loc"]["launches"]}
+                             "alg_gb_per_s_rank0": lf["loc"]["alg_gb_per_s"], "launches_per_step": lf["loc"]["launches"],
+                             "walks_end_at": "samples every %d text positions (device-side dense samples, %d bytes of HBM; the serialized index samples every %d)"
+                                             % (ix.locate_sample_rate, ix.dense_sample_bytes(), ix.sample_rate) if ix.dense_sample_bytes()
+                                             else "the index's own samples (every %d text positions)" % ix.sample_rate}
+            if lf["loc_own"]:
+                lo = lf["loc_own"]
+                out["locate"]["own_samples_rank0"] = {
+                    "what": "the same call with the dense samples switched off: walks end at the serialized index's own samples (identical positions)",
+                    "hits_per_s": lo["hits_per_s"], "ms_per_step": lo["ms_per_step"], "kernel_ms": lo["kernel_ms"], "lf_steps": lo["lf_steps"],
+                    "roofline_frac": lo["kernel_alg_bytes"] / (lo["kernel_ms"] / 1e3) / 1e9 / peak}
             out["extract_until_boundary"] = {"metric": "records/sec (extractUntilBoundary('\\n'), dst %d chars, of located hits)" % args.dst_len,
                                              "value": all_records / (eub_ms / 1e3), "unit": "records/s", "chars_per_s": all_chars / (eub_ms / 1e3),
                                              "ms_per_step": eub_ms, "records_per_step": all_records, "launches_per_step": lf["eub"]["launches"]}
@@ -681,7 +709,11 @@ def main():
                             % (args.max_hits, min(args.sweep_patterns, n_pat), world),
                 "by_sample_rate": {str(sr): {"hits_per_s": sweep[sr]["hits_per_s"], "ms_per_step": sweep[sr]["ms_per_step_max_over_ranks"],
                                              "hits_per_step": sweep[sr]["hits_all_ranks"], "index_hbm_bytes": sweep[sr]["hbm_bytes"],
-                                             "serialized_bytes": sweep[sr]["serialized_bytes"]} for sr in sorted(sweep)}}
+                                             "serialized_bytes": sweep[sr]["serialized_bytes"],
+                                             "with_dense_samples": ({"hits_per_s": sweep[sr]["dense_hits_per_s"], "rate": sweep[sr].get("dense_rate"),
+                                                                     "extra_hbm_bytes": sweep[sr].get("dense_bytes")}
+                                                                    if sweep[sr]["dense_hits_per_s"] else None)} for sr in sorted(sweep)},
+                "note": "hits_per_s / index_hbm_bytes: walks end at the serialized index's own samples (dense samples off); with_dense_samples: the library's default"}
         if strong:
             out["strong"] = {
                 "workload": "the ONE batch of %d patterns sharded over %d GPUs (BASELINE.json configs[1] as written)" % (n_pat, world),

@@ -64,7 +64,8 @@ typedef struct fmgpu_opts {
     int32_t device;         /* CUDA device ordinal (used when n_devices == 0); -1 = current device */
     int32_t host_threads;   /* threads used to re-lay the index out at load; 0 = all cores */
     int32_t n_devices;      /* > 0: replicate the index on devices[0 .. n_devices); < 0: on every visible device; 0: `device` alone */
-    int32_t reserved0;
+    int32_t locate_sample_rate; /* device-side denser sampling of the SA rows for locate (fmgpu_set_locate_dense): > 0 requested rate,
+                                 * 0 = default (FMGPU_LOCATE_SAMPLE_RATE in the environment, else 8), < 0 = none */
     const int32_t* devices; /* device ordinals, distinct */
     uint64_t reserved[1];
 } fmgpu_opts;
@@ -121,6 +122,20 @@ int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const ui
  * building it, FMGPU_START_TABLE_LOG2=n caps it at 2^n entries.  fmgpu_start_table_q: q, 0 = no table. */
 int fmgpu_set_start_table(fmgpu_index* idx, int enable);
 int32_t fmgpu_start_table_q(const fmgpu_index* idx);
+
+/* Denser SA sampling on the device.  FmIndex keeps suffixes[] for the rows whose suffix starts at a multiple of sampleRate
+ * (FM:343-357) and locate() LF-walks every hit to the nearest such row (FM:531-537): (sampleRate - 1) / 2 steps per hit, the
+ * size / speed trade of the serialized index.  HBM makes a different trade affordable: at load the LF kernels walk the text once
+ * (2 x length LF steps, ~0.1 s per 2^30 chars) and also record the rows of every multiple of a smaller rate d (the largest
+ * divisor of sampleRate <= fmgpu_opts.locate_sample_rate), as a plain mark vector with rank counters + their positions
+ * (length / 7 + 4 * length / d bytes).  Walks then end after (d - 1) / 2 steps.  Positions, their order and statuses are
+ * unchanged (position = sampled position + distance walked, whichever sample ends the walk); on indexes where an LF step of
+ * the reference can throw or cycle (length % 2^20 == 0; more than 256 symbols) no dense samples are built, so the reference's
+ * full walk and its exception are what run.  fmgpu_set_locate_dense(idx, 0) makes locate use the index's own samples
+ * (A/B measurements, tests); fmgpu_locate_sample_rate = the rate in effect (sampleRate when none were built). */
+int fmgpu_set_locate_dense(fmgpu_index* idx, int enable);
+int32_t fmgpu_locate_sample_rate(const fmgpu_index* idx);
+uint64_t fmgpu_dense_sample_bytes(const fmgpu_index* idx); /* HBM held by the dense marks + positions (part of fmgpu_device_bytes) */
 
 /* UTF-8 byte patterns: FmIndex.convertBytePatternToCharPattern(byte[] p, 0, p.length, dst) FM:239-298 followed by
  * count(dst, 0, n) / locate(dst, 0, n, ...).  Pattern i is the byte[] bytes[pat_off[i], pat_off[i+1]) — pat_off are BYTE

@@ -5,9 +5,8 @@
 //
 // Track B carries `end`, track A carries `start` (off when start == 0, rank(0, .) == 0, :1012).  Per step a lane issues
 //   1. the (block, symbol) cell of each track (one load when both positions lie in the same block), then
-//   2. AT MOST ONE occurrence record per track (layout.h: a sorted position list or a bit vector of the symbol's
-//      occurrences in the block; one load when both tracks need the same record; none for CONST / RUN cells and for symbols
-//      with <= 10 occurrences, whose positions sit in the cell).
+//   2. AT MOST ONE occurrence record per track (layout.h: a short sorted position list or a bit vector of the symbol's
+//      occurrences in the block; one load when both tracks need the same record; none for CONST / RUN cells).
 // All loads of a stage are issued before any is used.  A step is therefore two dependent memory round trips whatever the
 // code lengths of the symbols are — rounds 1-2 walked the wavelet levels here (one record per two tree levels), and a warp
 // ran to the deepest of its 64 tracks: 2.9 record trips per step for 1.15 needed per track.
@@ -74,39 +73,39 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
     if (STATS) cnt.ranks += on_a ? 2u : 1u;
 
     // stage 0: the cells
-    const Rec32 cell_b = FMGPU_LD256(ix.cells + ((uint64_t)blk_b * ix.sigma + c));
-    Rec32 cell_a = cell_b;
-    if (split) cell_a = FMGPU_LD256(ix.cells + ((uint64_t)blk_a * ix.sigma + c));
+    const Cell8 cell_b = FMGPU_LDCELL(ix.cells + ((uint64_t)blk_b * ix.sigma + c));
+    Cell8 cell_a = cell_b;
+    if (split) cell_a = FMGPU_LDCELL(ix.cells + ((uint64_t)blk_a * ix.sigma + c));
     if (STATS) cnt.loads += split ? 2u : 1u;
-    const uint32_t kind_b = (cell_b.w[2] >> 8) & 0xffu;
-    const uint32_t kind_a = on_a ? (cell_a.w[2] >> 8) & 0xffu : (uint32_t)CELL_CONST;
-    uint32_t err = (kind_b == CELL_THROW || kind_b == CELL_NORMAL || kind_a == CELL_THROW || kind_a == CELL_NORMAL) ? 1u : 0u;
+    const uint32_t kind_b = cell_kind(cell_b);
+    const uint32_t kind_a = on_a ? cell_kind(cell_a) : (uint32_t)CELL_CONST;
+    const bool need_b = kind_b == CELL_OCC_LIST || kind_b == CELL_OCC_BITS;
+    const bool need_a = kind_a == CELL_OCC_LIST || kind_a == CELL_OCC_BITS;
+    const uint32_t err = ((!need_b && kind_b != CELL_CONST && kind_b != CELL_RUN) || (!need_a && kind_a != CELL_CONST && kind_a != CELL_RUN)) ? 1u : 0u;
 
-    // stage 1: at most one occurrence record per track
-    const Rec32 *rec_b = nullptr, *rec_a = nullptr;
-    uint32_t part_b = 0, part_a = 0;
-    bool need_b = false, need_a = false;
-    if (kind_b >= CELL_OCC_INLINE) need_b = occ_locate(ix, cell_b, kind_b, rb, &rec_b, &part_b);
-    else if (kind_b == CELL_RUN) part_b = rb;  // boundary rank + position inside the single-symbol block (:1141-1146)
-    if (kind_a >= CELL_OCC_INLINE) need_a = occ_locate(ix, cell_a, kind_a, ra, &rec_a, &part_a);
-    else if (kind_a == CELL_RUN) part_a = ra;
+    // stage 1: one occurrence record per track that needs one
+    const Rec32* rec_b = need_b ? occ_record(ix, cell_b, kind_b, rb) : nullptr;
+    const Rec32* rec_a = need_a ? occ_record(ix, cell_a, kind_a, ra) : nullptr;
+    uint32_t part_b = kind_b == CELL_RUN ? rb : 0u;  // boundary rank + position inside the single-symbol block (:1141-1146)
+    uint32_t part_a = kind_a == CELL_RUN ? ra : 0u;
     const bool shared = need_a && need_b && rec_a == rec_b;
     Rec32 yb FMGPU_UNSET, ya FMGPU_UNSET;  // never interpreted unless loaded
-    if (need_b) yb = FMGPU_LD256(rec_b);
-    if (need_a && !shared) ya = FMGPU_LD256(rec_a);
+    if (need_b) yb = FMGPU_LD256_OCC(rec_b);
+    if (need_a && !shared) ya = FMGPU_LD256_OCC(rec_a);
+    uint32_t len_b = 0, len_a = 0;
+    if (need_b) part_b = occ_in_record(yb, kind_b, rb, &len_b);
+    if (need_a) part_a = occ_in_record(shared ? yb : ya, kind_a, ra, &len_a);
     if (STATS) {
         cnt.loads += (need_b ? 1u : 0u) + (need_a && !shared ? 1u : 0u);
         cnt.recs += (need_b ? 1u : 0u) + (need_a ? 1u : 0u);
-        cnt.levels += (kind_b >= CELL_OCC_INLINE ? cell_b.w[2] & 0xffu : 0u) + (kind_a >= CELL_OCC_INLINE ? cell_a.w[2] & 0xffu : 0u);
+        cnt.levels += len_b + len_a;
         ++cnt.kinds[kind_b & 7u];
         if (on_a) ++cnt.kinds[kind_a & 7u];
     }
-    if (need_b) part_b += occ_in_record(cell_b, yb, kind_b, rb);
-    if (need_a) part_a += occ_in_record(cell_a, shared ? yb : ya, kind_a, ra);
 
     // a rank never exceeds the number of positions; the clamp only matters for a corrupt (but loadable) index, whose
     // boundary ranks could otherwise send the next step outside the directories
-    const uint32_t va = cell_a.w[0] + part_a, vb = cell_b.w[0] + part_b;
+    const uint32_t va = cell_a.value + part_a, vb = cell_b.value + part_b;
     *sp = on_a ? (va < ix.length ? va : ix.length) : 0u;
     *ep = vb < ix.length ? vb : ix.length;
     return err;

@@ -91,7 +91,8 @@ struct FlatIndex {
     std::vector<uint32_t> C;
     std::vector<uint16_t> char2code, code2char;
     std::vector<fmgpu::SbDesc> sb;
-    std::vector<Rec32> cells, sectors, occ, blocks, nodes, sgroups, sa, isa;
+    std::vector<fmgpu::Cell8> cells;
+    std::vector<Rec32> sectors, occ, blocks, nodes, sgroups, sa, isa;
     std::vector<uint32_t> soffsets;
     int32_t alphabet_length = 0;
 };
@@ -141,18 +142,10 @@ struct VarReader {
 };
 
 // occurrence records a (block, symbol) pair with `occ` occurrences in a block of `block_size` positions needs (layout.h):
-// none when its positions fit the cell, a sorted position list while that is the smaller form, else one bit per position
-inline uint32_t occ_kind(uint32_t occ, uint32_t block_size) {
-    if (occ <= fmgpu::OCC_INLINE_MAX) return fmgpu::CELL_OCC_INLINE;
-    const uint32_t list = (occ + fmgpu::OCC_LIST_PER_REC - 1) / fmgpu::OCC_LIST_PER_REC;
-    const uint32_t bits = block_size / fmgpu::OCC_BITS_PER_REC + 1;
-    return (occ <= fmgpu::OCC_LIST_MAX && list <= bits) ? fmgpu::CELL_OCC_LIST : fmgpu::CELL_OCC_BITS;
-}
+// one list record while its positions fit one, else one bit per position
+inline uint32_t occ_kind(uint32_t occ, uint32_t) { return occ <= fmgpu::OCC_LIST_MAX ? fmgpu::CELL_OCC_LIST : fmgpu::CELL_OCC_BITS; }
 inline uint32_t occ_records(uint32_t occ, uint32_t block_size) {
-    const uint32_t k = occ_kind(occ, block_size);
-    if (k == fmgpu::CELL_OCC_INLINE) return 0;
-    if (k == fmgpu::CELL_OCC_LIST) return (occ + fmgpu::OCC_LIST_PER_REC - 1) / fmgpu::OCC_LIST_PER_REC;
-    return block_size / fmgpu::OCC_BITS_PER_REC + 1;
+    return occ_kind(occ, block_size) == fmgpu::CELL_OCC_LIST ? 1u : block_size / fmgpu::OCC_BITS_PER_REC + 1;
 }
 
 // `sigma`: the wavelet alphabet size — header symbols must lie below it (the kernels index C[] and the rank directories with them)
@@ -308,41 +301,25 @@ inline void parallel_sbs(size_t n, int threads, F&& f) {
     if (failed.load()) throw FormatError(err);
 }
 
-inline void put_cell(Rec32& c, uint32_t kind, uint32_t value) {
-    memset(&c, 0, sizeof c);
-    c.w[0] = value;
-    c.w[2] = kind << 8;
+inline void put_cell(fmgpu::Cell8& c, uint32_t kind, uint32_t value) {
+    c.value = value;
+    c.info = kind << fmgpu::CELL_KIND_SHIFT;
 }
 
-// occurrence structure of one (block, symbol) pair: positions (ascending, block-relative) of the symbol's occurrences
-// -> the cell words w1, w3..w7 and its records in F.occ[at ..] (layout.h)
-inline void put_occ(Rec32& cell, const std::vector<uint16_t>& pos, uint32_t block_size, uint32_t at, std::vector<Rec32>& occ) {
+// occurrence structure of one (block, symbol) pair: positions (ascending, block-relative) of the symbol's occurrences, its
+// code length in the block's tree -> the cell's kind / record pointer and its records in F.occ[at ..] (layout.h)
+inline void put_occ(fmgpu::Cell8& cell, const std::vector<uint16_t>& pos, uint32_t code_len, uint32_t block_size, uint32_t at,
+                    std::vector<Rec32>& occ) {
     const uint32_t n = (uint32_t)pos.size();
     const uint32_t kind = occ_kind(n, block_size);
-    cell.w[2] = (cell.w[2] & 0xffu) | (kind << 8);
-    auto put16 = [](Rec32& r, uint32_t first_word, uint32_t k, uint16_t v) {  // k-th u16 slot from word `first_word`
-        uint32_t& w = r.w[first_word + (k >> 1)];
-        w = (k & 1u) ? ((w & 0x0000ffffu) | ((uint32_t)v << 16)) : ((w & 0xffff0000u) | v);
-    };
-    if (kind == fmgpu::CELL_OCC_INLINE) {
-        cell.w[1] = n;
-        for (uint32_t k = 0; k < fmgpu::OCC_INLINE_MAX; ++k) put16(cell, 3, k, k < n ? pos[k] : 0xffffu);
-        return;
-    }
-    cell.w[1] = at;
+    if (at > fmgpu::CELL_PTR_MASK) throw FormatError("more occurrence records than a cell can address");
+    cell.info = (kind << fmgpu::CELL_KIND_SHIFT) | at;
     if (kind == fmgpu::CELL_OCC_LIST) {
-        const uint32_t nrec = (n + fmgpu::OCC_LIST_PER_REC - 1) / fmgpu::OCC_LIST_PER_REC;
-        for (uint32_t q = 0; q < nrec; ++q) {
-            Rec32& R = occ[(size_t)at + q];
-            for (uint32_t k = 0; k < fmgpu::OCC_LIST_PER_REC; ++k) {
-                const uint32_t i = q * fmgpu::OCC_LIST_PER_REC + k;
-                put16(R, 0, k, i < n ? pos[i] : 0xffffu);
-            }
-        }
-        // splitter j = first position of record j + 1
-        for (uint32_t j = 0; j < fmgpu::OCC_INLINE_MAX; ++j) {
-            const uint32_t i = (j + 1) * fmgpu::OCC_LIST_PER_REC;
-            put16(cell, 3, j, i < n ? pos[i] : 0xffffu);
+        Rec32& R = occ[(size_t)at];
+        for (uint32_t k = 0; k < 16; ++k) {
+            const uint32_t v = k < fmgpu::OCC_LIST_MAX ? (k < n ? pos[k] : 0xffffu) : (code_len & 0xffffu);
+            uint32_t& w = R.w[k >> 1];
+            w = (k & 1u) ? ((w & 0x0000ffffu) | (v << 16)) : ((w & 0xffff0000u) | v);
         }
         return;
     }
@@ -351,7 +328,7 @@ inline void put_occ(Rec32& cell, const std::vector<uint16_t>& pos, uint32_t bloc
     for (uint32_t q = 0; q < nrec; ++q) {
         Rec32& R = occ[(size_t)at + q];
         memset(&R, 0, sizeof R);
-        R.w[0] = (uint32_t)i;  // occurrences before the record
+        R.w[0] = (uint32_t)i | ((code_len & 0xffu) << 24);  // occurrences before the record (<= 65536)
         const uint32_t lo = q * fmgpu::OCC_BITS_PER_REC, hi = lo + fmgpu::OCC_BITS_PER_REC;
         while (i < n && pos[i] < hi) {
             const uint32_t bit = pos[i] - lo;
@@ -504,7 +481,7 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         const int64_t sb_c = W.global_mapping[sb * (size_t)sigma + (size_t)sym];
         const uint64_t rank_sb = (uint64_t)(int64_t)W.sb_rank[sb * (size_t)sigma + (size_t)sym];
         const uint64_t rank_hb = (uint64_t)W.hyper_rank[(size_t)sym];
-        auto cell_at = [&](size_t row) -> Rec32& { return F.cells[((size_t)P.first_block + row) * (size_t)sigma + (size_t)sym]; };
+        auto cell_at = [&](size_t row) -> fmgpu::Cell8& { return F.cells[((size_t)P.first_block + row) * (size_t)sigma + (size_t)sym]; };
         if (sb_c >= sb_sigma) {  // :1040 symbol absent from the superblock
             for (size_t row = 0; row < P.rows; ++row) put_cell(cell_at(row), fmgpu::CELL_CONST, (uint32_t)(rank_hb + rank_sb));
             continue;
@@ -521,7 +498,7 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
             const int32_t block_c = in_range ? (int32_t)S.mapping[(size_t)mi] : 0;
             const bool absent = in_range && block_c == sigma - 1;
             if ((size_t)b < P.rows) {
-                Rec32& cell = cell_at((size_t)b);
+                fmgpu::Cell8& cell = cell_at((size_t)b);
                 if (!in_range) {
                     put_cell(cell, fmgpu::CELL_THROW, 0);
                 } else if (absent) {
@@ -566,9 +543,7 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                         // the level walk of :1185-1279 along the leaf's code counts the elements among the first r positions
                         // of the block that reach the leaf: stored as the leaf's occurrence structure (layout.h)
                         const BlockTree::Leaf& L = T.leaves[(size_t)bc];
-                        memset(&cell, 0, sizeof cell);
-                        cell.w[0] = (uint32_t)(rank_hb + rank_sb + rank_blk);
-                        cell.w[2] = (uint32_t)L.len;  // code length: what the reference's walk costs (work counters)
+                        put_cell(cell, fmgpu::CELL_THROW, (uint32_t)(rank_hb + rank_sb + rank_blk));  // kind set by put_occ
                         const std::vector<uint16_t>& pos = leaf_pos[(size_t)b][(size_t)bc];
                         const uint32_t bsize = sb_block_size(W, sb, (size_t)b);
                         const uint32_t need = occ_records((uint32_t)pos.size(), bsize);
@@ -579,7 +554,7 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                             put_cell(cell, fmgpu::CELL_THROW, 0);
                         } else {
                             occ_next[(size_t)b] += need;
-                            put_occ(cell, pos, bsize, at, F.occ);
+                            put_occ(cell, pos, (uint32_t)L.len, bsize, at, F.occ);
                         }
                     }
                 }
@@ -599,11 +574,11 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
             D.w[3] = fmgpu::CELL_CONST;
             continue;
         }
-        const Rec32& cell = F.cells[((size_t)P.first_block + b) * (size_t)sigma + c];
-        const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
+        const fmgpu::Cell8& cell = F.cells[((size_t)P.first_block + b) * (size_t)sigma + c];
+        const uint32_t kind = cell.info >> fmgpu::CELL_KIND_SHIFT;
         if (kind != fmgpu::CELL_CONST && kind != fmgpu::CELL_RUN && kind != fmgpu::CELL_THROW)
             throw FormatError("single-symbol block with a tree walk");
-        D.w[2] = cell.w[0];
+        D.w[2] = cell.value;
         D.w[3] = kind;
     }
 }
@@ -733,11 +708,11 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
     }
     if (sectors_total >= 0xffffffffULL || nodes_total >= 0x7fffffffULL || occ_total >= 0xffffffffULL || blocks_total >= 0xffffffffULL)
         throw FormatError("index too large for 32-bit record indices");
-    const uint64_t cell_bytes = blocks_total * (uint64_t)W.sigma * 32;
+    const uint64_t cell_bytes = blocks_total * (uint64_t)W.sigma * sizeof(fmgpu::Cell8);
     if (cell_bytes > MAX_CELL_BYTES)
         throw FormatError("alphabet x block count too large for the dense cell table (" + std::to_string(cell_bytes >> 20) + " MiB)");
     if (blocks_total * (uint64_t)W.sigma >= 0xffffffffULL) throw FormatError("more than 2^32 (block, symbol) cells");
-    F.cells.assign((size_t)(blocks_total * (uint64_t)W.sigma), Rec32{});
+    F.cells.assign((size_t)(blocks_total * (uint64_t)W.sigma), fmgpu::Cell8{0u, (uint32_t)fmgpu::CELL_THROW << fmgpu::CELL_KIND_SHIFT});
     F.sectors.assign((size_t)sectors_total + 1, Rec32{});
     F.nodes.assign((size_t)nodes_total + 1, Rec32{});
     F.occ.assign((size_t)occ_total + 1, Rec32{});
@@ -778,7 +753,8 @@ inline void flatten_rrr(const RrrStream& r, FlatIndex& F) {
     F.char2code.assign(65536, 0);
     F.code2char.assign(1, 0);
     F.sb.assign(1, fmgpu::SbDesc{0, 16});
-    for (auto* v : {&F.cells, &F.sectors, &F.occ, &F.blocks, &F.nodes, &F.sa, &F.isa}) v->assign(1, Rec32{});
+    F.cells.assign(1, fmgpu::Cell8{0u, 0u});
+    for (auto* v : {&F.sectors, &F.occ, &F.blocks, &F.nodes, &F.sa, &F.isa}) v->assign(1, Rec32{});
     flatten_sampled(r, F);
 }
 

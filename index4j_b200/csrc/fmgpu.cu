@@ -33,6 +33,7 @@
 #include "kernels_utf8.cuh"
 #include "kernels_wavelet.cuh"
 #include "kernels_build.cuh"
+#include "kernels_dense.cuh"
 #include "layout.h"
 
 using namespace fmgpu;
@@ -211,7 +212,8 @@ struct Replica {
     uint64_t layout_bytes[8] = {0};
     uint64_t total_bytes = 0;
     int sm_count = 0;
-    int count_ctas = 0, locate_ctas = 0, extract_ctas = 0, eub_ctas = 0;
+    int count_ctas = 0, locate_ctas = 0, locate_dense_ctas = 0, extract_ctas = 0, eub_ctas = 0;
+    uint64_t dense_bytes = 0;  // dense marks + dsa (also counted in total_bytes)
     size_t tables_smem = 0;
     static constexpr int NCTX = 4;  // concurrent batch calls per device
     std::mutex mu;
@@ -236,6 +238,7 @@ struct fmgpu_index {
     std::mutex multi_mu;                            // one multi-device call at a time drives the workers
     bool count_stats = false;  // fmgpu_set_stats: kernels with work counters
     bool use_kmer = true;      // fmgpu_set_start_table: patterns start from the q-gram start table when the index has one
+    bool use_dense = true;     // fmgpu_set_locate_dense: locate walks end at the device-side dense samples when the index has them
     bool timing = false;
     Replica* primary() const { return reps[0].get(); }
 };
@@ -526,6 +529,104 @@ int build_start_table(fmgpu_index* ix, const std::vector<uint16_t>& code2char, c
     return 0;
 }
 
+// a device array made on the device itself joins the replica's layout (cloned to the other devices like the uploaded ones)
+template <typename T>
+void adopt(Replica* rp, const T* p, size_t bytes, const T** dptr, int layout_slot) {
+    rp->allocs.push_back((void*)p);
+    *dptr = p;
+    rp->total_bytes += bytes;
+    if (layout_slot >= 0) rp->layout_bytes[layout_slot] += bytes;
+    rp->arrays.push_back({(size_t)((const char*)dptr - (const char*)&rp->dev), bytes, layout_slot});
+}
+
+constexpr int LOCATE_SAMPLE_RATE_DEFAULT = 8;
+
+// Device-side denser sampling of the SA rows (layout.h, kernels_dense.cuh).  `want` = fmgpu_opts.locate_sample_rate: > 0 the
+// requested rate, 0 = FMGPU_LOCATE_SAMPLE_RATE or the default, < 0 = none.  The effective rate is the largest divisor of the
+// index's sampleRate that is <= the request (none if that is the sampleRate itself).  Skipped where a shorter walk could
+// differ from the reference's: an index on which LF steps can throw (length % 2^20 == 0, quirk Q4) or run in cycles (more than
+// 256 symbols, quirk Q1) — there the reference's full walk reports the exception, so the full walk is what runs.  Also skipped
+// (silently: it is an accelerator, not a result) when the device has too little free memory.
+int build_dense_samples(fmgpu_index* ix, int want) {
+    Replica* rp = ix->primary();
+    const DevIndex& D = rp->dev;
+    if (want == 0) {
+        want = LOCATE_SAMPLE_RATE_DEFAULT;
+        if (const char* e = getenv("FMGPU_LOCATE_SAMPLE_RATE")) want = atoi(e);
+    }
+    if (want <= 0 || D.sample_rate < 2 || D.q4 || D.sigma > 256 || D.n_sa == 0 || D.length < 2) return 0;
+    uint32_t rate = 0;
+    for (uint32_t d = 1; d <= (uint32_t)want && d < D.sample_rate; ++d)
+        if (D.sample_rate % d == 0) rate = d;
+    if (rate == 0) return 0;
+    const uint32_t n_rec = (D.length + DENSE_ROWS_PER_REC - 1) / DENSE_ROWS_PER_REC;
+    const uint32_t n_dense = (D.length - 1u) / rate + 1u;  // text positions 0 .. length - 1 that are multiples of rate
+    const size_t mark_bytes = (size_t)n_rec * 32, dsa_bytes = (size_t)n_dense * 4, seed_bytes = ((size_t)dense_seed_count(D) + 1) * 4;
+    const uint32_t n_blocks = (n_rec + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    const size_t scan_bytes = (size_t)n_rec * 4 + ((size_t)n_rec + 1) * 8 + ((size_t)n_blocks + 2) * 8;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return fail(FMGPU_ERR_CUDA, "cudaMemGetInfo failed");
+    if ((mark_bytes + dsa_bytes) * 2 + seed_bytes + scan_bytes > free_b) return 0;
+    Lease L(rp);
+    if (L.rc) return L.rc;
+    cudaStream_t st = L.c->stream;
+    Rec32* marks = nullptr;
+    uint32_t *dsa = nullptr, *seeds = nullptr;
+    unsigned int* flag = nullptr;
+    char* scan = nullptr;
+    auto drop = [&] {
+        for (void* p : {(void*)marks, (void*)dsa, (void*)seeds, (void*)flag, (void*)scan})
+            if (p) cudaFree(p);
+    };
+    auto check = [&](cudaError_t e) {
+        if (e == cudaSuccess) return 0;
+        drop();
+        return fail(FMGPU_ERR_CUDA, "dense samples: %s", cudaGetErrorString(e));
+    };
+    int rc = 0;
+    if ((rc = check(cudaMalloc((void**)&marks, mark_bytes))) || (rc = check(cudaMalloc((void**)&dsa, dsa_bytes))) ||
+        (rc = check(cudaMalloc((void**)&seeds, seed_bytes))) || (rc = check(cudaMalloc((void**)&flag, 4))) ||
+        (rc = check(cudaMalloc((void**)&scan, scan_bytes))))
+        return rc;
+    int32_t* ones = (int32_t*)scan;
+    uint64_t* before = (uint64_t*)(scan + (((size_t)n_rec * 4 + 7) & ~(size_t)7));
+    uint64_t* sums = before + n_rec + 1;
+    cudaMemsetAsync(marks, 0, mark_bytes, st);
+    cudaMemsetAsync(dsa, 0, dsa_bytes, st);
+    cudaMemsetAsync(seeds, 0xff, seed_bytes, st);
+    cudaMemsetAsync(flag, 0, 4, st);
+    const int grid = rp->sm_count * 2;
+    const size_t tsmem = tables_smem_bytes(D);
+    const uint32_t n_seeds = dense_seed_count(D);
+    k_dense_seeds<<<grid, DENSE_THREADS, LOCATE_TAB_WORDS * 4, st>>>(D, seeds, n_seeds);
+    k_dense_walk<0><<<grid, DENSE_THREADS, tsmem, st>>>(D, seeds, n_seeds, rate, (uint32_t*)marks, dsa, n_dense, flag);
+    k_dense_popc<<<(n_rec + 255) / 256, 256, 0, st>>>(marks, n_rec, ones);
+    k_scan_local<<<n_blocks, SCAN_BLOCK, 0, st>>>(ones, n_rec, before, sums);
+    k_scan_sums<<<1, SCAN_BLOCK, 0, st>>>(sums, n_blocks, sums + n_blocks);
+    k_scan_apply<<<n_blocks, SCAN_BLOCK, 0, st>>>(before, n_rec, sums, sums + n_blocks);
+    k_dense_fill<<<(n_rec + 255) / 256, 256, 0, st>>>(marks, n_rec, before);
+    k_dense_walk<1><<<grid, DENSE_THREADS, tsmem, st>>>(D, seeds, n_seeds, rate, (uint32_t*)marks, dsa, n_dense, flag);
+    uint64_t marked = 0;
+    unsigned int failed = 0;
+    if ((rc = check(cudaGetLastError())) || (rc = check(cudaMemcpyAsync(&marked, before + n_rec, 8, cudaMemcpyDeviceToHost, st))) ||
+        (rc = check(cudaMemcpyAsync(&failed, flag, 4, cudaMemcpyDeviceToHost, st))) || (rc = check(cudaStreamSynchronize(st))))
+        return rc;
+    cudaFree(seeds);
+    cudaFree(flag);
+    cudaFree(scan);
+    if (failed || marked != n_dense) {  // not the text-order walk of a consistent index: locate keeps the index's own samples
+        cudaFree(marks);
+        cudaFree(dsa);
+        return 0;
+    }
+    adopt<Rec32>(rp, marks, mark_bytes, &rp->dev.dmarks, -1);
+    adopt<uint32_t>(rp, dsa, dsa_bytes, &rp->dev.dsa, -1);
+    rp->dense_bytes = mark_bytes + dsa_bytes;
+    rp->dev.dense_rate = rate;
+    rp->dev.n_dense = n_dense;
+    return 0;
+}
+
 // per-device setup after the layout is resident: grid sizes, shared-memory opt-ins
 int lf_setup(Replica* rp);
 
@@ -596,6 +697,7 @@ namespace {
 int clone_replica(const Replica* src, int device, Replica* dst) {
     dst->device = device;
     dst->dev = src->dev;
+    dst->dense_bytes = src->dense_bytes;
     CU(cudaSetDevice(device));
     int can = 0;
     if (cudaDeviceCanAccessPeer(&can, device, src->device) == cudaSuccess && can) {
@@ -710,6 +812,7 @@ int load_common(const uint8_t* buf, size_t len, const fmgpu_opts* opts, fmgpu_in
         if (g && atoi(g) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
     }
     if (!rc && kind == KIND_FM) rc = build_start_table(ix, F.code2char, F.char2code);
+    if (!rc && kind == KIND_FM) rc = build_dense_samples(ix, opts ? opts->locate_sample_rate : 0);
     for (size_t i = 1; !rc && i < devices.size(); ++i) {
         ix->reps.emplace_back(new Replica());
         rc = clone_replica(rp, devices[i], ix->reps.back().get());
@@ -973,6 +1076,18 @@ int fmgpu_set_start_table(fmgpu_index* ix, int enable) {
     return 0;
 }
 int32_t fmgpu_start_table_q(const fmgpu_index* ix) { return ix ? (int32_t)ix->primary()->dev.kmer_q : -1; }
+
+int fmgpu_set_locate_dense(fmgpu_index* ix, int enable) {
+    if (!ix) return fail(FMGPU_ERR_ARG, "null handle");
+    ix->use_dense = enable != 0;
+    return 0;
+}
+int32_t fmgpu_locate_sample_rate(const fmgpu_index* ix) {
+    if (!ix) return -1;
+    const DevIndex& D = ix->primary()->dev;
+    return (int32_t)(D.dense_rate ? D.dense_rate : D.sample_rate);
+}
+uint64_t fmgpu_dense_sample_bytes(const fmgpu_index* ix) { return ix ? ix->primary()->dense_bytes : 0; }
 
 int fmgpu_set_stats(fmgpu_index* ix, int enable) {
     if (!ix) return fail(FMGPU_ERR_ARG, "null argument");

@@ -25,24 +25,35 @@ namespace fmgpu {
 #ifndef LOCATE_MIN_CTAS
 #define LOCATE_MIN_CTAS 2
 #endif
+// CTA shape of the dense-sample instantiations (no 64 KB table in shared memory: the register file is the only limit)
+#ifndef LOCATE_DENSE_THREADS
+#define LOCATE_DENSE_THREADS 640
+#endif
+#ifndef LOCATE_DENSE_MIN_CTAS
+#define LOCATE_DENSE_MIN_CTAS 2
+#endif
+constexpr int locate_threads(bool dense) { return dense ? LOCATE_DENSE_THREADS : LOCATE_THREADS; }
 constexpr uint32_t LOCATE_TAB_WORDS = (32768u * 2u + 16u * 2u) / 4u;  // inverse table + class bases
 
-inline size_t locate_smem_bytes(const DevIndex& ix) { return LOCATE_TAB_WORDS * 4 + tables_smem_bytes(ix); }
+inline size_t locate_smem_bytes(const DevIndex& ix, bool dense = false) { return (dense ? 0 : LOCATE_TAB_WORDS * 4) + tables_smem_bytes(ix); }
 
-// STATS: keep the work counters (fmgpu_set_stats); the production instantiation carries none
-template <bool STATS>
-__global__ void __launch_bounds__(LOCATE_THREADS, LOCATE_MIN_CTAS)
+// STATS: keep the work counters (fmgpu_set_stats); the production instantiation carries none.
+// DENSE: the sampled-row test reads the device-side dense marks (layout.h: dmarks / dsa, kernels_dense.cuh) instead of the RRR
+// vector — one plain 224-row record, no offset stream, no (class, offset) table in shared memory — and the walk ends at the
+// nearest multiple of dense_rate.
+template <bool STATS, bool DENSE>
+__global__ void __launch_bounds__(DENSE ? LOCATE_DENSE_THREADS : LOCATE_THREADS, DENSE ? LOCATE_DENSE_MIN_CTAS : LOCATE_MIN_CTAS)
 k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, uint32_t chunk, unsigned int* queue,
          unsigned long long* stats, const uint64_t* __restrict__ hit_off, uint32_t n_pat, int32_t* __restrict__ status) {
     extern __shared__ uint32_t smem[];
     uint16_t* inv = reinterpret_cast<uint16_t*>(smem);
     uint16_t* cbase = inv + 32768;
-    {
+    if (!DENSE) {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(ix.rrr_inv);
         for (uint32_t i = threadIdx.x; i < 16384u; i += blockDim.x) smem[i] = __ldg(src + i);
         if (threadIdx.x < 16) cbase[threadIdx.x] = __ldg(ix.rrr_cbase + threadIdx.x);
     }
-    const SmemTables T = stage_tables(ix, smem + LOCATE_TAB_WORDS);  // ends with __syncthreads()
+    const SmemTables T = stage_tables(ix, smem + (DENSE ? 0u : LOCATE_TAB_WORDS));  // ends with __syncthreads()
     RrrTab R;
     R.inv = inv;
     R.cbase = cbase;
@@ -91,13 +102,17 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
             const SbDesc sd = T.sb[pos >> SB_LOG];
             const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
             const uint32_t bmask = (1u << sd.block_log) - 1u;
-            const Rec32 G = ld256(sg_addr(ix, pos));
+            const Rec32 G = ld256(DENSE ? ix.dmarks + pos / DENSE_ROWS_PER_REC : sg_addr(ix, pos));
             const Rec32 D = ld256(ix.blocks + blk);
             uint32_t bit = 0, rank = 0;
             ++cnt.sbits;
-            sampled_access_rank(ix, R, G, pos, &bit, &rank);  // :531
+            if (DENSE) dense_access_rank(G, pos, &bit, &rank);
+            else sampled_access_rank(ix, R, G, pos, &bit, &rank);  // :531
             Rec32 SA;
-            if (bit) SA = ld256(ix.sa + (rank >> 3));  // issued before the other lanes' LF step, consumed after it
+            uint32_t dense_sa = 0;
+            // issued before the other lanes' LF step, consumed after it
+            if (bit && DENSE) dense_sa = __ldg(ix.dsa + (rank < ix.n_dense ? rank : 0u));
+            if (bit && !DENSE) SA = ld256(ix.sa + (rank >> 3));
             if (!bit) {
                 uint32_t sym = 0, err = 0;
                 const uint32_t jn = lf_step(ix, T, D, j, bmask, &sym, &err, cnt);  // :532-536
@@ -123,7 +138,7 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
                 }
             }
             if (bit) {
-                rows_pos[w] = rec_word(SA, rank & 7u) + dist;  // suffixes[rankOnes(j) - 1] + distance, rankOnes(j) = rankOnes(j-1) + 1 (:538-542)
+                rows_pos[w] = (DENSE ? dense_sa : rec_word(SA, rank & 7u)) + dist;  // suffixes[rankOnes(j) - 1] + distance, rankOnes(j) = rankOnes(j-1) + 1 (:538-542)
                 active = false;
             }
         }

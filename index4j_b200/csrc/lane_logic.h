@@ -67,22 +67,10 @@ FMGPU_HD uint32_t count_u16_below(const Rec32& x, int first, int n_words, uint32
         if (k >= first && k < first + n_words) n += ((x.w[k] & 0xffffu) < r ? 1u : 0u) + ((x.w[k] >> 16) < r ? 1u : 0u);
     return n;
 }
-// Does the cell need a record for position r of its block?  If so *rec = its address and *part = what the cell alone already
-// knows (list records wholly below r).  If not, *part = the occurrences below r.
-FMGPU_HD bool occ_locate(const DevIndex& ix, const Rec32& cell, uint32_t kind, uint32_t r, const Rec32** rec, uint32_t* part) {
-    *part = 0u;
-    if (kind == CELL_OCC_BITS) {
-        *rec = ix.occ + (cell.w[1] + r / OCC_BITS_PER_REC);
-        return true;
-    }
-    const uint32_t below = count_u16_below(cell, 3, 5, r);  // inline positions / list splitters below r
-    if (kind == CELL_OCC_LIST) {
-        *rec = ix.occ + (cell.w[1] + below);
-        *part = below * OCC_LIST_PER_REC;
-        return true;
-    }
-    *part = below;
-    return false;
+FMGPU_HD uint32_t cell_kind(const Cell8& c) { return c.info >> CELL_KIND_SHIFT; }
+// the ONE record an OCC_* cell needs for position r of its block
+FMGPU_HD const Rec32* occ_record(const DevIndex& ix, const Cell8& cell, uint32_t kind, uint32_t r) {
+    return ix.occ + ((cell.info & CELL_PTR_MASK) + (kind == CELL_OCC_BITS ? r / OCC_BITS_PER_REC : 0u));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -113,11 +101,20 @@ FMGPU_HD uint32_t plane_bit(const Rec32& x, uint32_t plane, uint32_t b) {
 // ends at this level).  Returns the position in grandchild (t, u) — in child t when the code ends here.
 FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t b, uint32_t t, uint32_t u) { return dlevel_base(x, t, u) + dlevel_count(x, b, t, u); }
 
-// occurrences below r inside the record occ_locate pointed at (y), for the cell's kind
-FMGPU_HD uint32_t occ_in_record(const Rec32& cell, const Rec32& y, uint32_t kind, uint32_t r) {
-    if (kind == CELL_OCC_LIST) return count_u16_below(y, 0, 8, r);
+// occurrences of the symbol among the first r positions of the block, from the record occ_record pointed at (y);
+// *len (work counters) = the symbol's code length in the block's tree
+FMGPU_HD uint32_t occ_in_record(const Rec32& y, uint32_t kind, uint32_t r, uint32_t* len) {
+    if (kind == CELL_OCC_LIST) {
+        *len = y.w[7] >> 16;
+        // slot 15 (the code length, < 64) is never counted: it would need r > length, and r <= 65535 excludes the padding
+        uint32_t n = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) n += ((y.w[k] & 0xffffu) < r ? 1u : 0u) + ((k < 7 && (y.w[k] >> 16) < r) ? 1u : 0u);
+        return n;
+    }
+    *len = y.w[0] >> 24;
     const uint32_t b = r % OCC_BITS_PER_REC;
-    uint32_t n = y.w[0];
+    uint32_t n = y.w[0] & 0xffffffu;
 #pragma unroll
     for (int k = 0; k < 7; ++k) n += popc32(y.w[1 + k] & low_mask_clamped((int)b - 32 * k));
     return n;
@@ -170,27 +167,23 @@ FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t 
     const SbDesc sd = T.sb[pos >> SB_LOG];
     const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
     const uint32_t r = pos & ((1u << sd.block_log) - 1u);
-    const Rec32 cell = FMGPU_LD256(ix.cells + ((uint64_t)blk * ix.sigma + sym));
+    const Cell8 cell = FMGPU_LDCELL(ix.cells + ((uint64_t)blk * ix.sigma + sym));
     ++*n_rank;
-    const uint32_t kind = (cell.w[2] >> 8) & 0xffu;
+    const uint32_t kind = cell_kind(cell);
     if (kind == CELL_CONST) {
-        *out = cell.w[0];
+        *out = cell.value;
         return 0u;
     }
     if (kind == CELL_RUN) {  // :1141-1146
-        *out = cell.w[0] + r;
+        *out = cell.value + r;
         return 0u;
     }
-    if (kind == CELL_THROW || kind == CELL_NORMAL) return 9u;
-    *n_level += cell.w[2] & 0xffu;
-    const Rec32* rec = nullptr;
-    uint32_t part = 0;
-    if (occ_locate(ix, cell, kind, r, &rec, &part)) {
-        const Rec32 y = FMGPU_LD256(rec);
-        ++*n_rec;
-        part += occ_in_record(cell, y, kind, r);
-    }
-    *out = cell.w[0] + part;
+    if (kind != CELL_OCC_LIST && kind != CELL_OCC_BITS) return 9u;  // THROW
+    const Rec32 y = FMGPU_LD256(occ_record(ix, cell, kind, r));
+    ++*n_rec;
+    uint32_t len = 0;
+    *out = cell.value + occ_in_record(y, kind, r, &len);
+    *n_level += len;
     return 0u;
 }
 

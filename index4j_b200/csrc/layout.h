@@ -16,33 +16,36 @@ struct alignas(32) Rec32 {
     uint32_t w[8];
 };
 
-// --- (block, symbol) cell: WaveletFixedBlockBoosting.rank(pos, sym) for every position of the block, flattened
+// --- (block, symbol) cell, 8 bytes: WaveletFixedBlockBoosting.rank(pos, sym) for every position of the block, flattened
 // (wavelet/WaveletFixedBlockBoosting.java:1022-1285).
-//   w0 value : hyper+super+block boundary rank (RUN / OCC_*) or the complete answer (CONST)
-//   w2       : code length of sym in the block's tree (bits 0-7: what the reference's level walk costs, kept for the work
-//              counters) | kind (bits 8-15)
-//   kinds    : CONST   the symbol does not occur in the block (or the superblock): the answer is w0, whatever the position
-//              RUN     single-symbol block: w0 + position in block (:1141-1146)
-//              THROW   the reference indexes out of its arrays
-//              OCC_*   the symbol occurs in the block: the reference walks the block's Huffman-shaped wavelet tree along the
-//                      symbol's code (:1185-1279), one RRR rank per level, which counts the occurrences of the symbol among the
-//                      first r positions of the block.  That count is stored directly, per (block, symbol), in one of three
-//                      forms — so a rank is the cell plus AT MOST ONE further record, whatever the code length:
-//              OCC_INLINE  <= 10 occurrences: their positions (u16, ascending, padded 0xffff) in w3..w7
-//              OCC_LIST    <= 176 occurrences: w1 = first record of a sorted position list in `occ` (16 u16 per record, padded
-//                          0xffff), w3..w7 = 10 splitters (splitter j = first position of list record j + 1)
-//              OCC_BITS    w1 = first record of a bit vector over the block's positions in `occ`: record q covers positions
-//                          [224 q, 224 q + 224): w0 = occurrences before the record, w1..w7 = 224 bits
+//   value : hyper+super+block boundary rank (RUN / OCC_*) or the complete answer (CONST)
+//   info  : kind << 29 | first occurrence record of the pair in `occ`
+//   kinds : CONST   the symbol does not occur in the block (or the superblock): the answer is `value`, whatever the position
+//                   (incl. the reference's scan for the next block that holds the symbol, :1048-1110, quirk Q3 restated)
+//           RUN     single-symbol block: value + position in block (:1141-1146)
+//           THROW   the reference indexes out of its arrays
+//           OCC_*   the symbol occurs in the block: the reference walks the block's Huffman-shaped wavelet tree along the
+//                   symbol's code (:1185-1279), one RRR rank per level, which counts the occurrences of the symbol among the
+//                   first r positions of the block.  That count is stored directly, per (block, symbol), so a rank is the cell
+//                   plus EXACTLY ONE record, whatever the code length:
+//           OCC_LIST  <= 15 occurrences: ONE record with their positions (u16, ascending, padded 0xffff) in slots 0..14;
+//                     slot 15 = the symbol's code length (what the reference's walk costs: work counters only)
+//           OCC_BITS  a bit vector over the block's positions: record q covers positions [224 q, 224 q + 224): w0 = occurrences
+//                     before the record (low 24 bits) | code length << 24, w1..w7 = 224 bits
+// The table is dense, cells[block][symbol]: 8 bytes per pair keep it L2-resident for log alphabets (30 MB per 2^30 chars at 70
+// symbols; it was 32 bytes per pair — 120 MB, which the 126 MB L2 did not hold beside the records: ncu showed the cell loads
+// stalling as long as the DRAM-bound record loads — with in-cell position lists / list splitters that < 1 % of the queries used).
 // (Rounds 1-2 kept the wavelet levels on this path too: one level record per two tree levels, up to three dependent records per
 // rank, and a warp of 64 rank tracks in lockstep ran 2.9 record trips per step for 1.15 needed per track.  The level records
 // remain what inverseSelect walks — the LF kernels — where the symbol is not known in advance.  Measured on the configs[1]
-// batch, 39 % of the rank queries end in a bit vector, 26 % in what could be served by the root's level record (codes of 1-2
-// bits; giving those their own bit vectors costs 9 % more occurrence records and removes a third code path from the kernel),
-// 32 % in RUN cells, 2.5 % in CONST cells, < 1 % in position lists.)
-enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3, CELL_OCC_INLINE = 4, CELL_OCC_LIST = 5, CELL_OCC_BITS = 6 };
-constexpr uint32_t OCC_INLINE_MAX = 10;      // positions that fit w3..w7 of the cell
-constexpr uint32_t OCC_LIST_PER_REC = 16;    // u16 positions per list record
-constexpr uint32_t OCC_LIST_MAX = 176;       // (10 splitters + 1) list records
+// batch, 65 % of the rank queries end in a bit vector, 32 % in RUN cells, 2.5 % in CONST cells, < 1 % in position lists.)
+struct alignas(8) Cell8 {
+    uint32_t value, info;
+};
+enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3, CELL_OCC_LIST = 5, CELL_OCC_BITS = 6 };
+constexpr uint32_t CELL_KIND_SHIFT = 29;
+constexpr uint32_t CELL_PTR_MASK = (1u << CELL_KIND_SHIFT) - 1u;
+constexpr uint32_t OCC_LIST_MAX = 15;        // positions of a list record (slot 15 holds the code length)
 constexpr uint32_t OCC_BITS_PER_REC = 224;   // positions per bit-vector record
 
 // --- level record (32 bytes): TWO tree levels of 96 positions.  Only the wavelet-tree nodes at EVEN depth own records;
@@ -115,7 +118,7 @@ struct DevIndex {
     const uint16_t* char2code;  // [65536], 0 = not in alphabet (monotonicMap.getOrDefault(c, 0))
     const uint16_t* code2char;  // monotonicLookUp
     const SbDesc* sb;
-    const Rec32* cells;    // [n_blocks_total][sigma]
+    const Cell8* cells;    // [n_blocks_total][sigma]
     const Rec32* sectors;  // level records of the even-depth wavelet nodes (inverseSelect)
     const Rec32* occ;      // occurrence records of the (block, symbol) pairs (position lists / bit vectors)
     const Rec32* blocks;   // block descriptors
@@ -126,6 +129,18 @@ struct DevIndex {
     const uint16_t* rrr_cbase;  // [16]    RrrVector.java:8692-8698
     const Rec32* sa;       // SA samples, 8 per Rec32
     const Rec32* isa;      // ISA samples, 8 per Rec32
+    // Device-side DENSER sampling of the SA rows for locate (0 = none; fmgpu.cu build_dense_samples): the serialized index
+    // samples the rows whose suffix starts at a multiple of sampleRate (fm/FmIndex.java:343-357); at load the LF kernels walk
+    // the text once and also mark the rows of every multiple of dense_rate (a divisor of sampleRate), so a hit's walk
+    // (fm/FmIndex.java:531-537) ends after (dense_rate - 1) / 2 steps on average instead of (sampleRate - 1) / 2 — the same
+    // positions, HBM traded for LF steps.
+    //   dmarks record q: w0 = marked rows before row 224 q, w1..w7 = marks of rows [224 q, 224 q + 224)
+    //   dsa[k] = suffix start of the k-th marked row
+    uint32_t dense_rate;
+    uint32_t n_dense;
+    const Rec32* dmarks;
+    const uint32_t* dsa;
 };
+constexpr uint32_t DENSE_ROWS_PER_REC = 224;
 
 }  // namespace fmgpu

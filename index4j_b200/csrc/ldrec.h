@@ -28,13 +28,41 @@ __device__ __forceinline__ Rec32 ld256_stream(const Rec32* p) {
                  : "l"(p));
     return r;
 }
+// one 8-byte (block, symbol) cell
+__device__ __forceinline__ Cell8 ldcell(const Cell8* p) {
+    Cell8 c;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(c.value), "=r"(c.info) : "l"(p));
+    return c;
+}
+__device__ __forceinline__ Cell8 ldcell_keep(const Cell8* p) {
+    Cell8 c;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v2.b32 {%0,%1}, [%2];" : "=r"(c.value), "=r"(c.info) : "l"(p));
+    return c;
+}
 }  // namespace fmgpu
 #endif
+// L2 eviction priorities of the backward search's two record families (experiment knob, -DCOUNT_L2_HINTS=n):
+// 1 = cells evict_last + occurrence records evict_first, 2 = cells evict_last only, 3 = occurrence records evict_first only
+#ifndef COUNT_L2_HINTS
+#define COUNT_L2_HINTS 0
+#endif
 #if defined(__CUDA_ARCH__)
+#if COUNT_L2_HINTS == 1 || COUNT_L2_HINTS == 2
+#define FMGPU_LDCELL(p) ::fmgpu::ldcell_keep(p)
+#else
+#define FMGPU_LDCELL(p) ::fmgpu::ldcell(p)
+#endif
+#if COUNT_L2_HINTS == 1 || COUNT_L2_HINTS == 3
+#define FMGPU_LD256_OCC(p) ::fmgpu::ld256_stream(p)
+#else
+#define FMGPU_LD256_OCC(p) ::fmgpu::ld256(p)
+#endif
 #define FMGPU_LD256(p) ::fmgpu::ld256(p)
 #define FMGPU_LDG32(p) __ldg(p)
 #define FMGPU_LDG16(p) __ldg(p)
 #else
+#define FMGPU_LDCELL(p) (*(p))
+#define FMGPU_LD256_OCC(p) (*(p))
 #define FMGPU_LD256(p) (*(p))
 #define FMGPU_LDG32(p) (*(p))
 #define FMGPU_LDG16(p) (*(p))

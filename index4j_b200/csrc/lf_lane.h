@@ -71,6 +71,18 @@ FMGPU_HD void sampled_access_rank(const DevIndex& ix, const RrrTab& R, const Rec
     *rank = ones + popc32(block & ((1u << use) - 1u));
 }
 
+// The same test on the device-side dense marks (layout.h: DevIndex::dmarks): is row `pos` marked, and how many marked rows
+// precede it (= its index in dsa)?  G = dmarks[pos / 224], already fetched.
+FMGPU_HD void dense_access_rank(const Rec32& G, uint32_t pos, uint32_t* bit, uint32_t* rank) {
+    const uint32_t o = pos % DENSE_ROWS_PER_REC, wi = o >> 5, sh = o & 31u;
+    const uint32_t word = rec_word(G, 1u + wi);
+    uint32_t r = G.w[0];
+#pragma unroll
+    for (uint32_t k = 0; k < 6; ++k) r += k < wi ? popc32(G.w[1 + k]) : 0u;
+    *bit = (word >> sh) & 1u;
+    *rank = r + popc32(word & ((1u << sh) - 1u));
+}
+
 // One LF step from row j (Java's 1-based j): returns the new j.  D is the block descriptor of position j-1
 // (already fetched), bmask the block-size mask of that position's superblock.
 //   * tree block: inverseSelect walks DOWN the block's tree, two levels per level record (plus the node record of
@@ -125,6 +137,44 @@ FMGPU_HD uint32_t lf_step(const DevIndex& ix, const SmemTables& T, const Rec32& 
     // 1 <= LF(j) <= length - 1 on a consistent index; the clamps keep a corrupt (but loadable) one inside the tables
     const uint32_t jn = T.C[sym] + rank_j;
     return jn == 0u ? 1u : (jn < ix.length ? jn : ix.length);
+}
+
+// One item of the dense-sample build (kernels_dense.cuh): from `row`, whose suffix starts at text position p, LF-walk towards
+// the start of the text and hand every (row, position) visited to `visit`, up to (not including) the next multiple of
+// sampleRate — that row is a sampled row and the start of its own item.  Returns false where an LF step fails.
+template <typename Visit>
+FMGPU_HD bool dense_walk_item(const DevIndex& ix, const SmemTables& T, uint32_t row, uint32_t p, Visit&& visit) {
+    LfCounters cnt;
+    cnt.lf_steps = cnt.lf_levels = cnt.ranks = cnt.rank_levels = cnt.sbits = cnt.recs = 0;
+    visit(row, p);
+    while (p != 0u) {
+        const SbDesc sd = T.sb[row >> SB_LOG];
+        const uint32_t blk = sd.first_block + ((row & SB_MASK) >> sd.block_log);
+        const Rec32 D = FMGPU_LD256(ix.blocks + blk);
+        uint32_t sym = 0, err = 0;
+        const uint32_t jn = lf_step(ix, T, D, row + 1u, (1u << sd.block_log) - 1u, &sym, &err, cnt);
+        if (err) return false;
+        row = jn - 1u;
+        --p;
+        if (p % ix.sample_rate == 0u) break;
+        visit(row, p);
+    }
+    return true;
+}
+// the items: k < n_seeds = the k-th sampled row (position suffixes[k]; n_seeds = ones of the sampled-row vector — suffixes[]
+// itself has length / sampleRate + 1 entries, one more than there are sampled rows when sampleRate divides length,
+// fm/FmIndex.java:343-344); k == n_seeds = row 0, the sentinel's suffix (position length - 1), which covers the positions
+// behind the last multiple of sampleRate.  Returns 0 = walk it, 1 = nothing to do, 2 = not a consistent index.
+FMGPU_HD uint32_t dense_seed_count(const DevIndex& ix) { return ix.s_total_ones < ix.n_sa ? ix.s_total_ones : ix.n_sa; }
+FMGPU_HD int dense_item(const DevIndex& ix, const uint32_t* seed_row, uint32_t n_seeds, uint64_t k, uint32_t* row, uint32_t* p) {
+    if (k < n_seeds) {
+        *row = seed_row[k];
+        *p = reinterpret_cast<const uint32_t*>(ix.sa)[k];
+        return (*row >= ix.length || *p >= ix.length || *p % ix.sample_rate != 0u) ? 2 : 0;
+    }
+    *row = 0;
+    *p = ix.length - 1u;
+    return *p % ix.sample_rate == 0u ? 1 : 0;  // 1: the sentinel's row is a sampled row itself
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -118,6 +118,11 @@ def native():
         L.fmgpu_set_stats.argtypes = [vp, i32]
         L.fmgpu_set_start_table.argtypes = [vp, i32]
         L.fmgpu_start_table_q.argtypes = [vp]
+        L.fmgpu_set_locate_dense.argtypes = [vp, i32]
+        L.fmgpu_locate_sample_rate.argtypes = [vp]
+        L.fmgpu_locate_sample_rate.restype = i32
+        L.fmgpu_dense_sample_bytes.argtypes = [vp]
+        L.fmgpu_dense_sample_bytes.restype = u64
         L.fmgpu_search_kernel_ms.argtypes = [vp, u32, C.POINTER(C.c_float)]
         L.fmgpu_kernel_ms.argtypes = [vp, i32, u32, u32, C.POINTER(C.c_float)]
         _lib = L
@@ -125,7 +130,7 @@ def native():
 
 
 class _Opts(C.Structure):
-    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("n_devices", C.c_int32), ("reserved0", C.c_int32),
+    _fields_ = [("device", C.c_int32), ("host_threads", C.c_int32), ("n_devices", C.c_int32), ("locate_sample_rate", C.c_int32),
                 ("devices", C.POINTER(C.c_int32)), ("reserved", C.c_uint64 * 1)]
 
 
@@ -178,14 +183,18 @@ class FmIndex:
 
     # --- construction --------------------------------------------------------------------
     @classmethod
-    def read(cls, serialized, device: int | None = None, host_threads: int = 0, devices=None) -> "FmIndex":
+    def read(cls, serialized, device: int | None = None, host_threads: int = 0, devices=None, locate_sample_rate: int = 0) -> "FmIndex":
         """``Serialization.readFromByteArray(FmIndex::read, bytes)`` (Serialization.java:89, FmIndex.java:983).
+
+        ``locate_sample_rate``: device-side denser sampling of the SA rows for locate (include/fmgpu.h): > 0 the requested rate,
+        0 = the library's default, < 0 = the index's own sampling only.
 
         ``devices``: a list of CUDA ordinals (or ``"all"``) — the index is replicated on each of them and every host-pointer batch
         call is cut into one slice per device."""
         lib = native()
         buf = np.frombuffer(serialized, dtype=np.uint8)
         opts = _Opts(-1 if device is None else int(device), int(host_threads))
+        opts.locate_sample_rate = int(locate_sample_rate)
         if devices is not None:
             if isinstance(devices, str):
                 opts.n_devices = -1
@@ -256,6 +265,18 @@ class FmIndex:
     def set_stats(self, enable: bool = True):
         """Work counters of the kernels (``last_stats``) on/off; off by default (production kernels carry none)."""
         self._check(self._lib.fmgpu_set_stats(self._h, int(enable)))
+
+    def set_locate_dense(self, enable: bool = True):
+        """locate walks end at the device-side dense samples (default when the index has them) or at the index's own samples."""
+        self._check(self._lib.fmgpu_set_locate_dense(self._h, int(enable)))
+
+    @property
+    def locate_sample_rate(self) -> int:
+        """Rate of the samples locate walks to: the dense rate when dense samples were built, else the index's sampleRate."""
+        return int(self._lib.fmgpu_locate_sample_rate(self._h))
+
+    def dense_sample_bytes(self) -> int:
+        return int(self._lib.fmgpu_dense_sample_bytes(self._h))
 
     def set_start_table(self, enable: bool = True):
         """Use (default) / bypass the q-gram start table of the backward search; results are identical either way."""

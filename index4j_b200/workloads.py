@@ -74,7 +74,7 @@ def locate_workload_nostats(ix, d_chars, d_off, max_hits: int, steps: int, warmu
     d_pos = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
     fn = lambda: ix.locate_batch_device(d_chars, d_off, max_hits, d_n_hits, d_hit_off, d_pos, None)  # noqa: E731
     ms = _timed(fn, steps, warmup)
-    out = {"patterns": n_pat, "hits": int(total), "ms_per_step": ms, "lf_steps_est": float(total) * (ix.sample_rate - 1) / 2.0}
+    out = {"patterns": n_pat, "hits": int(total), "ms_per_step": ms, "lf_steps_est": float(total) * (ix.locate_sample_rate - 1) / 2.0}
     return out, d_hit_off, d_pos
 
 

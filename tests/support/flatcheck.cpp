@@ -95,7 +95,7 @@ void fc_free(void* h) { delete (FC*)h; }
 int32_t fc_alphabet_length(void* h) { return ((FC*)h)->F.alphabet_length; }
 void fc_sizes(void* hv, uint64_t* out8) {
     FC* h = (FC*)hv;
-    out8[0] = h->F.cells.size() * 32;
+    out8[0] = h->F.cells.size() * sizeof(Cell8);
     out8[1] = h->F.sectors.size() * 32;
     out8[2] = h->F.nodes.size() * 32;
     out8[3] = h->F.blocks.size() * 32;
@@ -109,7 +109,7 @@ void fc_sizes(void* hv, uint64_t* out8) {
 void fc_cell_kinds(void* hv, uint64_t* out6) {
     FC* h = (FC*)hv;
     for (int i = 0; i < 6; ++i) out6[i] = 0;
-    for (const Rec32& c : h->F.cells) out6[(c.w[2] >> 8) & 3u]++;
+    for (const Cell8& c : h->F.cells) out6[cell_kind(c) & 3u]++;
     out6[4] = h->F.blocks.size();
     for (const Rec32& b : h->F.blocks) out6[5] += b.w[1] & 1u;
 }
@@ -399,6 +399,85 @@ void fc_locate_rows(void* hv, uint32_t* rows_pos, uint32_t n, uint64_t* counters
         counters[3] += cnt.lf_levels;
         counters[4] += cnt.sbits;
     }
+}
+// Dense-sample build (kernels_dense.cuh / fmgpu.cu build_dense_samples) replayed on the host with the same lane code: seeds
+// from the sampled-row vector, the marking walk, the rank counters, the walk that writes the positions.  marks: n_rec * 8
+// words, dsa: (length - 1) / rate + 1 entries.  Returns the number of marked rows, or -1 where the device build gives up.
+int64_t fc_dense_build(void* hv, uint32_t rate, uint32_t* marks, uint32_t* dsa) {
+    FC& h = *(FC*)hv;
+    const DevIndex& ix = h.ix;
+    const fmgpu_host::RrrTables& RT = fmgpu_host::rrr_tables();
+    RrrTab R;
+    R.inv = RT.inverse;
+    R.cbase = RT.class_base;
+    const uint32_t n_rec = (ix.length + DENSE_ROWS_PER_REC - 1) / DENSE_ROWS_PER_REC;
+    const uint32_t n_dense = (ix.length - 1u) / rate + 1u;
+    const uint32_t n_seeds = dense_seed_count(ix);
+    std::vector<uint32_t> seeds((size_t)n_seeds + 1, 0xffffffffu);
+    for (uint32_t row = 0; row < ix.length; ++row) {  // k_dense_seeds
+        uint32_t bit = 0, rank = 0;
+        sampled_access_rank(ix, R, *sg_addr(ix, row), row, &bit, &rank);
+        if (bit && rank < n_seeds) seeds[rank] = row;
+    }
+    std::memset(marks, 0, (size_t)n_rec * 32);
+    bool failed = false;
+    for (int pass = 0; pass < 2; ++pass) {
+        auto visit = [&](uint32_t row, uint32_t p) {
+            if (p % rate != 0u) return;
+            const uint32_t q = row / DENSE_ROWS_PER_REC, o = row % DENSE_ROWS_PER_REC;
+            if (pass == 0) {
+                marks[(size_t)q * 8u + 1u + (o >> 5)] |= 1u << (o & 31u);
+            } else {
+                uint32_t bit = 0, rank = 0;
+                dense_access_rank(*reinterpret_cast<const Rec32*>(marks + (size_t)q * 8u), row, &bit, &rank);
+                if (bit && rank < n_dense) dsa[rank] = p;
+                else failed = true;
+            }
+        };
+        for (uint64_t k = 0; k <= n_seeds; ++k) {  // k_dense_walk<pass>
+            uint32_t row = 0, p = 0;
+            const int what = dense_item(ix, seeds.data(), n_seeds, k, &row, &p);
+            if (what == 1) continue;
+            if (what == 2 || !dense_walk_item(ix, h.T, row, p, visit)) failed = true;
+        }
+        if (pass == 0) {  // k_dense_popc + scan + k_dense_fill
+            uint32_t before = 0;
+            for (uint32_t q = 0; q < n_rec; ++q) {
+                marks[(size_t)q * 8u] = before;
+                for (int k = 1; k < 8; ++k) before += popc32(marks[(size_t)q * 8u + k]);
+            }
+            if (before != n_dense) return -1;
+        }
+    }
+    return failed ? -1 : (int64_t)n_dense;
+}
+// k_locate<., DENSE = true>, one hit at a time
+void fc_locate_rows_dense(void* hv, const uint32_t* marks, const uint32_t* dsa, uint32_t* rows_pos, uint32_t n, uint64_t* lf_steps) {
+    FC& h = *(FC*)hv;
+    LfCounters cnt{};
+    for (uint32_t w = 0; w < n; ++w) {
+        uint32_t j = rows_pos[w] + 1u, dist = 0;
+        for (;;) {
+            const uint32_t pos = j - 1u;
+            const SbDesc sd = h.T.sb[pos >> SB_LOG];
+            const uint32_t blk = sd.first_block + ((pos & SB_MASK) >> sd.block_log);
+            uint32_t bit = 0, rank = 0;
+            dense_access_rank(*reinterpret_cast<const Rec32*>(marks + (size_t)(pos / DENSE_ROWS_PER_REC) * 8u), pos, &bit, &rank);
+            if (bit) {
+                rows_pos[w] = dsa[rank] + dist;
+                break;
+            }
+            uint32_t sym = 0, err = 0;
+            const uint32_t jn = lf_step(h.ix, h.T, h.ix.blocks[blk], j, (1u << sd.block_log) - 1u, &sym, &err, cnt);
+            if (err || dist >= h.ix.length) {
+                rows_pos[w] = err ? 0xffffffffu : 0xfffffffeu;
+                break;
+            }
+            j = jn;
+            ++dist;
+        }
+    }
+    if (lf_steps) *lf_steps += cnt.lf_steps;
 }
 void fc_sampled(void* hv, uint32_t pos, int32_t* bit, int32_t* rank) {
     FC& h = *(FC*)hv;

@@ -40,6 +40,9 @@ def lib():
         L.fc_build_start_table.argtypes = [vp, u32]
         L.fc_build_start_table.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
+        L.fc_dense_build.argtypes = [vp, u32, vp, vp]
+        L.fc_dense_build.restype = C.c_int64
+        L.fc_locate_rows_dense.argtypes = [vp, vp, vp, vp, u32, vp]
         L.fc_extract.argtypes = [vp, vp, vp, u32, vp, vp, vp, vp, vp, i32]
         L.fc_eub.argtypes = [vp, vp, u32, C.c_uint16, i32, i32, vp, vp, vp, vp, i32]
         L.fc_records.argtypes = [vp, vp, u32, C.c_uint16, i32, vp, vp, vp, vp, vp]
@@ -111,6 +114,20 @@ class FlatIndexHost:
         rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()
         lib().fc_locate_rows(self._h, rp.ctypes.data, rp.size, self.counters.ctypes.data)
         return rp.astype(np.int64)
+
+    def dense_build(self, rate: int, length: int):
+        """Host replay of the device-side dense-sample build: -> (marks uint32[n_rec, 8], dsa uint32[n_dense]) or None."""
+        n_rec = (length + 223) // 224
+        marks = np.zeros((n_rec, 8), dtype=np.uint32)
+        dsa = np.full((length - 1) // rate + 1, 0xFFFFFFFF, dtype=np.uint32)
+        n = lib().fc_dense_build(self._h, rate, marks.ctypes.data, dsa.ctypes.data)
+        return None if n < 0 else (marks, dsa)
+
+    def locate_rows_dense(self, marks, dsa, rows):
+        rp = np.ascontiguousarray(rows, dtype=np.uint32).copy()
+        steps = np.zeros(1, dtype=np.uint64)
+        lib().fc_locate_rows_dense(self._h, marks.ctypes.data, dsa.ctypes.data, rp.ctypes.data, rp.size, steps.ctypes.data)
+        return rp.astype(np.int64), int(steps[0])
 
     def extract(self, start, stop, arena_off, offset=0):
         start = np.ascontiguousarray(start, dtype=np.int32)

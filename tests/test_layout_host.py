@@ -246,3 +246,50 @@ def test_record_lanes(flats, name, dst_len):
     good = _check_records(case, frm, dst_len, idx, ln, st, records)
     if dst_len >= 130 and name.startswith("log"):
         assert good > 500 and records.shape[0] < 0.7 * frm.size  # the clustered hits share records
+
+
+def _naive_sa(text):
+    """suffix array of text + sentinel (sentinel smallest), symbols ordered by first appearance (fm/FmIndex.java:396-435)"""
+    order = {}
+    for c in text:
+        order.setdefault(int(c), len(order) + 1)
+    codes = [order[int(c)] for c in text] + [0]
+    return sorted(range(len(codes)), key=lambda i: codes[i:])
+
+
+@pytest.mark.parametrize("n,sr,rate", [(5003, 32, 8), (4096, 16, 4), (1000, 32, 8), (33, 32, 8), (7, 4, 2), (2000, 8, 1), (640, 64, 16)])
+def test_dense_samples_build_small(n, sr, rate):
+    """Dense-sample build (kernels_dense.cuh) replayed on the host against a naive suffix array: exactly the rows whose suffix
+    starts at a multiple of the rate are marked, each with its position — incl. the rows behind the last multiple of
+    sampleRate (walk from the sentinel's row) and position 0."""
+    from index4j_b200.builder import build_index, gen_log_text
+    text = gen_log_text(n, seed=31 + n)
+    f = flatcheck.FlatIndexHost(build_index(text, sr))
+    built = f.dense_build(rate, n + 1)
+    assert built is not None
+    marks, dsa = built
+    sa = np.array(_naive_sa(text), dtype=np.int64)
+    bits = np.unpackbits(marks[:, 1:].copy().view(np.uint8), bitorder="little")[: n + 1].astype(bool)
+    assert np.array_equal(bits, sa % rate == 0)
+    assert np.array_equal(dsa.astype(np.int64), sa[bits])
+    assert np.array_equal(marks[:, 0], np.concatenate([[0], np.cumsum(bits)])[np.arange(marks.shape[0]) * 224])
+    got, _ = f.locate_rows_dense(marks, dsa, np.arange(n + 1, dtype=np.uint32))
+    assert np.array_equal(got, sa)
+
+
+@pytest.mark.parametrize("name", ["log1m_sr32", "log3m_sr16", "log300k_sr64", "tiny600k_sr4", "nul1m_sr32"])
+def test_dense_samples_locate_lanes(flats, name):
+    """locate through the dense marks (lane code of k_locate<., DENSE>) = locate through the index's own samples = the oracle."""
+    case, f = get_case(name), flats(name)
+    L = case.oracle.getInputLength()
+    rate = 8 if case.sample_rate > 8 else 2
+    built = f.dense_build(rate, L)
+    assert built is not None
+    marks, dsa = built
+    assert int(marks[-1, 0]) + int(np.unpackbits(marks[-1, 1:].copy().view(np.uint8)).sum()) == (L - 1) // rate + 1
+    rows = np.concatenate([np.random.default_rng(4).integers(0, L, 30000), [0, L - 1]]).astype(np.uint32)
+    f.counters[:] = 0
+    want = f.locate_rows(rows)
+    got, steps = f.locate_rows_dense(marks, dsa, rows)
+    assert np.array_equal(got, want)
+    assert steps < int(f.counters[2])
