@@ -214,6 +214,10 @@ struct Replica {
     int sm_count = 0;
     int count_ctas = 0, locate_ctas = 0, locate_dense_ctas = 0, extract_ctas = 0, eub_ctas = 0;
     uint64_t dense_bytes = 0;  // dense marks + dsa (also counted in total_bytes)
+    // L2 residency of the (block, symbol) cell table: a persisting access-policy window (replica_setup / l2_window)
+    size_t l2_window_bytes = 0;
+    float l2_hit_ratio = 0.f;
+    std::vector<cudaStream_t> l2_streams;  // streams that already carry the window
     size_t tables_smem = 0;
     static constexpr int NCTX = 4;  // concurrent batch calls per device
     std::mutex mu;
@@ -369,6 +373,28 @@ struct Utf8Src {
     int32_t* d_conv_value;   // ... and the offending code point
 };
 
+// The backward search reads one cell per rank query from a table that is small (8 bytes per (block, symbol) pair) but shares the
+// L2 with the occurrence records streaming through it; ncu showed the cell loads missing L2 about half the time.  The table is
+// therefore given a PERSISTING access-policy window on every stream that launches k_count (set-aside sized at load,
+// replica_setup): measured -10 % kernel time on the configs[1] batch.  FMGPU_L2_PERSIST=0 in the environment disables it.
+void l2_window(Replica* rp, cudaStream_t st) {
+    if (!rp->l2_window_bytes) return;
+    {
+        std::lock_guard<std::mutex> lk(rp->mu);
+        for (cudaStream_t s : rp->l2_streams)
+            if (s == st) return;
+        if (rp->l2_streams.size() >= 64) rp->l2_streams.clear();
+        rp->l2_streams.push_back(st);
+    }
+    cudaStreamAttrValue av{};
+    av.accessPolicyWindow.base_ptr = (void*)rp->dev.cells;
+    av.accessPolicyWindow.num_bytes = rp->l2_window_bytes;
+    av.accessPolicyWindow.hitRatio = rp->l2_hit_ratio;
+    av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av) != cudaSuccess) (void)cudaGetLastError();
+}
+
 // Backward search over n_pat patterns on stream `st`.  `first_of_call` resets the work counters; later
 // chunks of the same call only re-arm the work queue.
 int count_on_stream(fmgpu_index* ix, Replica* rp, CallCtx* cx, const uint16_t* d_chars, const uint64_t* d_pat_off, uint32_t n_pat,
@@ -424,6 +450,7 @@ int count_on_stream(fmgpu_index* ix, Replica* rp, CallCtx* cx, const uint16_t* d
         CU(cudaEventRecord(pre_ev, pre));
         CU(cudaStreamWaitEvent(st, pre_ev, 0));
     }
+    l2_window(rp, st);
     const int slot = timing_slot(ix, rp, FMGPU_KERNEL_COUNT);
     if (slot >= 0) CU(cudaEventRecord(rp->ev0[FMGPU_KERNEL_COUNT][slot], st));
     int grid = rp->count_ctas;
@@ -635,6 +662,24 @@ int replica_setup(Replica* rp) {
     if (cudaGetDeviceProperties(&prop, rp->device) != cudaSuccess) return fail(FMGPU_ERR_CUDA, "cudaGetDeviceProperties failed");
     rp->sm_count = prop.multiProcessorCount;
     rp->tables_smem = count_smem_bytes(rp->dev);
+    {  // persisting-L2 set-aside for the cell table (l2_window): the table + 25 %, at most half of what the device allows; a
+       // larger table gets the fraction of its accesses that fits
+        int want_mb = -1;
+        if (const char* e = getenv("FMGPU_L2_PERSIST")) want_mb = atoi(e);
+        const size_t cells = (size_t)rp->layout_bytes[0];
+        size_t set_aside = want_mb > 0 ? (size_t)want_mb << 20 : cells + cells / 4 + (1u << 20);
+        const size_t cap = (size_t)prop.persistingL2CacheMaxSize / (want_mb > 0 ? 1 : 2);
+        if (set_aside > cap) set_aside = cap;
+        rp->l2_window_bytes = 0;
+        if (want_mb != 0 && cells > 0 && set_aside > 0 && prop.accessPolicyMaxWindowSize > 0 &&
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
+            rp->l2_window_bytes = cells < (size_t)prop.accessPolicyMaxWindowSize ? cells : (size_t)prop.accessPolicyMaxWindowSize;
+            const double r = (double)set_aside / 1.25 / (double)rp->l2_window_bytes;
+            rp->l2_hit_ratio = r >= 1.0 ? 1.0f : (float)r;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     // the attribute is per function, not per index: always the largest table set any index can stage
     if (cudaFuncSetAttribute((const void*)k_count<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess ||
         cudaFuncSetAttribute((const void*)k_count<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COUNT_SMEM_MAX_BYTES) != cudaSuccess)
@@ -678,6 +723,7 @@ void fmgpu_index_free(fmgpu_index* ix) {
         Replica* rp = up.get();
         if (cudaSetDevice(rp->device) != cudaSuccess) continue;
         cudaDeviceSynchronize();
+        if (rp->l2_window_bytes) cudaCtxResetPersistingL2Cache();  // the cell table's persisting lines
         for (void* p : rp->allocs) cudaFree(p);
         for (CallCtx& c : rp->ctx) c.destroy();
         for (int k = 0; k < Replica::TIMING_KINDS; ++k)

@@ -34,6 +34,14 @@ __device__ __forceinline__ Cell8 ldcell(const Cell8* p) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(c.value), "=r"(c.info) : "l"(p));
     return c;
 }
+// the same through L1 (allocating): 4 cells share a sector, 16 a line
+__device__ __forceinline__ Cell8 ldcell_l1(const Cell8* p) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+    Cell8 c;
+    c.value = v.x;
+    c.info = v.y;
+    return c;
+}
 __device__ __forceinline__ Cell8 ldcell_keep(const Cell8* p) {
     Cell8 c;
     asm volatile("ld.global.nc.L1::no_allocate.L2::evict_last.v2.b32 {%0,%1}, [%2];" : "=r"(c.value), "=r"(c.info) : "l"(p));
@@ -42,13 +50,16 @@ __device__ __forceinline__ Cell8 ldcell_keep(const Cell8* p) {
 }  // namespace fmgpu
 #endif
 // L2 eviction priorities of the backward search's two record families (experiment knob, -DCOUNT_L2_HINTS=n):
-// 1 = cells evict_last + occurrence records evict_first, 2 = cells evict_last only, 3 = occurrence records evict_first only
+// 1 = cells evict_last + occurrence records evict_first, 2 = cells evict_last only, 3 = occurrence records evict_first only,
+// 4 = cells through L1 (allocating loads)
 #ifndef COUNT_L2_HINTS
-#define COUNT_L2_HINTS 0
+#define COUNT_L2_HINTS 3  // measured best together with the persisting window on the cell table (fmgpu.cu l2_window)
 #endif
 #if defined(__CUDA_ARCH__)
 #if COUNT_L2_HINTS == 1 || COUNT_L2_HINTS == 2
 #define FMGPU_LDCELL(p) ::fmgpu::ldcell_keep(p)
+#elif COUNT_L2_HINTS == 4
+#define FMGPU_LDCELL(p) ::fmgpu::ldcell_l1(p)
 #else
 #define FMGPU_LDCELL(p) ::fmgpu::ldcell(p)
 #endif
