@@ -418,6 +418,28 @@ def main():
     stats["launches"] = launches_per_step
     ix.set_stats(False)
     clocks = sampler.stop() if rank == 0 else None
+    # the reference's "non-indexed" JMH workload (jmh/.../FmIndexThroughputState.java:106-112): random a-z strings of the same
+    # lengths — the early-exit path (the range empties after a few steps); reported separately, rank 0's batch only
+    rng_ni = np.random.default_rng(4242 + rank)
+    ni_len = rng_ni.integers(args.min_len, args.max_len + 1, n_pat)
+    ni_off = np.zeros(n_pat + 1, dtype=np.int64)
+    ni_off[1:] = np.cumsum(ni_len)
+    ni_chars = rng_ni.integers(ord("a"), ord("z") + 1, int(ni_off[-1])).astype(np.int16)
+    d_ni_chars, d_ni_off = torch.from_numpy(ni_chars).to(dev), torch.from_numpy(ni_off).to(dev)
+    d_ni_counts = torch.empty(n_pat, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        ix.count_batch_device(d_ni_chars, d_ni_off, d_ni_counts, None)
+    torch.cuda.synchronize()
+    n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n0.record()
+    for _ in range(args.steps):
+        ix.count_batch_device(d_ni_chars, d_ni_off, d_ni_counts, None)
+    n1.record()
+    torch.cuda.synchronize()
+    non_indexed = {"workload": "count of %d random a-z strings len %d-%d (the reference's non-indexed JMH batch: early exit)" % (n_pat, args.min_len, args.max_len),
+                   "patterns_per_s_rank0": n_pat * args.steps / (n0.elapsed_time(n1) / 1e3), "ms_per_step": n0.elapsed_time(n1) / args.steps,
+                   "patterns_found": int((d_ni_counts > 0).sum().item())}
+    del d_ni_chars, d_ni_off, d_ni_counts
     # end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region)
     p_chars = torch.from_numpy(chars.view(np.int16)).pin_memory()
     p_off = torch.from_numpy(off.view(np.int64)).pin_memory()
@@ -611,8 +633,8 @@ def main():
         value = world * n_pat * args.steps / (ms_total / 1e3)
         e2e_value = world * n_pat * args.steps / (e2e_ms / 1e3)
         peak, peak_src = hbm_peak()
-        # algorithmic bytes of one k_count launch: every rank query reads one 32-byte cell and one 32-byte level
-        # record per TWO wavelet levels; plus the pattern chars and descriptors it streams.
+        # algorithmic bytes of one k_count launch: every rank query touches one 32-byte sector for its (block, symbol) cell and at
+        # most one 32-byte occurrence record; plus the pattern chars and descriptors it streams.
         alg_bytes = 32.0 * (stats["ranks"] + stats["level_records"]) + 2.0 * chars.size + 16.0 * n_pat + 8.0 * n_pat
         achieved = alg_bytes / (kern_ms / 1e3) / 1e9
         out = {
@@ -629,8 +651,9 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "kernel": "k_count", "kernel_ms": kern_ms, "peak_source": peak_src,
                          "alg_bytes_per_launch": alg_bytes,
-                         "alg_bytes_formula": "32 * (ranks + occurrence records) + pattern chars / descriptors: one 32-byte (block, symbol) cell per rank "
-                                              "and at most one 32-byte occurrence record (none for absent / run / <= 10-occurrence symbols) (DESIGN.md section 5)",
+                         "alg_bytes_formula": "32 * (ranks + occurrence records) + pattern chars / descriptors: per rank query one 32-byte sector for its "
+                                              "8-byte (block, symbol) cell and at most one 32-byte occurrence record (none for absent / run symbols) "
+                                              "(DESIGN.md section 5)",
                          "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
                          "level_records_per_launch": stats["level_records"],
                          "records_loaded_per_launch": stats["search_records_loaded"],
@@ -642,6 +665,7 @@ def main():
                       "start_table_q": ix.start_table_q(), "sample_rate": ix.sample_rate, "locate_sample_rate": ix.locate_sample_rate,
                       "dense_sample_bytes": ix.dense_sample_bytes()},
         }
+        out["count_non_indexed"] = non_indexed
         if lf:
             out["locate"] = {"metric": "located hits/sec (max %d hits per pattern)" % args.max_hits, "value": all_hits / (loc_ms / 1e3),
                              "unit": "hits/s", "hits_per_step": all_hits, "ms_per_step": loc_ms, "steps": args.lf_steps,

@@ -7,9 +7,12 @@ i=0
 for spec in "$@"; do
   i=$((i+1))
   envs="${spec%%|*}"; flags="${spec#*|}"
+  if [ "$flags" != "$prev_flags" ] || [ $i -eq 1 ]; then
   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 --use_fast_math -Xcompiler -fPIC,-O3,-pthread -shared -Xptxas -v \
        -I include $flags -o index4j_b200/libfmgpu.so index4j_b200/csrc/fmgpu.cu -lcudart 2> gpurun_out/${TAG}_variant_$i.nvcc.log
-  grep -A2 "k_countILb0" gpurun_out/${TAG}_variant_$i.nvcc.log | grep -E "Used|spill" | tr '\n' ' ' | sed -e 's/ptxas info *://g' -e 's/bytes//g'
+  prev_flags="$flags"
+  fi
+  [ -f gpurun_out/${TAG}_variant_$i.nvcc.log ] && grep -A2 "k_countILb0" gpurun_out/${TAG}_variant_$i.nvcc.log | grep -E "Used|spill" | tr '\n' ' ' | sed -e 's/ptxas info *://g' -e 's/bytes//g'
   echo "== variant $i: env[$envs] flags[$flags]"
   env $envs python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-sr-sweep --no-lf 2> gpurun_out/${TAG}_variant_$i.log | tee gpurun_out/${TAG}_variant_$i.json | python -c "
 import json,sys
