@@ -44,7 +44,7 @@ inline size_t locate_smem_bytes(const DevIndex& ix, bool dense = false) { return
 template <bool STATS, bool DENSE>
 __global__ void __launch_bounds__(DENSE ? LOCATE_DENSE_THREADS : LOCATE_THREADS, DENSE ? LOCATE_DENSE_MIN_CTAS : LOCATE_MIN_CTAS)
 k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, uint32_t chunk, unsigned int* queue,
-         unsigned long long* stats, const uint64_t* __restrict__ hit_off, uint32_t n_pat, int32_t* __restrict__ status) {
+         unsigned long long* stats, const uint64_t* __restrict__ hit_off, uint32_t n_pat, int32_t* __restrict__ status, uint32_t row_base) {
     extern __shared__ uint32_t smem[];
     uint16_t* inv = reinterpret_cast<uint16_t*>(smem);
     uint16_t* cbase = inv + 32768;
@@ -124,10 +124,10 @@ k_locate(const DevIndex ix, uint32_t* __restrict__ rows_pos, uint32_t n_items, u
                     rows_pos[w] = 0xffffffffu;
                     active = false;
                     if (status) {
-                        uint32_t lo = 0, hi = n_pat;  // last pattern with hit_off[p] <= w
+                        uint32_t lo = 0, hi = n_pat;  // last pattern with hit_off[p] <= the hit's row in the whole call
                         while (hi - lo > 1u) {
                             const uint32_t mid = (lo + hi) >> 1;
-                            if (hit_off[mid] <= (uint64_t)w) lo = mid;
+                            if (hit_off[mid] <= (uint64_t)w + row_base) lo = mid;
                             else hi = mid;
                         }
                         atomicMax(status + lo, err == 2 ? 12 : 9);

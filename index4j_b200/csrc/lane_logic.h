@@ -241,6 +241,24 @@ FMGPU_HD EubOut eub_right_chunks(int32_t from, int32_t down_len, int32_t rel, in
     o.status = 0;
     o.value = 0;
     int32_t final_pos = -1, times = 1;
+    {
+        // Skip the chunks in which provably nothing happens, so the loop below only runs the chunk that ends the call (and at most
+        // one more): chunk t is uneventful while it is a full 4-char chunk before the end of the text (t < te), lies before the
+        // boundary's chunk (t < th) and — full chunks only get closer to the destination's end — does not overflow (t < to).
+        // The loop body itself stays the reference's arithmetic.  (A lane used to run this loop alone, ~30 trips per record,
+        // while the other 31 lanes of its warp waited: 38 % of k_extract's issued instructions.)
+        const int64_t l1 = (int64_t)length - 1;
+        const int64_t te = (int64_t)from >= l1 ? 1 : (l1 - from + 3) / 4;
+        const int64_t th = rel >= 0 ? (int64_t)rel / 4 + 1 : te;
+        const int64_t x = (int64_t)dst_len - offset - (right_only ? 0 : down_len);  // full chunk t overflows iff 4t - 1 >= x
+        const int64_t to = x <= 3 ? 1 : (x + 4) / 4;
+        int64_t t0 = te < th ? te : th;
+        if (to < t0) t0 = to;
+        if (t0 > 1) {
+            times = (int32_t)t0;
+            from += (int32_t)(4 * (t0 - 1));
+        }
+    }
     for (;;) {
         const int32_t prev = from;
         from += 4;

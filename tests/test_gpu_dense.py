@@ -103,3 +103,29 @@ def test_opt_out():
         assert ix.dense_sample_bytes() == 0 and ix.locate_sample_rate == 32
     finally:
         ix.close()
+
+
+@pytest.mark.parametrize("name", ["log1m_sr32", "q4_2m_sr32", "tiny600k_sr4"])
+def test_host_locate_in_chunks(name, monkeypatch):
+    """fmgpu_locate_batch walks the rows in chunks so that the download of chunk k overlaps the walks of chunk k + 1: same
+    positions and statuses as the oracle when a small batch is forced into several chunks (incl. the per-pattern status of
+    walks on which the reference throws, quirk Q4, which is looked up by the hit's row in the whole call)."""
+    from index4j_b200 import FmIndex
+    case = get_case(name)
+    ix = FmIndex.read(case.blob)
+    try:
+        chars, off = make_patterns(case.text, 1500, 1, 20, seed=5)
+        counts, _ = case.oracle.count_batch(chars, off, threads=4)
+        stride = int(max(1, min(200, counts.max())))
+        want_n, want_pos, want_st = case.oracle.locate_batch(chars, off, 200, stride, threads=4)
+        monkeypatch.setenv("FMGPU_LOCATE_CHUNK_ROWS", "997")
+        n, o, p, s = ix.locate_batch(chars, off, 200)
+        monkeypatch.delenv("FMGPU_LOCATE_CHUNK_ROWS")
+        n1, o1, p1, s1 = ix.locate_batch(chars, off, 200)
+        assert np.array_equal(n, want_n) and np.array_equal(s, want_st)
+        assert np.array_equal(n1, n) and np.array_equal(o1, o) and np.array_equal(p1, p) and np.array_equal(s1, s)
+        for i in range(want_n.size):
+            if want_st[i] == 0:
+                assert np.array_equal(p[int(o[i]): int(o[i + 1])], want_pos[i, : want_n[i]])
+    finally:
+        ix.close()
