@@ -122,7 +122,10 @@ def test_host_locate_in_chunks(name, monkeypatch):
         n, o, p, s = ix.locate_batch(chars, off, 200)
         monkeypatch.delenv("FMGPU_LOCATE_CHUNK_ROWS")
         n1, o1, p1, s1 = ix.locate_batch(chars, off, 200)
-        assert np.array_equal(n, want_n) and np.array_equal(s, want_st)
+        ok = want_st == 0  # where the reference throws, only the status is defined
+        assert np.array_equal(s, want_st) and np.array_equal(n[ok], want_n[ok])
+        if name == "q4_2m_sr32":
+            assert (want_st == 9).any()
         assert np.array_equal(n1, n) and np.array_equal(o1, o) and np.array_equal(p1, p) and np.array_equal(s1, s)
         for i in range(want_n.size):
             if want_st[i] == 0:
