@@ -24,6 +24,7 @@
 
 #include "../../include/fmgpu.h"
 #include "flatten.hpp"
+#include "host_pack.hpp"
 #include "jstream.hpp"
 #include "kernels.cuh"
 #include "kernels_lf.cuh"
@@ -89,6 +90,27 @@ struct Scratch {
     }
 };
 
+// page-locked host staging (packed transport of the host-pointer count call)
+struct Pinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 4096;
+        cudaError_t e = cudaHostAlloc(&p, want, cudaHostAllocPortable);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
 enum { CTRL_QUEUE = 0, CTRL_QUEUE2 = 1, CTRL_STATS = 2 /* u64 x FMGPU_N_STATS at word 2.. */, CTRL_WORDS = 64 };
 
 enum { KIND_FM = 0, KIND_WAVELET = 1, KIND_RRR = 2 };
@@ -106,7 +128,8 @@ struct CallCtx {
     cudaEvent_t pipe_in[PIPE_SLOTS] = {nullptr}, pipe_out[PIPE_SLOTS] = {nullptr}, pre_done[PIPE_SLOTS] = {nullptr};
     cudaEvent_t done = nullptr;  // end of the most recent call that used this context
     bool done_pending = false;   // ... which may still be running (a *_device call)
-    Scratch codes, pats, ctrl, ranges, in_a, in_b, out_a, out_b, out_c, tmp_a, tmp_b, order, bins, u8conv;
+    Scratch codes, pats, ctrl, ranges, in_a, in_b, in_c, out_a, out_b, out_c, tmp_a, tmp_b, order, bins, u8conv;
+    Pinned stage;
     struct CountCtx {
         Scratch pats, ctrl, order, bins;
     } cctx[COUNT_CTX - 1];
@@ -135,7 +158,8 @@ struct CallCtx {
         return 0;
     }
     void destroy() {
-        for (Scratch* s : {&codes, &pats, &ctrl, &ranges, &in_a, &in_b, &out_a, &out_b, &out_c, &tmp_a, &tmp_b, &order, &bins, &u8conv}) s->release();
+        for (Scratch* s : {&codes, &pats, &ctrl, &ranges, &in_a, &in_b, &in_c, &out_a, &out_b, &out_c, &tmp_a, &tmp_b, &order, &bins, &u8conv}) s->release();
+        stage.release();
         for (int i = 0; i < COUNT_CTX - 1; ++i) {
             for (Scratch* sc : {&cctx[i].pats, &cctx[i].ctrl, &cctx[i].order, &cctx[i].bins}) sc->release();
             if (cstream[i]) cudaStreamDestroy(cstream[i]);
@@ -1003,15 +1027,82 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
         }
         CU(cudaEventRecord(t0, cp));
     }
-    for (uint32_t k = 0; k < n_chunks; ++k) {  // all uploads are queued first: they only depend on the host buffers
+    // Packed transport (host_pack.hpp): char[] chunks whose chars all fit a byte cross PCIe as bytes + chunk-relative uint32
+    // offsets, narrowed by the pack pool into this context's page-locked staging buffer while earlier chunks are on the wire.
+    // FMGPU_HOST_PACK=0 sends the caller's arrays as they are (they should then be page-locked).
+    // FMGPU_HOST_PACK_MIN: smallest slice (chars) that is packed (tests force the path on small batches).
+    bool pack_enabled = true;
+    uint64_t pack_min = 1u << 20;
+    if (const char* e = getenv("FMGPU_HOST_PACK")) pack_enabled = atoi(e) != 0;
+    if (const char* e = getenv("FMGPU_HOST_PACK_MIN")) pack_min = (uint64_t)atoll(e);
+    const bool pack = pack_enabled && !utf8 && total >= pack_min && total > 0 && total < (1ull << 32) && fmgpu_host::PackPool::get().threads() > 0;
+    std::vector<std::atomic<uint32_t>> wide(pack ? n_chunks : 0);  // per chunk: OR of its chars (> 0xFF: the chunk is sent as it is)
+    struct JobGuard {  // whatever way this function is left, the pool must be done with the buffers above first
+        std::shared_ptr<fmgpu_host::PackJob> j;
+        ~JobGuard() {
+            if (j) j->wait_all();
+        }
+    } guard;
+    std::shared_ptr<fmgpu_host::PackJob>& job = guard.j;
+    uint8_t* h_bytes = nullptr;
+    uint32_t* h_off32 = nullptr;
+    uint8_t* d_bytes = nullptr;
+    uint32_t* d_off32 = nullptr;
+    constexpr uint32_t PACK_PARTS = 16;
+    if (pack) {
+        const size_t bytes_cap = ((size_t)total + 63) & ~(size_t)63;
+        CU(cx->stage.reserve(bytes_cap + ((size_t)n_pat + n_chunks + 1) * 4));
+        CU(cx->codes.reserve(bytes_cap + 64));
+        CU(cx->in_c.reserve(((size_t)n_pat + n_chunks + 1) * 4));
+        h_bytes = (uint8_t*)cx->stage.p;
+        h_off32 = (uint32_t*)(h_bytes + bytes_cap);
+        d_bytes = (uint8_t*)cx->codes.p;
+        d_off32 = (uint32_t*)cx->in_c.p;
+        for (auto& w : wide) w.store(0, std::memory_order_relaxed);
+        const uint16_t* h16 = (const uint16_t*)in;
+        std::atomic<uint32_t>* wide_p = wide.data();
+        job = fmgpu_host::PackPool::get().submit(n_chunks, PACK_PARTS, [=](uint32_t k, uint32_t part) {
+            const uint32_t lo = lo_pat + (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = lo_pat + (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
+            const uint64_t c0 = pat_off[lo], c1 = pat_off[hi];
+            const uint64_t a = c0 + (c1 - c0) * part / PACK_PARTS, b = c0 + (c1 - c0) * (part + 1) / PACK_PARTS;
+            const uint32_t m = fmgpu_host::narrow_u16(h16 + a, h_bytes + (a - base), (size_t)(b - a));
+            if (m > 0xffu) wide_p[k].fetch_or(m, std::memory_order_relaxed);
+            // the chunk's offsets, relative to its first char: hi - lo + 1 entries at slot (lo - lo_pat) + k
+            const uint32_t n_off = hi - lo + 1;
+            const uint32_t i0 = (uint32_t)((uint64_t)n_off * part / PACK_PARTS), i1 = (uint32_t)((uint64_t)n_off * (part + 1) / PACK_PARTS);
+            uint32_t* dst = h_off32 + (lo - lo_pat) + k;
+            for (uint32_t i = i0; i < i1; ++i) dst[i] = (uint32_t)(pat_off[lo + i] - c0);
+        });
+    }
+    // Uploads run ahead of the kernels: before the kernels of chunk k are enqueued, every chunk that is ready (all of them for
+    // the direct path; with the packed transport those the pool has finished, and chunk k itself once it has) is put on the
+    // copy stream.
+    bool narrow_k[CallCtx::PIPE_SLOTS] = {false};
+    auto upload_chunk = [&](uint32_t k) -> int {
         const uint32_t lo = lo_pat + (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = lo_pat + (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
         const uint64_t c0 = pat_off[lo], c1 = pat_off[hi];
-        if (c1 > c0) CU(cudaMemcpyAsync(d_in + c0 * unit, h_in + c0 * unit, (size_t)(c1 - c0) * unit, cudaMemcpyHostToDevice, cp));
-        CU(cudaMemcpyAsync(d_off + lo, pat_off + lo, ((size_t)(hi - lo) + 1) * 8, cudaMemcpyHostToDevice, cp));
+        if (pack) {
+            job->wait_group(k);
+            narrow_k[k] = wide[k].load(std::memory_order_relaxed) <= 0xffu;
+        }
+        if (narrow_k[k]) {
+            const uint32_t slot = (lo - lo_pat) + k, n_off = hi - lo + 1;
+            if (c1 > c0) CU(cudaMemcpyAsync(d_bytes + (c0 - base), h_bytes + (c0 - base), (size_t)(c1 - c0), cudaMemcpyHostToDevice, cp));
+            CU(cudaMemcpyAsync(d_off32 + slot, h_off32 + slot, (size_t)n_off * 4, cudaMemcpyHostToDevice, cp));
+        } else {
+            if (c1 > c0) CU(cudaMemcpyAsync(d_in + c0 * unit, h_in + c0 * unit, (size_t)(c1 - c0) * unit, cudaMemcpyHostToDevice, cp));
+            CU(cudaMemcpyAsync(d_off + lo, pat_off + lo, ((size_t)(hi - lo) + 1) * 8, cudaMemcpyHostToDevice, cp));
+        }
         CU(cudaEventRecord(cx->pipe_in[k], cp));
         if (trace) CU(cudaEventRecord(t_in[k], cp));
-    }
+        return 0;
+    };
+    uint32_t next_up = 0;
     for (uint32_t k = 0; k < n_chunks; ++k) {
+        while (next_up < n_chunks && (next_up <= k || !pack || job->done[next_up].load(std::memory_order_acquire) >= PACK_PARTS)) {
+            if (int e = upload_chunk(next_up)) return e;
+            ++next_up;
+        }
         const uint32_t lo = lo_pat + (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = lo_pat + (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
         const int ctx = (int)(k % (uint32_t)n_ctx);
         cudaStream_t cs = ctx ? cx->cstream[ctx - 1] : st;
@@ -1022,9 +1113,17 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
         if (k >= (uint32_t)n_ctx) CU(cudaStreamWaitEvent(ps, cx->pipe_out[k - n_ctx], 0));
         Utf8Src u8{d_in, d_chars, d_conv + (lo - lo_pat), d_conv + n_pat + (lo - lo_pat)};
         if (trace) CU(cudaEventRecord(t_k0[k], ps));
+        if (narrow_k[k]) {  // bytes + relative offsets -> the chars and offsets the pre-pass reads
+            const uint64_t c0 = pat_off[lo], c1 = pat_off[hi];
+            const uint32_t slot = (lo - lo_pat) + k, n_off = hi - lo + 1;
+            const uint64_t work = (c1 - c0) > n_off ? (c1 - c0) : n_off;
+            k_unpack_narrow<<<prepass_grid(work / 2 + 1, rp->sm_count), 256, 0, ps>>>(d_bytes + (c0 - base), c1 - c0, d_chars + c0, d_off32 + slot, n_off,
+                                                                                   c0, d_off + lo);
+        }
         rc = count_on_stream(ix, rp, cx, d_chars, d_off + lo, hi - lo, d_counts + lo, d_status + lo, nullptr, cs, k < (uint32_t)n_ctx, ctx,
                              utf8 ? &u8 : nullptr, ps, cx->pre_done[k], pipe_threads);
         if (rc) return rc;
+        if (narrow_k[k]) cx->last_launches += 1;
         CU(cudaEventRecord(cx->pipe_out[k], cs));
         if (trace) CU(cudaEventRecord(t_k1[k], cs));
         CU(cudaStreamWaitEvent(cx->down_stream, cx->pipe_out[k], 0));

@@ -77,6 +77,16 @@ __global__ void __launch_bounds__(256) k_prepass(const uint16_t* __restrict__ ch
     for (uint32_t i = threadIdx.x; i < LEN_BINS; i += blockDim.x)
         if (h[i]) atomicAdd(&bins[i], h[i]);
 }
+// Packed transport of the host-pointer count call (host_pack.hpp): a chunk arrived as one byte per char and chunk-relative
+// uint32 offsets; widen both to what the pre-pass reads (UTF-16 units at the chunk's absolute char offsets, uint64 offsets).
+__global__ void __launch_bounds__(256) k_unpack_narrow(const uint8_t* __restrict__ bytes, uint64_t n_chars, uint16_t* __restrict__ chars,
+                                                       const uint32_t* __restrict__ off32, uint32_t n_off, uint64_t base,
+                                                       uint64_t* __restrict__ off64) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = t; i < n_chars; i += stride) chars[i] = bytes[i];
+    for (uint64_t i = t; i < n_off; i += stride) off64[i] = base + off32[i];
+}
+
 // exclusive scan of the bins, longest patterns first (they are the long poles of the launch).  256 threads x 4 bins: small
 // enough to share an SM with resident k_count CTAs of an earlier chunk (the chunked host call overlaps launches).
 constexpr uint32_t SCAN_THREADS = 256;
