@@ -455,6 +455,21 @@ def main():
         ix.count_batch_into(h_chars, h_off, h_counts, h_status)
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(h_counts, d_counts.cpu().numpy())
+    # the same call with the packed transport switched off (the caller's pinned arrays cross PCIe as they are)
+    from index4j_b200.fm_index import native
+    e2e_direct_s = None
+    pack_threads = int(native().fmgpu_host_pack_threads())
+    if pack_threads > 0 and os.environ.get("FMGPU_HOST_PACK", "1") != "0":
+        os.environ["FMGPU_HOST_PACK"] = "0"
+        try:
+            ix.count_batch_into(h_chars, h_off, h_counts, h_status)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                ix.count_batch_into(h_chars, h_off, h_counts, h_status)
+            e2e_direct_s = time.perf_counter() - t0
+        finally:
+            del os.environ["FMGPU_HOST_PACK"]
 
     # the same batch as UTF-8 byte patterns through fmgpu_count_batch_utf8 (the reference's convertBytePatternToCharPattern +
     # count, FmIndex.java:239-298): 1 byte per char crosses PCIe, decoding happens in the device pre-pass
@@ -641,8 +656,15 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic", "config": workload_config(args), "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(chars.nbytes + off.nbytes),
-                    "d2h_bytes_per_step": int(h_counts.nbytes + h_status.nbytes)},
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": int(chars.size + 4 * (off.size + 8)) if e2e_direct_s is not None else int(chars.nbytes + off.nbytes),
+                    "caller_input_bytes_per_step": int(chars.nbytes + off.nbytes),
+                    "d2h_bytes_per_step": int(h_counts.nbytes + h_status.nbytes),
+                    "transport": ("packed: %d host threads narrow the Latin-1 char[] to bytes + uint32 offsets into pinned staging (%d bytes cross PCIe per step)"
+                                  % (pack_threads, int(chars.size + 4 * (off.size + 8))) if e2e_direct_s is not None
+                                  else "direct: the caller's pinned arrays cross PCIe as they are"),
+                    "direct_rank0": ({"value": n_pat * args.steps / e2e_direct_s, "unit": UNIT, "what": "the same call with FMGPU_HOST_PACK=0"}
+                                     if e2e_direct_s is not None else None)},
             "e2e_utf8": ({"value": world * n_pat * args.steps / (utf8_ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": utf8["h2d"],
                           "d2h_bytes_per_step": int(h_counts.nbytes + h_status.nbytes),
                           "call": "fmgpu_count_batch_utf8: the same patterns as UTF-8 bytes (1 byte per char), decoded on the device"}

@@ -107,7 +107,14 @@ int fmgpu_host_alloc(size_t bytes, void** out);
 int fmgpu_host_free(void* p);
 
 /* FmIndex.count(char[] p, int off, int len)  FM:455-474 — one result per pattern.
- * status_out may be NULL. */
+ * status_out may be NULL.
+ * Transport of the host-pointer call: it is bound by the upload of the chars (2 bytes each), so on a single-device handle a pool
+ * of host threads narrows every chunk of the batch whose chars all fit a byte (Latin-1: log text) to bytes + chunk-relative
+ * uint32 offsets into the library's own page-locked staging buffer while earlier chunks are on the wire, and the device widens
+ * them again; other chunks go as they are.  The caller's arrays need not be page-locked for the packed chunks.  Pool size =
+ * fmgpu_host_pack_threads(): half the hardware threads (divided by LOCAL_WORLD_SIZE), at most 8, none below 6 — then, and with
+ * FMGPU_HOST_PACK=0, every chunk goes as it is; FMGPU_PACK_THREADS overrides the size. */
+int32_t fmgpu_host_pack_threads(void);
 int fmgpu_count_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat,
                       int32_t* counts_out, int32_t* status_out);
 int fmgpu_count_batch_device(fmgpu_index* idx, const uint16_t* d_chars, const uint64_t* d_pat_off, uint64_t total_chars,

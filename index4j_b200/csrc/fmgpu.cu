@@ -10,6 +10,7 @@
 // caller's outputs.
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -928,6 +929,8 @@ void fmgpu_layout_bytes(const fmgpu_index* ix, uint64_t out8[8]) {
 
 // Page-locked host memory for the host-pointer batch calls: cudaMemcpyAsync only overlaps with the kernels (and reaches the
 // PCIe rate) from page-locked buffers.
+int32_t fmgpu_host_pack_threads(void) { return (int32_t)fmgpu_host::PackPool::get().threads(); }
+
 int fmgpu_host_register(void* p, size_t bytes) {
     if (!p || !bytes) return fail(FMGPU_ERR_ARG, "null argument");
     CU(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
@@ -974,7 +977,7 @@ namespace {
 // pattern's dependent chain (~0.2 ms), so consecutive chunks run on different compute streams and the next chunk's CTAs fill
 // the SMs while the previous chunk's last warps drain.  Chunk chars land at their offsets relative to the slice's first char.
 int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, const uint64_t* pat_off, uint32_t lo_pat, uint32_t hi_pat,
-                       int32_t* counts_out, int32_t* status_out) {
+                       int32_t* counts_out, int32_t* status_out, bool allow_pack) {
     Replica* rp = L.r;
     CallCtx* cx = L.c;
     CU(cudaSetDevice(rp->device));
@@ -1016,10 +1019,14 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
     const uint8_t* h_in = (const uint8_t*)in;
     // FMGPU_PIPE_TRACE=1: per-chunk timeline of the call on stderr (timing events; diagnostic only)
     const bool trace = getenv("FMGPU_PIPE_TRACE") != nullptr;
-    cudaEvent_t t0 = nullptr, t_in[CallCtx::PIPE_SLOTS], t_k0[CallCtx::PIPE_SLOTS], t_k1[CallCtx::PIPE_SLOTS], t_out[CallCtx::PIPE_SLOTS];
+    const auto host_t0 = std::chrono::steady_clock::now();
+    auto host_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0).count(); };
+    double h_up[CallCtx::PIPE_SLOTS] = {0}, h_kern[CallCtx::PIPE_SLOTS] = {0}, h_submit = 0;
+    cudaEvent_t t0 = nullptr, t_in0[CallCtx::PIPE_SLOTS], t_in[CallCtx::PIPE_SLOTS], t_k0[CallCtx::PIPE_SLOTS], t_k1[CallCtx::PIPE_SLOTS], t_out[CallCtx::PIPE_SLOTS];
     if (trace) {
         CU(cudaEventCreate(&t0));
         for (uint32_t k = 0; k < n_chunks; ++k) {
+            CU(cudaEventCreate(&t_in0[k]));
             CU(cudaEventCreate(&t_in[k]));
             CU(cudaEventCreate(&t_k0[k]));
             CU(cudaEventCreate(&t_k1[k]));
@@ -1032,10 +1039,11 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
     // FMGPU_HOST_PACK=0 sends the caller's arrays as they are (they should then be page-locked).
     // FMGPU_HOST_PACK_MIN: smallest slice (chars) that is packed (tests force the path on small batches).
     bool pack_enabled = true;
+    const bool pack_help = !(getenv("FMGPU_PACK_HELP") && atoi(getenv("FMGPU_PACK_HELP")) == 0);  // the caller's thread packs too
     uint64_t pack_min = 1u << 20;
     if (const char* e = getenv("FMGPU_HOST_PACK")) pack_enabled = atoi(e) != 0;
     if (const char* e = getenv("FMGPU_HOST_PACK_MIN")) pack_min = (uint64_t)atoll(e);
-    const bool pack = pack_enabled && !utf8 && total >= pack_min && total > 0 && total < (1ull << 32) && fmgpu_host::PackPool::get().threads() > 0;
+    const bool pack = allow_pack && pack_enabled && !utf8 && total >= pack_min && total > 0 && total < (1ull << 32) && fmgpu_host::PackPool::get().threads() > 0;
     std::vector<std::atomic<uint32_t>> wide(pack ? n_chunks : 0);  // per chunk: OR of its chars (> 0xFF: the chunk is sent as it is)
     struct JobGuard {  // whatever way this function is left, the pool must be done with the buffers above first
         std::shared_ptr<fmgpu_host::PackJob> j;
@@ -1071,7 +1079,8 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
             const uint32_t n_off = hi - lo + 1;
             const uint32_t i0 = (uint32_t)((uint64_t)n_off * part / PACK_PARTS), i1 = (uint32_t)((uint64_t)n_off * (part + 1) / PACK_PARTS);
             uint32_t* dst = h_off32 + (lo - lo_pat) + k;
-            for (uint32_t i = i0; i < i1; ++i) dst[i] = (uint32_t)(pat_off[lo + i] - c0);
+            for (uint32_t i = i0; i < i1; ++i) _mm_stream_si32((int*)(dst + i), (int)(uint32_t)(pat_off[lo + i] - c0));  // (non-temporal, as the bytes)
+            _mm_sfence();
         });
     }
     // Uploads run ahead of the kernels: before the kernels of chunk k are enqueued, every chunk that is ready (all of them for
@@ -1082,9 +1091,12 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
         const uint32_t lo = lo_pat + (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = lo_pat + (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
         const uint64_t c0 = pat_off[lo], c1 = pat_off[hi];
         if (pack) {
-            job->wait_group(k);
+            if (pack_help) job->wait_group(k);
+            else
+                while (job->done[k].load(std::memory_order_acquire) < PACK_PARTS) std::this_thread::yield();
             narrow_k[k] = wide[k].load(std::memory_order_relaxed) <= 0xffu;
         }
+        if (trace) CU(cudaEventRecord(t_in0[k], cp));
         if (narrow_k[k]) {
             const uint32_t slot = (lo - lo_pat) + k, n_off = hi - lo + 1;
             if (c1 > c0) CU(cudaMemcpyAsync(d_bytes + (c0 - base), h_bytes + (c0 - base), (size_t)(c1 - c0), cudaMemcpyHostToDevice, cp));
@@ -1095,8 +1107,22 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
         }
         CU(cudaEventRecord(cx->pipe_in[k], cp));
         if (trace) CU(cudaEventRecord(t_in[k], cp));
+        if (trace) h_up[k] = host_ms();
         return 0;
     };
+    auto download_chunk = [&](uint32_t k) -> int {
+        const uint32_t lo = lo_pat + (uint32_t)((uint64_t)n_pat * k / n_chunks), hi = lo_pat + (uint32_t)((uint64_t)n_pat * (k + 1) / n_chunks);
+        CU(cudaStreamWaitEvent(cx->down_stream, cx->pipe_out[k], 0));
+        if (hi > lo) {
+            CU(cudaMemcpyAsync(counts_out + lo, d_counts + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, cx->down_stream));
+            if (status_out)
+                CU(cudaMemcpyAsync(status_out + lo, d_status + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, cx->down_stream));
+        }
+        if (trace) CU(cudaEventRecord(t_out[k], cx->down_stream));
+        return 0;
+    };
+    if (trace) h_submit = host_ms();
+    if (pack && getenv("FMGPU_PACK_SYNC")) job->wait_all();  // diagnostic: pack everything before the first upload
     uint32_t next_up = 0;
     for (uint32_t k = 0; k < n_chunks; ++k) {
         while (next_up < n_chunks && (next_up <= k || !pack || job->done[next_up].load(std::memory_order_acquire) >= PACK_PARTS)) {
@@ -1126,24 +1152,35 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
         if (narrow_k[k]) cx->last_launches += 1;
         CU(cudaEventRecord(cx->pipe_out[k], cs));
         if (trace) CU(cudaEventRecord(t_k1[k], cs));
-        CU(cudaStreamWaitEvent(cx->down_stream, cx->pipe_out[k], 0));
-        if (hi > lo) {
-            CU(cudaMemcpyAsync(counts_out + lo, d_counts + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, cx->down_stream));
-            if (status_out)
-                CU(cudaMemcpyAsync(status_out + lo, d_status + lo, (size_t)(hi - lo) * 4, cudaMemcpyDeviceToHost, cx->down_stream));
+        // The downloads of a packed call are enqueued after its last upload (below): streams share the device's few hardware
+        // queues, and a download that waits for its kernel at the head of the queue it shares with the copy stream held back
+        // the uploads enqueued after it (measured: the last chunk's 5 MB upload took 0.7 ms).  The direct path enqueues all
+        // uploads before anything else, so its downloads can follow their kernels at once.
+        if (!pack) {
+            if (int e = download_chunk(k)) return e;
         }
-        if (trace) CU(cudaEventRecord(t_out[k], cx->down_stream));
+        if (trace) h_kern[k] = host_ms();
     }
+    if (pack)
+        for (uint32_t k = 0; k < n_chunks; ++k)
+            if (int e = download_chunk(k)) return e;
     if (trace) {
+        const double h_enq = host_ms();
         CU(cudaStreamSynchronize(cx->down_stream));
+        fprintf(stderr, "[fmgpu trace] host: pack job submitted %.3f ms, all enqueued %.3f ms, device done %.3f ms after entry (packed transport %d)\n",
+                h_submit, h_enq, host_ms(), (int)pack);
+        for (uint32_t k = 0; k < n_chunks; ++k)
+            fprintf(stderr, "[fmgpu trace] host: chunk %u upload enqueued %.3f ms, kernels enqueued %.3f ms\n", k, h_up[k], h_kern[k]);
         for (uint32_t k = 0; k < n_chunks; ++k) {
-            float a = 0, b = 0, c = 0, d = 0;
+            float a0 = 0, a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a0, t0, t_in0[k]);
             cudaEventElapsedTime(&a, t0, t_in[k]);
             cudaEventElapsedTime(&b, t0, t_k0[k]);
             cudaEventElapsedTime(&c, t0, t_k1[k]);
             cudaEventElapsedTime(&d, t0, t_out[k]);
-            fprintf(stderr, "[fmgpu trace] device %d chunk %u: h2d done %.3f ms, kernels %.3f .. %.3f ms, d2h done %.3f ms\n", rp->device, k, a, b,
+            fprintf(stderr, "[fmgpu trace] device %d chunk %u: h2d %.3f .. %.3f ms, kernels %.3f .. %.3f ms, d2h done %.3f ms\n", rp->device, k, a0, a, b,
                     c, d);
+            cudaEventDestroy(t_in0[k]);
             cudaEventDestroy(t_in[k]);
             cudaEventDestroy(t_k0[k]);
             cudaEventDestroy(t_k1[k]);
@@ -1177,7 +1214,8 @@ int count_host(fmgpu_index* ix, const void* in, size_t unit, const uint64_t* pat
     return run_on_replicas(ix, R, [&](size_t r) -> int {
         Lease L(ix->reps[r].get());
         if (L.rc) return L.rc;
-        int rc = count_host_enqueue(ix, L, in, unit, pat_off, slice_lo(n_pat, r, R), slice_lo(n_pat, r + 1, R), counts_out, status_out);
+        // (a multi-replica call feeds several PCIe links at once: together they outrun the host's packing rate, so it goes direct)
+        int rc = count_host_enqueue(ix, L, in, unit, pat_off, slice_lo(n_pat, r, R), slice_lo(n_pat, r + 1, R), counts_out, status_out, R == 1);
         const int w = count_host_wait(L);  // wait for whatever was enqueued, also after a failure
         return rc ? rc : w;
     });

@@ -103,6 +103,7 @@ def native():
         L.fmgpu_num_devices.restype = i32
         L.fmgpu_device_at.argtypes = [vp, i32]
         L.fmgpu_device_at.restype = i32
+        L.fmgpu_host_pack_threads.restype = i32
         L.fmgpu_host_register.argtypes = [vp, C.c_size_t]
         L.fmgpu_host_unregister.argtypes = [vp]
         L.fmgpu_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]

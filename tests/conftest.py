@@ -10,6 +10,10 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests", "suppo
         sys.path.insert(0, p)
 
 
+# the packed transport of fmgpu_count_batch needs its host thread pool, whatever the size of the test machine
+os.environ.setdefault("FMGPU_PACK_THREADS", "4")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200 box)")
 
