@@ -112,7 +112,7 @@ int fmgpu_host_free(void* p);
  * of host threads narrows every chunk of the batch whose chars all fit a byte (Latin-1: log text) to bytes + chunk-relative
  * uint32 offsets into the library's own page-locked staging buffer while earlier chunks are on the wire, and the device widens
  * them again; other chunks go as they are.  The caller's arrays need not be page-locked for the packed chunks.  Pool size =
- * fmgpu_host_pack_threads(): half the hardware threads (divided by LOCAL_WORLD_SIZE), at most 8, none below 6 — then, and with
+ * fmgpu_host_pack_threads(): half the hardware threads (divided by LOCAL_WORLD_SIZE), at most 8, none below 8 — then, and with
  * FMGPU_HOST_PACK=0, every chunk goes as it is; FMGPU_PACK_THREADS overrides the size. */
 int32_t fmgpu_host_pack_threads(void);
 int fmgpu_count_batch(fmgpu_index* idx, const uint16_t* chars, const uint64_t* pat_off, uint32_t n_pat,

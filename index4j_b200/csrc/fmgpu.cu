@@ -1152,18 +1152,9 @@ int count_host_enqueue(fmgpu_index* ix, Lease& L, const void* in, size_t unit, c
         if (narrow_k[k]) cx->last_launches += 1;
         CU(cudaEventRecord(cx->pipe_out[k], cs));
         if (trace) CU(cudaEventRecord(t_k1[k], cs));
-        // The downloads of a packed call are enqueued after its last upload (below): streams share the device's few hardware
-        // queues, and a download that waits for its kernel at the head of the queue it shares with the copy stream held back
-        // the uploads enqueued after it (measured: the last chunk's 5 MB upload took 0.7 ms).  The direct path enqueues all
-        // uploads before anything else, so its downloads can follow their kernels at once.
-        if (!pack) {
-            if (int e = download_chunk(k)) return e;
-        }
+        if (int e = download_chunk(k)) return e;
         if (trace) h_kern[k] = host_ms();
     }
-    if (pack)
-        for (uint32_t k = 0; k < n_chunks; ++k)
-            if (int e = download_chunk(k)) return e;
     if (trace) {
         const double h_enq = host_ms();
         CU(cudaStreamSynchronize(cx->down_stream));

@@ -124,14 +124,14 @@ public:
 private:
     // Pool size: half the hardware threads, at most 8 — divided by LOCAL_WORLD_SIZE when several processes share the box (one
     // process per GPU under torchrun).  Packing only pays with enough threads to outrun the PCIe link (measured on the B200 box:
-    // 4 threads 0.60 G patterns/s = the direct path, 8 threads 0.77 G/s), so a budget below 6 threads means no pool and no
-    // packing.  FMGPU_PACK_THREADS overrides (0 = off).
+    // 4 threads 0.60 G patterns/s = the direct path, 8 threads 0.77 G/s, 12-15 threads no better), so a budget below 8 threads
+    // means no pool and no packing.  FMGPU_PACK_THREADS overrides (0 = off).
     PackPool() {
         int share = 1;
         if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = atoi(e) > 0 ? atoi(e) : 1;
         int n = (int)std::thread::hardware_concurrency() / 2 / share;
         if (n > 8) n = 8;
-        if (n < 6) n = 0;
+        if (n < 8) n = 0;
         if (const char* e = getenv("FMGPU_PACK_THREADS")) n = atoi(e);
         if (n < 0) n = 0;
         if (n > 64) n = 64;
