@@ -79,8 +79,8 @@ FMGPU_HD uint32_t count_step(const DevIndex& ix, const CountTables& T, uint32_t 
     if (STATS) cnt.loads += split ? 2u : 1u;
     const uint32_t kind_b = cell_kind(cell_b);
     const uint32_t kind_a = on_a ? cell_kind(cell_a) : (uint32_t)CELL_CONST;
-    const bool need_b = kind_b == CELL_OCC_LIST || kind_b == CELL_OCC_BITS;
-    const bool need_a = kind_a == CELL_OCC_LIST || kind_a == CELL_OCC_BITS;
+    const bool need_b = kind_b >= CELL_OCC_FIRST;
+    const bool need_a = kind_a >= CELL_OCC_FIRST;
     const uint32_t err = ((!need_b && kind_b != CELL_CONST && kind_b != CELL_RUN) || (!need_a && kind_a != CELL_CONST && kind_a != CELL_RUN)) ? 1u : 0u;
 
     // stage 1: one occurrence record per track that needs one

@@ -95,6 +95,7 @@ struct FlatIndex {
     std::vector<Rec32> sectors, occ, blocks, nodes, sgroups, sa, isa;
     std::vector<uint32_t> soffsets;
     int32_t alphabet_length = 0;
+    std::vector<uint32_t> occ_base, occ_used;  // per block: first occurrence record reserved by the sizing pass / records in use
 };
 
 // Explicit shape of one block's Huffman-shaped wavelet tree, rebuilt from the variable-size
@@ -308,21 +309,42 @@ inline void put_cell(fmgpu::Cell8& c, uint32_t kind, uint32_t value) {
 
 // occurrence structure of one (block, symbol) pair: positions (ascending, block-relative) of the symbol's occurrences, its
 // code length in the block's tree -> the cell's kind / record pointer and its records in F.occ[at ..] (layout.h)
-inline void put_occ(fmgpu::Cell8& cell, const std::vector<uint16_t>& pos, uint32_t code_len, uint32_t block_size, uint32_t at,
-                    std::vector<Rec32>& occ) {
+inline uint32_t put_occ(fmgpu::Cell8& cell, const std::vector<uint16_t>& pos, uint32_t code_len, uint32_t block_size, uint32_t at,
+                        std::vector<Rec32>& occ) {
     const uint32_t n = (uint32_t)pos.size();
-    const uint32_t kind = occ_kind(n, block_size);
+    uint32_t kind = occ_kind(n, block_size);
     if (at > fmgpu::CELL_PTR_MASK) throw FormatError("more occurrence records than a cell can address");
-    cell.info = (kind << fmgpu::CELL_KIND_SHIFT) | at;
+    auto put16 = [](Rec32& R, uint32_t k, uint32_t v) {  // u16 slot k of a record
+        uint32_t& w = R.w[k >> 1];
+        w = (k & 1u) ? ((w & 0x0000ffffu) | (v << 16)) : ((w & 0xffff0000u) | v);
+    };
     if (kind == fmgpu::CELL_OCC_LIST) {
+        cell.info = (kind << fmgpu::CELL_KIND_SHIFT) | at;
         Rec32& R = occ[(size_t)at];
-        for (uint32_t k = 0; k < 16; ++k) {
-            const uint32_t v = k < fmgpu::OCC_LIST_MAX ? (k < n ? pos[k] : 0xffffu) : (code_len & 0xffffu);
-            uint32_t& w = R.w[k >> 1];
-            w = (k & 1u) ? ((w & 0x0000ffffu) | (v << 16)) : ((w & 0xffff0000u) | v);
-        }
-        return;
+        for (uint32_t k = 0; k < 16; ++k) put16(R, k, k < fmgpu::OCC_LIST_MAX ? (k < n ? pos[k] : 0xffffu) : (code_len & 0xffffu));
+        return 1;
     }
+    // position lists over fixed ranges where no range holds more than 14 occurrences: the largest range that qualifies
+    for (uint32_t shift : {12u, 10u}) {
+        const uint32_t R = 1u << shift;
+        if (R >= block_size) continue;
+        bool ok = true;
+        for (uint32_t i = fmgpu::OCC_RANGE_MAX; i < n && ok; ++i) ok = ((uint32_t)pos[i] >> shift) != ((uint32_t)pos[i - fmgpu::OCC_RANGE_MAX] >> shift);
+        if (!ok) continue;
+        kind = shift == 12u ? fmgpu::CELL_OCC_R4K : fmgpu::CELL_OCC_R1K;
+        cell.info = (kind << fmgpu::CELL_KIND_SHIFT) | at;
+        const uint32_t nrec = (block_size + R - 1) >> shift;
+        size_t i = 0;
+        for (uint32_t q = 0; q < nrec; ++q) {
+            Rec32& X = occ[(size_t)at + q];
+            memset(&X, 0xff, sizeof X);
+            X.w[0] = (uint32_t)i | ((code_len & 0xffu) << 24);
+            uint32_t k = 2;  // slots 2..15 = w1..w7
+            while (i < n && ((uint32_t)pos[i] >> shift) == q) put16(X, k++, pos[i++]);
+        }
+        return nrec;
+    }
+    cell.info = (kind << fmgpu::CELL_KIND_SHIFT) | at;
     const uint32_t nrec = block_size / fmgpu::OCC_BITS_PER_REC + 1;
     size_t i = 0;
     for (uint32_t q = 0; q < nrec; ++q) {
@@ -336,6 +358,7 @@ inline void put_occ(fmgpu::Cell8& cell, const std::vector<uint16_t>& pos, uint32
             ++i;
         }
     }
+    return nrec;
 }
 
 inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, FlatIndex& F) {
@@ -553,14 +576,19 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
                             // sized for one structure per leaf
                             put_cell(cell, fmgpu::CELL_THROW, 0);
                         } else {
-                            occ_next[(size_t)b] += need;
-                            put_occ(cell, pos, (uint32_t)L.len, bsize, at, F.occ);
+                            // (`need` is the upper bound the sizing pass reserved; range lists use less: compact_occ closes the gaps)
+                            occ_next[(size_t)b] += put_occ(cell, pos, (uint32_t)L.len, bsize, at, F.occ);
                         }
                     }
                 }
             }
             if (in_range && !absent) next_present = b;
         }
+    }
+
+    for (size_t b = 0; b < nblk; ++b) {
+        F.occ_base[(size_t)P.first_block + b] = (uint32_t)block_occ_base[b];
+        F.occ_used[(size_t)P.first_block + b] = trees[b].h != 0 ? occ_next[b] - (uint32_t)block_occ_base[b] : 0u;
     }
 
     // single-symbol blocks: the LF step needs rank(j, c') for the symbol c' inverseSelect decodes (low byte only) and
@@ -581,6 +609,31 @@ inline void flatten_superblock(const WfbbStream& W, size_t sb, const SbPlan& P, 
         D.w[2] = cell.value;
         D.w[3] = kind;
     }
+}
+
+// The sizing pass reserves every (block, symbol) pair's occurrence records by an upper bound (a bit vector unless the pair has
+// <= 15 occurrences); pairs that ended up as range lists use fewer.  Close the gaps: blocks keep their order, records move down,
+// the cells' record pointers follow.
+inline void compact_occ(FlatIndex& F, uint32_t sigma) {
+    const size_t n_blocks = F.occ_base.size();
+    uint32_t at = 0;
+    for (size_t b = 0; b < n_blocks; ++b) {
+        const uint32_t used = F.occ_used[b], from = F.occ_base[b];
+        if (used == 0) continue;
+        const uint32_t delta = from - at;
+        if (delta) {
+            memmove(&F.occ[at], &F.occ[from], (size_t)used * sizeof(Rec32));
+            fmgpu::Cell8* row = &F.cells[b * (size_t)sigma];
+            for (uint32_t c = 0; c < sigma; ++c)
+                if ((row[c].info >> fmgpu::CELL_KIND_SHIFT) >= fmgpu::CELL_OCC_FIRST) row[c].info -= delta;
+        }
+        at += used;
+    }
+    F.occ.resize((size_t)at + 1);
+    F.occ.back() = Rec32{};
+    F.occ.shrink_to_fit();
+    std::vector<uint32_t>().swap(F.occ_base);
+    std::vector<uint32_t>().swap(F.occ_used);
 }
 
 inline void flatten_sampled(const RrrStream& r, FlatIndex& F) {
@@ -717,9 +770,12 @@ inline void flatten(const FmStream& fm, int threads, FlatIndex& F, bool wavelet_
     F.nodes.assign((size_t)nodes_total + 1, Rec32{});
     F.occ.assign((size_t)occ_total + 1, Rec32{});
     F.blocks.assign((size_t)blocks_total + 1, Rec32{});
+    F.occ_base.assign((size_t)blocks_total, 0);
+    F.occ_used.assign((size_t)blocks_total, 0);
 
     // pass 2: fill
     parallel_sbs(nsb, threads, [&](size_t sb) { flatten_superblock(W, sb, plan[sb], F); });
+    compact_occ(F, (uint32_t)W.sigma);
 
     if (wavelet_only) {
         F.sgroups.assign(1, Rec32{});

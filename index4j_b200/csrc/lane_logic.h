@@ -70,7 +70,8 @@ FMGPU_HD uint32_t count_u16_below(const Rec32& x, int first, int n_words, uint32
 FMGPU_HD uint32_t cell_kind(const Cell8& c) { return c.info >> CELL_KIND_SHIFT; }
 // the ONE record an OCC_* cell needs for position r of its block
 FMGPU_HD const Rec32* occ_record(const DevIndex& ix, const Cell8& cell, uint32_t kind, uint32_t r) {
-    return ix.occ + ((cell.info & CELL_PTR_MASK) + (kind == CELL_OCC_BITS ? r / OCC_BITS_PER_REC : 0u));
+    const uint32_t q = kind == CELL_OCC_BITS ? r / OCC_BITS_PER_REC : (kind == CELL_OCC_R1K ? r >> 10 : (kind == CELL_OCC_R4K ? r >> 12 : 0u));
+    return ix.occ + ((cell.info & CELL_PTR_MASK) + q);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -113,8 +114,13 @@ FMGPU_HD uint32_t occ_in_record(const Rec32& y, uint32_t kind, uint32_t r, uint3
         return n;
     }
     *len = y.w[0] >> 24;
-    const uint32_t b = r % OCC_BITS_PER_REC;
     uint32_t n = y.w[0] & 0xffffffu;
+    if (kind != CELL_OCC_BITS) {  // range list: 14 positions in w1..w7
+#pragma unroll
+        for (int k = 1; k < 8; ++k) n += ((y.w[k] & 0xffffu) < r ? 1u : 0u) + ((y.w[k] >> 16) < r ? 1u : 0u);
+        return n;
+    }
+    const uint32_t b = r % OCC_BITS_PER_REC;
 #pragma unroll
     for (int k = 0; k < 7; ++k) n += popc32(y.w[1 + k] & low_mask_clamped((int)b - 32 * k));
     return n;
@@ -178,7 +184,7 @@ FMGPU_HD uint32_t rank_single(const DevIndex& ix, const SmemTables& T, uint32_t 
         *out = cell.value + r;
         return 0u;
     }
-    if (kind != CELL_OCC_LIST && kind != CELL_OCC_BITS) return 9u;  // THROW
+    if (kind < CELL_OCC_FIRST) return 9u;  // THROW
     const Rec32 y = FMGPU_LD256(occ_record(ix, cell, kind, r));
     ++*n_rec;
     uint32_t len = 0;

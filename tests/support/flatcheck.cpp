@@ -114,49 +114,33 @@ void fc_cell_kinds(void* hv, uint64_t* out6) {
     for (const Rec32& b : h->F.blocks) out6[5] += b.w[1] & 1u;
 }
 
-// design aid: what the bit-vector cells would cost as position lists over fixed position ranges (record q = the occurrences
-// inside [q R, (q + 1) R), at most 14 per record).  out: [0] bit-vector cells, [1] their records, [2] records under the policy
-// "cheapest eligible of R = 4096, 1024, 256, else bits", [3..6] cells that end up as R = 4096 / 1024 / 256 / bits
-void fc_occ_census(void* hv, uint64_t* out) {
+// (block, symbol) cells by kind (CellKind 0..7)
+void fc_cell_kinds8(void* hv, uint64_t* out8) {
     FC* h = (FC*)hv;
-    for (int i = 0; i < 8; ++i) out[i] = 0;
+    for (int i = 0; i < 8; ++i) out8[i] = 0;
+    for (const Cell8& c : h->F.cells) out8[cell_kind(c) & 7u]++;
+}
+
+// up to `max` (block, symbol) cells of one kind: out[4 i ..] = {symbol, first text row of the block, block size, 0}
+uint32_t fc_find_cells(void* hv, uint32_t kind, uint32_t max, uint32_t* out) {
+    FC* h = (FC*)hv;
     const uint32_t sigma = h->ix.sigma;
     const size_t n_blocks = h->F.cells.size() / sigma;
-    for (uint32_t sb = 0; sb < h->ix.n_sb; ++sb) {
+    uint32_t n = 0;
+    for (uint32_t sb = 0; sb < h->ix.n_sb && n < max; ++sb) {
         const SbDesc sd = h->F.sb[sb];
         const size_t first = sd.first_block, last = sb + 1 < h->ix.n_sb ? h->F.sb[sb + 1].first_block : n_blocks;
-        const uint32_t bsize = 1u << sd.block_log;
-        for (size_t b = first; b < last; ++b)
-            for (uint32_t c = 0; c < sigma; ++c) {
-                const Cell8& cell = h->F.cells[b * sigma + c];
-                if (cell_kind(cell) != CELL_OCC_BITS) continue;
-                const uint32_t nrec = bsize / OCC_BITS_PER_REC + 1;
-                ++out[0];
-                out[1] += nrec;
-                uint32_t best = nrec, which = 3;
-                const uint32_t Rs[3] = {4096, 1024, 256};
-                for (int k = 0; k < 3; ++k) {
-                    const uint32_t R = Rs[k];
-                    if (R >= bsize * 2) continue;
-                    const uint32_t need = (bsize + R - 1) / R;
-                    if (need >= best) continue;
-                    bool ok = true;
-                    uint32_t cnt = 0, cur = 0;
-                    for (uint32_t q = 0; q < nrec && ok; ++q) {
-                        const Rec32& Rr = h->F.occ[(cell.info & CELL_PTR_MASK) + q];
-                        for (uint32_t bit = 0; bit < OCC_BITS_PER_REC; ++bit)
-                            if ((Rr.w[1 + (bit >> 5)] >> (bit & 31u)) & 1u) {
-                                const uint32_t pos = q * OCC_BITS_PER_REC + bit;
-                                if (pos / R != cur) { cur = pos / R; cnt = 0; }
-                                if (++cnt > 14) { ok = false; break; }
-                            }
-                    }
-                    if (ok) { best = need; which = (uint32_t)k; break; }
+        for (size_t b = first; b < last && n < max; ++b)
+            for (uint32_t c = 0; c < sigma && n < max; ++c)
+                if (cell_kind(h->F.cells[b * sigma + c]) == kind) {
+                    out[4 * n] = c;
+                    out[4 * n + 1] = (sb << SB_LOG) + (uint32_t)((b - first) << sd.block_log);
+                    out[4 * n + 2] = 1u << sd.block_log;
+                    out[4 * n + 3] = 0;
+                    ++n;
                 }
-                out[2] += best;
-                ++out[3 + which];
-            }
     }
+    return n;
 }
 
 int fc_rank(void* h, uint32_t pos, uint32_t sym, int64_t* out) {

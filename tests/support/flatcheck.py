@@ -40,6 +40,9 @@ def lib():
         L.fc_build_start_table.argtypes = [vp, u32]
         L.fc_build_start_table.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
+        L.fc_cell_kinds8.argtypes = [vp, vp]
+        L.fc_find_cells.argtypes = [vp, u32, u32, vp]
+        L.fc_find_cells.restype = C.c_uint32
         L.fc_dense_build.argtypes = [vp, u32, vp, vp]
         L.fc_dense_build.restype = C.c_int64
         L.fc_locate_rows_dense.argtypes = [vp, vp, vp, vp, u32, vp]
@@ -73,6 +76,18 @@ class FlatIndexHost:
         out = np.zeros(8, dtype=np.uint64)
         lib().fc_sizes(self._h, out.ctypes.data)
         return out
+
+    def cell_kinds(self):
+        """(block, symbol) cells by kind: [normal, const, run, throw, range-1K, list, bits, range-4K]"""
+        out = np.zeros(8, dtype=np.uint64)
+        lib().fc_cell_kinds8(self._h, out.ctypes.data)
+        return [int(x) for x in out]
+
+    def find_cells(self, kind: int, max_cells: int = 8):
+        """-> [(symbol, first row of the block, block size)] of up to max_cells cells of one CellKind"""
+        out = np.zeros(4 * max_cells, dtype=np.uint32)
+        n = lib().fc_find_cells(self._h, kind, max_cells, out.ctypes.data)
+        return [(int(out[4 * i]), int(out[4 * i + 1]), int(out[4 * i + 2])) for i in range(n)]
 
     def rank(self, pos, sym):
         out = C.c_int64()

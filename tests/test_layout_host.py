@@ -91,9 +91,13 @@ def test_count_and_locate_lanes(flats, name):
 
 @pytest.mark.parametrize("name", ALL_CASES)
 def test_occurrence_cells_cover_all_forms(flats, name):
-    """rank through the (block, symbol) occurrence structures (inline positions / sorted position list / bit vector, layout.h) at
-    EVERY position of a few blocks and for every symbol of the alphabet — all three forms and their record boundaries."""
+    """rank through the (block, symbol) occurrence structures (short position list / range lists / bit vector, layout.h) at
+    EVERY position of a few blocks and for every symbol of the alphabet — all forms and their record boundaries."""
     case, f = get_case(name), flats(name)
+    kinds = f.cell_kinds()  # [normal, const, run, throw, range-1K, list, bits, range-4K]
+    assert kinds[0] == 0 and kinds[5] > 0 and kinds[6] > 0
+    if name in ("log1m_sr32", "log3m_sr16", "multi400k_sr8"):
+        assert kinds[4] > 0 and kinds[7] > 0
     L = case.oracle.getInputLength()
     sigma = case.oracle.getAlphabetLength() + 1
     rng = np.random.default_rng(8)
@@ -293,3 +297,20 @@ def test_dense_samples_locate_lanes(flats, name):
     got, steps = f.locate_rows_dense(marks, dsa, rows)
     assert np.array_equal(got, want)
     assert steps < int(f.counters[2])
+
+
+@pytest.mark.parametrize("name", ["log1m_sr32", "log3m_sr16", "multi400k_sr8", "tiny600k_sr4"])
+def test_every_occurrence_form_over_whole_blocks(flats, name):
+    """For a few (block, symbol) cells of EVERY occurrence form (position list, range lists over 1024 / 4096 positions, bit
+    vector): rank at every record boundary of the block and at a stride of positions in between, against the oracle."""
+    case, f = get_case(name), flats(name)
+    L = case.oracle.getInputLength()
+    for kind in (4, 5, 6, 7):
+        for sym, row0, bsize in f.find_cells(kind, 4):
+            ps = set(range(row0, min(L, row0 + bsize) + 1, 37))
+            for step in (224, 1024, 4096):
+                for q in range(row0, min(L, row0 + bsize) + 1, step):
+                    ps.update(p for p in (q - 1, q, q + 1) if row0 <= p <= min(L, row0 + bsize))
+            for p in sorted(ps):
+                got_st, got = f.rank(p, sym)
+                assert got_st == 0 and got == case.oracle.wfbb_rank(p, sym), (kind, sym, row0, bsize, p)
