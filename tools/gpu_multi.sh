@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, multi-GPU: bash tools/gpu_multi_r2.sh <tag> <N>   (under gpurun --gpus N)
+# round 2, multi-GPU: bash tools/gpu_multi.sh <tag> <N>   (under gpurun --gpus N)
 TAG=${1:-r2m}; N=${2:-2}
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -6 > gpurun_out/${TAG}_n${N}_pytest.txt; tail -3 gpurun_out/${TAG}_n${N}_pytest.txt

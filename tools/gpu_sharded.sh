@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, sharded index (BASELINE.json configs[4]): bash tools/gpu_sharded_r2.sh <tag> <N> <shard_chars> <n_pat>   (under gpurun --gpus N)
+# round 2, sharded index (BASELINE.json configs[4]): bash tools/gpu_sharded.sh <tag> <N> <shard_chars> <n_pat>   (under gpurun --gpus N)
 TAG=${1:-r2s}; N=${2:-2}; S=${3:-16777216}; NP=${4:-20000}
 mkdir -p gpurun_out
 free -g | head -2; nproc
