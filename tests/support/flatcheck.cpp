@@ -12,6 +12,7 @@
 #include "../../index4j_b200/csrc/count_lane.h"
 #include "../../index4j_b200/csrc/lf_lane.h"
 #include "../../index4j_b200/csrc/utf8_lane.h"
+#include "../../index4j_b200/csrc/host_pack.hpp"
 
 using namespace fmgpu;
 
@@ -759,4 +760,22 @@ extern "C" void fc_sparse_sim(void* hv, const uint16_t* chars, const uint64_t* p
             ep = h.ix.C[c] + b;
         }
     }
+}
+
+// Packed transport of the host-pointer count call (host_pack.hpp), host half: the pool narrows n_groups chunks of a char[] into
+// bytes exactly as count_host_enqueue submits them (parts_per_group parts per chunk).  wide_out[g] = OR of the chunk's chars.
+extern "C" int32_t fc_pack_threads(void) { return (int32_t)fmgpu_host::PackPool::get().threads(); }
+extern "C" void fc_pack_narrow(const uint16_t* chars, uint64_t n, uint32_t n_groups, uint32_t parts, uint8_t* bytes_out, uint32_t* wide_out) {
+    std::vector<std::atomic<uint32_t>> wide(n_groups);
+    for (auto& w : wide) w.store(0);
+    std::atomic<uint32_t>* wp = wide.data();
+    auto job = fmgpu_host::PackPool::get().submit(n_groups, parts, [=](uint32_t g, uint32_t part) {
+        const uint64_t c0 = n * g / n_groups, c1 = n * (g + 1) / n_groups;
+        const uint64_t a = c0 + (c1 - c0) * part / parts, b = c0 + (c1 - c0) * (part + 1) / parts;
+        const uint32_t m = fmgpu_host::narrow_u16(chars + a, bytes_out + a, (size_t)(b - a));
+        wp[g].fetch_or(m);
+    });
+    for (uint32_t g = 0; g < n_groups; ++g) job->wait_group(g);  // in order, as the uploader does
+    job->wait_all();
+    for (uint32_t g = 0; g < n_groups; ++g) wide_out[g] = wide[g].load();
 }

@@ -15,7 +15,7 @@ _lib = None
 
 def build(force=False):
     srcs = [os.path.join(HERE, "flatcheck.cpp")] + [
-        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "lf_lane.h", "ldrec.h", "layout.h", "count_lane.h", "utf8_lane.h")
+        os.path.join(ROOT, "index4j_b200", "csrc", f) for f in ("flatten.hpp", "jstream.hpp", "walk_lane.h", "lane_logic.h", "lf_lane.h", "ldrec.h", "layout.h", "count_lane.h", "utf8_lane.h", "host_pack.hpp")
     ]
     if force or not os.path.exists(LIB) or any(os.path.getmtime(s) > os.path.getmtime(LIB) for s in srcs):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-Wno-unknown-pragmas",
@@ -41,6 +41,8 @@ def lib():
         L.fc_build_start_table.restype = C.c_uint64
         L.fc_locate_rows.argtypes = [vp, vp, u32, vp]
         L.fc_cell_kinds8.argtypes = [vp, vp]
+        L.fc_pack_threads.restype = i32
+        L.fc_pack_narrow.argtypes = [vp, u64, u32, u32, vp, vp]
         L.fc_find_cells.argtypes = [vp, u32, u32, vp]
         L.fc_find_cells.restype = C.c_uint32
         L.fc_dense_build.argtypes = [vp, u32, vp, vp]
@@ -199,3 +201,12 @@ def utf8_convert(data: bytes):
     if n < 0:
         return None, int(-n), int(val.value)
     return out[:n].copy(), 0, 0
+
+
+def pack_narrow(chars: np.ndarray, n_groups: int, parts: int):
+    """host_pack.hpp: the pack pool narrows `chars` (uint16) to bytes in n_groups chunks -> (bytes uint8[n], OR of each chunk's chars)"""
+    chars = np.ascontiguousarray(chars, dtype=np.uint16) if chars.dtype != np.uint16 else chars
+    out = np.zeros(chars.size, dtype=np.uint8)
+    wide = np.zeros(n_groups, dtype=np.uint32)
+    lib().fc_pack_narrow(chars.ctypes.data, chars.size, n_groups, parts, out.ctypes.data, wide.ctypes.data)
+    return out, wide
