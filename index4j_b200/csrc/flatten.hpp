@@ -143,8 +143,8 @@ struct VarReader {
 };
 
 // occurrence records a (block, symbol) pair with `occ` occurrences in a block of `block_size` positions needs (layout.h):
-// one list record while its positions fit one, else one bit per position
-inline uint32_t occ_kind(uint32_t occ, uint32_t) { return occ <= fmgpu::OCC_LIST_MAX ? fmgpu::CELL_OCC_LIST : fmgpu::CELL_OCC_BITS; }
+// one list record while its positions fit one, else (upper bound for the sizing pass) one bit per position
+inline uint32_t occ_kind(uint32_t occ, uint32_t) { return occ <= fmgpu::OCC_RANGE_MAX ? fmgpu::CELL_OCC_LIST : fmgpu::CELL_OCC_BITS; }
 inline uint32_t occ_records(uint32_t occ, uint32_t block_size) {
     return occ_kind(occ, block_size) == fmgpu::CELL_OCC_LIST ? 1u : block_size / fmgpu::OCC_BITS_PER_REC + 1;
 }
@@ -318,10 +318,12 @@ inline uint32_t put_occ(fmgpu::Cell8& cell, const std::vector<uint16_t>& pos, ui
         uint32_t& w = R.w[k >> 1];
         w = (k & 1u) ? ((w & 0x0000ffffu) | (v << 16)) : ((w & 0xffff0000u) | v);
     };
-    if (kind == fmgpu::CELL_OCC_LIST) {
+    if (kind == fmgpu::CELL_OCC_LIST) {  // one record for the whole block
         cell.info = (kind << fmgpu::CELL_KIND_SHIFT) | at;
-        Rec32& R = occ[(size_t)at];
-        for (uint32_t k = 0; k < 16; ++k) put16(R, k, k < fmgpu::OCC_LIST_MAX ? (k < n ? pos[k] : 0xffffu) : (code_len & 0xffffu));
+        Rec32& X = occ[(size_t)at];
+        memset(&X, 0xff, sizeof X);
+        X.w[0] = (code_len & 0xffu) << 24;
+        for (uint32_t k = 0; k < n; ++k) put16(X, 2 + k, pos[k]);
         return 1;
     }
     // position lists over fixed ranges where no range holds more than 14 occurrences: the largest range that qualifies

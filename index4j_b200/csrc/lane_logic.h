@@ -70,7 +70,7 @@ FMGPU_HD uint32_t count_u16_below(const Rec32& x, int first, int n_words, uint32
 FMGPU_HD uint32_t cell_kind(const Cell8& c) { return c.info >> CELL_KIND_SHIFT; }
 // the ONE record an OCC_* cell needs for position r of its block
 FMGPU_HD const Rec32* occ_record(const DevIndex& ix, const Cell8& cell, uint32_t kind, uint32_t r) {
-    const uint32_t q = kind == CELL_OCC_BITS ? r / OCC_BITS_PER_REC : (kind == CELL_OCC_R1K ? r >> 10 : (kind == CELL_OCC_R4K ? r >> 12 : 0u));
+    const uint32_t q = kind == CELL_OCC_BITS ? r / OCC_BITS_PER_REC : r >> ((uint32_t)(OCC_RANGE_SHIFTS >> (8u * kind)) & 31u);
     return ix.occ + ((cell.info & CELL_PTR_MASK) + q);
 }
 
@@ -105,17 +105,9 @@ FMGPU_HD uint32_t dlevel_rank(const Rec32& x, uint32_t b, uint32_t t, uint32_t u
 // occurrences of the symbol among the first r positions of the block, from the record occ_record pointed at (y);
 // *len (work counters) = the symbol's code length in the block's tree
 FMGPU_HD uint32_t occ_in_record(const Rec32& y, uint32_t kind, uint32_t r, uint32_t* len) {
-    if (kind == CELL_OCC_LIST) {
-        *len = y.w[7] >> 16;
-        // slot 15 (the code length, < 64) is never counted: it would need r > length, and r <= 65535 excludes the padding
-        uint32_t n = 0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) n += ((y.w[k] & 0xffffu) < r ? 1u : 0u) + ((k < 7 && (y.w[k] >> 16) < r) ? 1u : 0u);
-        return n;
-    }
     *len = y.w[0] >> 24;
     uint32_t n = y.w[0] & 0xffffffu;
-    if (kind != CELL_OCC_BITS) {  // range list: 14 positions in w1..w7
+    if (kind != CELL_OCC_BITS) {  // position list: 14 u16 slots in w1..w7 (padding 0xffff is never below r <= 65535)
 #pragma unroll
         for (int k = 1; k < 8; ++k) n += ((y.w[k] & 0xffffu) < r ? 1u : 0u) + ((y.w[k] >> 16) < r ? 1u : 0u);
         return n;

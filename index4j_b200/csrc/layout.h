@@ -28,15 +28,15 @@ struct alignas(32) Rec32 {
 //                   symbol's code (:1185-1279), one RRR rank per level, which counts the occurrences of the symbol among the
 //                   first r positions of the block.  That count is stored directly, per (block, symbol), so a rank is the cell
 //                   plus EXACTLY ONE record, whatever the code length:
-//           OCC_LIST  <= 15 occurrences: ONE record with their positions (u16, ascending, padded 0xffff) in slots 0..14;
-//                     slot 15 = the symbol's code length (what the reference's walk costs: work counters only)
-//           OCC_BITS  a bit vector over the block's positions: record q covers positions [224 q, 224 q + 224): w0 = occurrences
-//                     before the record (low 24 bits) | code length << 24, w1..w7 = 224 bits
-//           OCC_R1K / OCC_R4K  position lists over fixed position RANGES, for symbols that are neither rare nor frequent in a
-//                     large block (typical of large alphabets): record q holds the occurrences inside [q R, (q + 1) R), R = 1024
-//                     / 4096 — at most 14 per range, else the pair gets a bit vector: w0 as above, w1..w7 = up to 14 u16
-//                     positions (ascending, padded 0xffff).  B / R records instead of B / 224 (a 456-symbol multi-script
-//                     text: 3.2 x fewer occurrence records; 4 % fewer for log text)
+//           every record: w0 = occurrences before the record (low 24 bits) | the symbol's code length << 24 (what the
+//                     reference's walk costs: work counters only)
+//           OCC_BITS  a bit vector over the block's positions: record q covers positions [224 q, 224 q + 224), w1..w7 = 224 bits
+//           OCC_LIST / OCC_R4K / OCC_R1K  position lists over fixed position RANGES: record q holds the occurrences inside
+//                     [q R, (q + 1) R) — at most 14 per range — as u16 positions (ascending, padded 0xffff) in w1..w7.
+//                     OCC_LIST: R = 65536 = the whole block, i.e. ONE record for a symbol with <= 14 occurrences; R = 4096 /
+//                     1024 for symbols that are neither rare nor frequent in a large block (typical of large alphabets):
+//                     B / R records instead of B / 224 (a 456-symbol multi-script text: 3.2 x fewer occurrence records;
+//                     1.3 % fewer for log text).  A pair with more than 14 occurrences in some 1024-range gets a bit vector.
 // The table is dense, cells[block][symbol]: 8 bytes per pair keep it L2-resident for log alphabets (30 MB per 2^30 chars at 70
 // symbols; it was 32 bytes per pair — 120 MB, which the 126 MB L2 did not hold beside the records: ncu showed the cell loads
 // stalling as long as the DRAM-bound record loads — with in-cell position lists / list splitters that < 1 % of the queries used).
@@ -49,10 +49,11 @@ struct alignas(8) Cell8 {
 };
 enum CellKind : uint32_t { CELL_NORMAL = 0, CELL_CONST = 1, CELL_RUN = 2, CELL_THROW = 3, CELL_OCC_R1K = 4, CELL_OCC_LIST = 5, CELL_OCC_BITS = 6, CELL_OCC_R4K = 7 };
 constexpr uint32_t CELL_OCC_FIRST = CELL_OCC_R1K;  // kinds >= this one need their one occurrence record
-constexpr uint32_t OCC_RANGE_MAX = 14;      // positions of a range-list record
+constexpr uint32_t OCC_RANGE_MAX = 14;      // positions of a list record
+// log2 of the position range a list record covers, by kind (OCC_R1K = 4: 10, OCC_LIST = 5: 16, OCC_R4K = 7: 12)
+constexpr unsigned long long OCC_RANGE_SHIFTS = (10ull << (8 * 4)) | (16ull << (8 * 5)) | (12ull << (8 * 7));
 constexpr uint32_t CELL_KIND_SHIFT = 29;
 constexpr uint32_t CELL_PTR_MASK = (1u << CELL_KIND_SHIFT) - 1u;
-constexpr uint32_t OCC_LIST_MAX = 15;        // positions of a list record (slot 15 holds the code length)
 constexpr uint32_t OCC_BITS_PER_REC = 224;   // positions per bit-vector record
 
 // --- level record (32 bytes): TWO tree levels of 96 positions.  Only the wavelet-tree nodes at EVEN depth own records;
