@@ -696,8 +696,22 @@ int replica_setup(Replica* rp) {
         const size_t cap = (size_t)prop.persistingL2CacheMaxSize / (want_mb > 0 ? 1 : 2);
         if (set_aside > cap) set_aside = cap;
         rp->l2_window_bytes = 0;
-        if (want_mb != 0 && cells > 0 && set_aside > 0 && prop.accessPolicyMaxWindowSize > 0 &&
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
+        // the set-aside is one per device and process: it only grows (a small index loaded after a large one must not take
+        // the large one's L2 away)
+        static std::mutex l2_mu;
+        static size_t l2_set_aside[64] = {0};
+        bool reserved = false;
+        if (want_mb != 0 && cells > 0 && set_aside > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            std::lock_guard<std::mutex> lk(l2_mu);
+            size_t& cur = l2_set_aside[rp->device & 63];
+            if (set_aside <= cur) {
+                reserved = true;
+            } else if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside) == cudaSuccess) {
+                cur = set_aside;
+                reserved = true;
+            }
+        }
+        if (reserved) {
             rp->l2_window_bytes = cells < (size_t)prop.accessPolicyMaxWindowSize ? cells : (size_t)prop.accessPolicyMaxWindowSize;
             const double r = (double)set_aside / 1.25 / (double)rp->l2_window_bytes;
             rp->l2_hit_ratio = r >= 1.0 ? 1.0f : (float)r;
