@@ -679,7 +679,6 @@ def main():
                          "ranks_per_launch": stats["ranks"], "levels_per_launch": stats["rank_levels"],
                          "level_records_per_launch": stats["level_records"],
                          "records_loaded_per_launch": stats["search_records_loaded"],
-                         "spec_root_loads_wasted_per_launch": stats.get("spec_root_wasted", 0),
                          "records_per_rank": (stats["ranks"] + stats["level_records"]) / max(1, stats["ranks"]),
                          "ranks_per_s": stats["ranks"] / (kern_ms / 1e3),
                          "occurrence_records_per_launch": stats["level_records"]},

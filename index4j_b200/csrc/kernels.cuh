@@ -1,8 +1,8 @@
 // sm_100a kernels of the FM-index query path (hand-written; no library calls on the hot path).
 //
-// Execution model.  Every memory access of the query path is ONE 32-byte record =
-// one DRAM sector, fetched with a single 256-bit load (LDG.E.256); a record carries everything the
-// operation needs from that address.  Backward search (FmIndex.count, fm/FmIndex.java:455-474) runs
+// Execution model.  Every memory access of the query path is ONE self-contained record — an 8-byte
+// (block, symbol) cell or a 32-byte record = one DRAM sector, fetched with a single 256-bit load (LDG.E.256); a record
+// carries everything the operation needs from that address.  Backward search (FmIndex.count, fm/FmIndex.java:455-474) runs
 // warp-lockstep: the batch is ordered by pattern length (k_prepass / k_len_scan / k_len_scatter), a
 // warp takes 32 patterns of equal length, lane = pattern, and every lane executes count_step
 // (count_lane.h) once per pattern char.  Work is taken from a global queue, one atomic per warp batch.
@@ -155,10 +155,9 @@ __global__ void __launch_bounds__(256, 8) k_len_scatter(const PatDesc* __restric
 //
 // A warp takes 32 patterns of equal length from the length-ordered batch; lane = pattern.  All lanes perform step k of
 // their pattern together; what a lane does in a step is count_step (count_lane.h): the two rank queries rank(start, c) and
-// rank(end, c) as two tracks of one fused walk, cells and speculative root records issued together.  The code is plain
-// SIMT loops — the hardware reconverges the warp after each level — which costs ~5x fewer issued instructions per rank
-// than the lane state machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...); the price is that a step
-// lasts as long as its deepest walk.
+// rank(end, c) as two tracks of one fused step — the 8-byte cells first, then at most one occurrence record per track.  The
+// code is plain SIMT — the hardware reconverges the warp after each step — which costs ~5x fewer issued instructions per rank
+// than the lane state machines of v1/v2 (profiles/r01_k_count_v1_ncu_summary.txt, ..._v2_...).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ CountTables stage_count_tables(const DevIndex& ix, uint32_t* smem) { return stage_tables(ix, smem); }
 constexpr size_t COUNT_SMEM_MAX_BYTES = TABLES_SMEM_MAX_BYTES;
