@@ -293,8 +293,8 @@ int fmgpu_last_stats(fmgpu_index* idx, uint64_t out8[8]);
 int fmgpu_set_stats(fmgpu_index* idx, int enable);
 /* Same, all FMGPU_N_STATS counters (n_out >= FMGPU_N_STATS):
  * [8 + k] rank queries of the backward-search kernel whose (block, symbol) cell had kind k: 1 = CONST (symbol absent: the
- *     cell is the answer), 2 = RUN (single-symbol block), 3 = THROW, 4 = positions inline in the cell, 5 = sorted position
- *     list, 6 = bit vector; kinds 5 and 6 fetch one record. */
+ *     cell is the answer), 2 = RUN (single-symbol block), 3 = THROW, 5 = position list (<= 14 occurrences), 4 / 7 = position
+ *     lists over 1024- / 4096-position ranges, 6 = bit vector; kinds 4-7 fetch one record. */
 #define FMGPU_N_STATS 16
 int fmgpu_last_stats_ex(fmgpu_index* idx, uint64_t* out, uint32_t n_out);
 

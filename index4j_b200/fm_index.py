@@ -259,8 +259,8 @@ class FmIndex:
         out = np.zeros(16, dtype=np.uint64)
         self._check(self._lib.fmgpu_last_stats_ex(self._h, out.ctypes.data, out.size))
         names = ["ranks", "rank_levels", "lf_steps", "lf_levels", "sampled_tests", "launches", "search_records_loaded", "level_records",
-                 "kind0", "rank_cells_const", "rank_cells_run", "rank_cells_throw", "rank_cells_inline", "rank_cells_list", "rank_cells_bits",
-                 "kind7"]
+                 "kind0", "rank_cells_const", "rank_cells_run", "rank_cells_throw", "rank_cells_range1k", "rank_cells_list", "rank_cells_bits",
+                 "rank_cells_range4k"]
         return {k: int(v) for k, v in zip(names, out)}
 
     def set_stats(self, enable: bool = True):
