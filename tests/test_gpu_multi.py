@@ -56,6 +56,35 @@ def test_concurrent_callers_of_one_handle(gpu_indexes):
     assert not errors, errors
 
 
+def test_concurrent_callers_with_the_packed_transport(gpu_indexes, monkeypatch):
+    """The same with every count call forced through the packed transport (host_pack.hpp) in several chunks: the callers' pack
+    jobs queue up in one pool, each call stages into its own context's pinned buffer."""
+    case, g = get_case("log1m_sr32"), gpu_indexes("log1m_sr32")
+    monkeypatch.setenv("FMGPU_HOST_PACK_MIN", "1")
+    monkeypatch.setenv("FMGPU_PIPE_CHUNK", "1500")
+    work = []
+    for t in range(6):
+        chars, off = make_patterns(case.text, 9000 + 700 * t, 1, 60, seed=200 + t)
+        work.append((chars, off, case.oracle.count_batch(chars, off, threads=2)))
+    errors = []
+
+    def run(t):
+        try:
+            chars, off, (want, want_st) = work[t]
+            for _ in range(8):
+                got, st = g.count_batch(chars, off, return_status=True)
+                assert np.array_equal(got, want) and np.array_equal(st, want_st)
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
 def test_device_calls_on_two_streams(gpu_indexes):
     """*_device calls return before their work has finished; two of them on different streams may end up sharing the handle's
     internal scratch buffers and must still both be right (the library orders such calls with events)."""
