@@ -191,7 +191,9 @@ int fmgpu_extract_batch_device(fmgpu_index* idx, const int32_t* d_start, const i
  * destination.length, FM:662) and `offset` enters the "does not fit" test and its N (FM:732-737, :817-821, :894-898) but not
  * the returned length; a left part that does not fit behind `offset` makes System.arraycopy throw (FM:688-690): status
  * FMGPU_ST_INDEX_OOB.  len_out[i] = returned length (or N of the "does not fit" message when status is
- * FMGPU_ST_DOES_NOT_FIT).  Only arena[i*dst_len + offset, +len) is defined, like the Java array beyond the returned length. */
+ * FMGPU_ST_DOES_NOT_FIT).  Only arena[i*dst_len + offset, +len) is defined, like the Java array beyond the returned length.
+ * (from == getInputLength() - 1, the terminator's own position: the reference's end-of-text rule, FM:745-752, returns a length
+ * one beyond the chars it wrote; that last slot keeps what the destination held, in Java and here.) */
 int fmgpu_extract_until_boundary_batch(fmgpu_index* idx, const int32_t* from, uint32_t n, uint16_t boundary, int32_t dst_len,
                                        int32_t offset, int32_t mode, uint16_t* arena, int32_t* len_out, int32_t* status_out);
 int fmgpu_extract_until_boundary_batch_device(fmgpu_index* idx, const int32_t* d_from, uint32_t n, uint16_t boundary,

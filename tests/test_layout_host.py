@@ -314,3 +314,32 @@ def test_every_occurrence_form_over_whole_blocks(flats, name):
             for p in sorted(ps):
                 got_st, got = f.rank(p, sym)
                 assert got_st == 0 and got == case.oracle.wfbb_rank(p, sym), (kind, sym, row0, bsize, p)
+
+
+@pytest.mark.parametrize("sr", [2, 4, 32])
+def test_extract_until_boundary_exhaustive_on_small_texts(sr):
+    """extractUntilBoundary{,Left,Right} from EVERY position (and just outside the text) of small multi-line texts, for every
+    destination length 1..26 and offsets 0..4: status, returned length / N of "does not fit", contents — the reference's 4-char
+    chunk arithmetic incl. its end-of-text rule (quirks Q5 / Q6), which the lanes evaluate in closed form (eub_right_chunks)."""
+    import pyoracle
+    from index4j_b200.builder import build_index
+    texts = ["ab\ncde\n\nfghij\nk", "\n\nxy\nabcdefghijklmnopqrstuvw\nz\n", "no boundary at all in this one", "a\nbb\nccc\ndddd\neeeee\nffffff\nggggggg\nhhhhhhhh"]
+    for t in texts:
+        text = np.frombuffer(t.encode("utf-16-le"), dtype=np.uint16)
+        blob = build_index(text, sr)
+        f, o = flatcheck.FlatIndexHost(blob), pyoracle.OracleFmIndex(blob)
+        n = text.size
+        frm = np.arange(-1, n + 2, dtype=np.int32)
+        for boundary in (10, ord("z") + 1):  # '\n', and a char that is not in the alphabet ("Boundary does not exist")
+            for mode in (0, 1, 2):
+                for dst_len in list(range(0, 27)) + [64]:
+                    for offset in range(0, 5):
+                        a1, l1, s1 = o.extract_until_boundary_batch(frm, boundary, dst_len, mode, threads=1, offset=offset)
+                        a2, l2, s2 = f.eub(frm, boundary, dst_len, mode, offset=offset)
+                        assert np.array_equal(s1, s2), (t, mode, dst_len, offset, frm[s1 != s2][:5], s1[s1 != s2][:5], s2[s1 != s2][:5])
+                        ok = (s1 == 0) | (s1 == 8)
+                        assert np.array_equal(l1[ok], l2[ok]), (t, mode, dst_len, offset, frm[ok][l1[ok] != l2[ok]][:5])
+                        for i in np.flatnonzero(s1 == 0):
+                            if frm[i] >= n:  # the terminator's own position: the reference returns a length that covers a
+                                continue     # slot it never writes (end-of-text rule) — only status and length are defined
+                            assert np.array_equal(a1[i, offset: offset + l1[i]], a2[i, offset: offset + l1[i]]), (t, mode, dst_len, offset, int(frm[i]))
