@@ -343,3 +343,34 @@ def test_extract_until_boundary_exhaustive_on_small_texts(sr):
                             if frm[i] >= n:  # the terminator's own position: the reference returns a length that covers a
                                 continue     # slot it never writes (end-of-text rule) — only status and length are defined
                             assert np.array_equal(a1[i, offset: offset + l1[i]], a2[i, offset: offset + l1[i]]), (t, mode, dst_len, offset, int(frm[i]))
+
+
+@pytest.mark.parametrize("sr", [1, 3, 32])
+def test_count_and_locate_exhaustive_on_small_texts(sr):
+    """Every substring (up to 7 chars) of small texts, plus every 1- and 2-char string over the alphabet + an unknown char: count and
+    the located position sets through the lane code, against the oracle and a naive scan."""
+    import pyoracle
+    from index4j_b200.builder import build_index
+    texts = ["abracadabra abracadabra\nabra", "aaaaaaaaaaaaaaaaaaaaaaaaaaaaaaab", "\n\n\n", "the quick brown fox\njumps over the lazy dog\nthe end"]
+    for t in texts:
+        text = np.frombuffer(t.encode("utf-16-le"), dtype=np.uint16)
+        blob = build_index(text, sr)
+        f, o = flatcheck.FlatIndexHost(blob), pyoracle.OracleFmIndex(blob)
+        pats = {t[i: i + k] for i in range(len(t)) for k in range(1, 8) if i + k <= len(t)}
+        alpha = sorted(set(t)) + ["中"]
+        pats |= {a for a in alpha} | {a + b for a in alpha for b in alpha}
+        pats = sorted(pats)
+        arrs = [np.frombuffer(p.encode("utf-16-le"), dtype=np.uint16) for p in pats]
+        off = np.zeros(len(arrs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([a.size for a in arrs])
+        chars = np.concatenate(arrs)
+        want, want_st = o.count_batch(chars, off, threads=1)
+        got, got_st, ranges = f.count_batch(chars, off)
+        assert np.array_equal(got_st, want_st) and np.array_equal(got, want)
+        for i, p in enumerate(pats):
+            naive = sum(1 for j in range(len(t) - len(p) + 1) if t[j: j + len(p)] == p)
+            assert got[i] == naive, (t, p)
+            rows = np.arange(int(ranges[i, 0]), int(ranges[i, 0]) + int(got[i]), dtype=np.uint32)
+            if rows.size:
+                pos = f.locate_rows(rows)
+                assert sorted(pos.tolist()) == [j for j in range(len(t) - len(p) + 1) if t[j: j + len(p)] == p], (t, p)
