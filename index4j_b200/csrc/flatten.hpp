@@ -19,31 +19,42 @@ namespace fmgpu_host {
 
 using fmgpu::Rec32;
 
-// (class, offset) -> 15-bit block, generated from the ordering rule of the reference's literal
-// tables (RrrVector.java:8692-8698, :8705-16899): classes by popcount; inside a class by
-// descending value of the block read LSB-first.
+// (class, offset) -> 15-bit block.  The reference ships these tables as literals (RrrVector.java:8692-8698, :8705-16899); here
+// they are computed by combinatorial unranking: class k = blocks with k ones, C(15, k) of them; inside a class the blocks are
+// in descending order of their value read LSB-first, so offset `off` of class k is found bit by bit — bit j (the j-th position
+// of the block) is set iff off < C(14 - j, ones still to place - 1), else off skips those C(..) blocks.  (The oracle enumerates
+// bit-reversed values instead; tests pin both against the sha256 of the Java literal.)
 struct RrrTables {
     uint16_t inverse[32768];
     uint16_t class_base[16];
     uint8_t bits_needed[16];  // RrrVector.java:111-129
     RrrTables() {
-        int cnt[16] = {0};
-        for (int v = 0; v < 32768; ++v) cnt[__builtin_popcount(v)]++;
-        int acc = 0;
+        uint32_t binom[16][16] = {{0}};  // binom[n][k] = C(n, k)
+        for (int n = 0; n < 16; ++n) {
+            binom[n][0] = 1;
+            for (int k = 1; k <= n; ++k) binom[n][k] = binom[n - 1][k - 1] + (k <= n - 1 ? binom[n - 1][k] : 0u);
+        }
+        uint32_t acc = 0;
         for (int k = 0; k < 16; ++k) {
+            const uint32_t members = binom[15][k];
             class_base[k] = (uint16_t)acc;
             int b = 0;
-            while ((1 << b) <= cnt[k]) ++b;
+            while ((1u << b) <= members) ++b;
             bits_needed[k] = (uint8_t)b;
-            acc += cnt[k];
-        }
-        int fill[16] = {0};
-        for (int r = 32767; r >= 0; --r) {
-            int v = 0;
-            for (int b = 0; b < 15; ++b)
-                if (r & (1 << b)) v |= 1 << (14 - b);
-            const int k = __builtin_popcount(v);
-            inverse[class_base[k] + fill[k]++] = (uint16_t)v;
+            for (uint32_t off = 0; off < members; ++off) {
+                uint32_t v = 0, rest = off, ones = (uint32_t)k;
+                for (int j = 0; j < 15 && ones; ++j) {
+                    const uint32_t with_bit = binom[14 - j][ones - 1];  // blocks of this class that have bit j set, given the prefix
+                    if (rest < with_bit) {
+                        v |= 1u << j;
+                        --ones;
+                    } else {
+                        rest -= with_bit;
+                    }
+                }
+                inverse[acc + off] = (uint16_t)v;
+            }
+            acc += members;
         }
     }
 };

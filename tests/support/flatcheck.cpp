@@ -554,6 +554,13 @@ int64_t fc_utf8_convert(const uint8_t* bytes, uint64_t len, uint16_t* out, int32
 }
 
 // all 32768 (class, offset) pairs through the device unranking, in table order
+// the product's own (class, offset) -> block table (flatten.hpp: what the loader decodes with and uploads to the device)
+void fc_product_rrr_table(uint16_t* out32768, uint16_t* class_base16, uint8_t* bits16) {
+    const fmgpu_host::RrrTables& T = fmgpu_host::rrr_tables();
+    std::memcpy(out32768, T.inverse, sizeof T.inverse);
+    std::memcpy(class_base16, T.class_base, sizeof T.class_base);
+    std::memcpy(bits16, T.bits_needed, sizeof T.bits_needed);
+}
 void fc_unrank_table(uint16_t* out32768) {
     uint16_t binom[15 * 16];
     fill_binom(binom);

@@ -54,6 +54,7 @@ def lib():
         L.fc_records.restype = C.c_uint64
         L.fc_sampled.argtypes = [vp, u32, C.POINTER(i32), C.POINTER(i32)]
         L.fc_unrank_table.argtypes = [vp]
+        L.fc_product_rrr_table.argtypes = [vp, vp, vp]
         L.fc_utf8_convert.argtypes = [vp, C.c_uint64, vp, C.POINTER(i32)]
         L.fc_utf8_convert.restype = C.c_int64
         _lib = L
@@ -184,6 +185,13 @@ class FlatIndexHost:
         b, r = C.c_int32(), C.c_int32()
         lib().fc_sampled(self._h, pos, C.byref(b), C.byref(r))
         return b.value, r.value
+
+
+def product_rrr_table():
+    """-> (inverse uint16[32768], class_base uint16[16], bits_needed uint8[16]) of the product's loader (flatten.hpp)"""
+    t, cb, bits = np.zeros(32768, dtype=np.uint16), np.zeros(16, dtype=np.uint16), np.zeros(16, dtype=np.uint8)
+    lib().fc_product_rrr_table(t.ctypes.data, cb.ctypes.data, bits.ctypes.data)
+    return t, cb, bits
 
 
 def unrank_table():

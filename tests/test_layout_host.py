@@ -29,6 +29,17 @@ def test_unranking_reproduces_reference_table():
     assert np.array_equal(flatcheck.unrank_table(), pyoracle.rrr_inverse_table())
 
 
+def test_product_rrr_tables_match_the_java_literals():
+    """The loader's own tables (flatten.hpp, computed by combinatorial unranking; uploaded to the device) against the sha256 of the
+    reference's INVERSE_VALUES literal, its CARDINALITY_OFFSETS (RrrVector.java:8692-8698) and BITS_NEEDED (:111-129)."""
+    import hashlib
+    inv, cbase, bits = flatcheck.product_rrr_table()
+    assert hashlib.sha256(inv.astype("<u2").tobytes()).hexdigest().startswith("314a5a51")
+    assert np.array_equal(inv, pyoracle.rrr_inverse_table())
+    assert cbase.tolist() == [0, 1, 16, 121, 576, 1941, 4944, 9949, 16384, 22819, 27824, 30827, 32192, 32647, 32752, 32767]
+    assert bits.tolist() == [1, 4, 7, 9, 11, 12, 13, 13, 13, 13, 12, 11, 9, 7, 4, 1]
+
+
 @pytest.mark.parametrize("name", ALL_CASES)
 def test_rank_cells_match_oracle(flats, name):
     case, f = get_case(name), flats(name)
